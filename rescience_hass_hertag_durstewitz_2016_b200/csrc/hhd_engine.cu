@@ -1,0 +1,1043 @@
+/*
+ * hhd_engine.cu — sm_100a engine behind the C ABI of include/hhd.h (plan HHD_PLAN_GRAPH: grid-wide kernels).
+ *
+ * One time step = three kernels on the handle's stream, captured STEPS_PER_GRAPH at a time into a CUDA graph:
+ *   k_neuron   one thread per neuron, SoA fp64: finish the previous step (reset `V=V_r; w+=b`, the `w_crossing`
+ *              projection — both need the conductances AFTER that step's deliveries), sample the monitors (Brian's
+ *              `start` slot), integrate the 8 ODEs (euler / rk2 / rk4), evaluate threshold + refractoriness +
+ *              w_crossing, and append spikes to the spike ring with one atomic per warp (ballot compaction).
+ *              Replaces NeuronGroup's stateupdater/thresholder/resetter + StateMonitor + SpikeMonitor
+ *              (codes/CortexNetwork.py:304-311, 487, 510).
+ *   k_stp      one CTA per NEW spike, threads over that neuron's CSR row: failure draw (Philox keyed by synapse and
+ *              step), Tsodyks–Markram update of (u, R), and the amplitude the delayed pathways will add
+ *              (pathways p0..p6, codes/CortexNetwork.py:360-366).
+ *   k_deliver  one warp per ACTIVE spike (any spike not older than the longest delay): the row is sorted by delay, the
+ *              lanes scan its uint16 delay column and the synapses whose delay equals the spike's age add their
+ *              CURRENT amplitude to the target conductances (pathways p7a..p9b with `delay = dtax`, :367-372,463-468).
+ *              The spike history itself is the delay queue: no per-event queue memory, bounded by one spike per neuron
+ *              per refractory period, and values are read at delivery time exactly as Brian's SpikeQueue does
+ *              (SURVEY F5).  External SpikeGeneratorGroup events (:570-622) are delivered by the same kernel.
+ *
+ * Data layout in HBM: structure of arrays, fp64; per neuron 8 state + 12 parameter doubles + last_spike + int32
+ * lastspike step + 1 flag byte (≈ 240 B read+written per neuron-update, the roofline figure of SURVEY §8d);
+ * per synapse (CSR by presynaptic neuron, sorted by delay) tgt int32, delay uint16, chan uint8, 5 fp64 parameters,
+ * u, R, amplitude, original index uint32 (≈ 75 B).
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/hhd.h"
+#include "hhd_model.cuh"
+
+#define MAX_MON 16
+#define NEURON_BLOCK 128
+#define STP_BLOCK 128
+#define DELIVER_BLOCK 128
+#define STEPS_PER_GRAPH 50
+
+enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_N };
+enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2 };
+
+struct MonDesc {
+  int var, reduce, active;
+  long long n_idx;
+  long long k0;          /* sample index of step k is k - k0 */
+  long long capacity;    /* samples */
+  const int* slot;       /* [N] position of neuron in the monitor's list, or -1; NULL = identity */
+  double* buf;           /* [capacity][width] */
+};
+
+struct Params {
+  int N, NG, off, refr_steps, accum, n_mon, max_delay, W;
+  double dt;
+  unsigned long long seed;
+  ChannelConst cc;
+  double* par[HHD_N_PARAMS];
+  double* x[8];
+  double* last_spike;          /* [NG] */
+  int* lastspike_step;         /* [N]  */
+  unsigned char* flags;        /* [N]  */
+  const unsigned char* has_out;/* [NG] */
+  long long* pend;             /* [3][N] fixed-point increments (HHD_ACCUM_FIXED) */
+  /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
+  const long long* row_ptr;    /* [NG+1] */
+  const int* tgt;              /* local target */
+  const unsigned short* delay;
+  const unsigned char* chan;
+  const double *gmax, *U, *tau_rec, *tau_fac, *pfail;
+  double *u, *R, *amp;
+  const unsigned int* orig;
+  long long syn_id_base;
+  /* spike ring */
+  int* spk_neuron;             /* global ids */
+  int* spk_step;
+  unsigned int cap_mask;
+  unsigned long long* head;    /* monotone count of spikes appended */
+  unsigned long long* step_end;/* [W] head value at the end of step (k % W) */
+  /* external input events, grouped by step */
+  const int* ext_ptr;          /* [ext_last - ext_first + 2] */
+  long long ext_first, ext_last;
+  const int* ext_tgt;
+  const unsigned char* ext_mask;
+  const double *ext_gmax, *ext_pfail;
+  const unsigned int* ext_id;
+  MonDesc* mon;                /* [MAX_MON] device */
+  unsigned long long* counters;
+  const long long* base_step;
+};
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ NeuronPar load_par(const Params& P, int i) {
+  NeuronPar p;
+  p.C = __ldg(P.par[HHD_P_C] + i); p.gL = __ldg(P.par[HHD_P_GL] + i); p.EL = __ldg(P.par[HHD_P_EL] + i);
+  p.dT = __ldg(P.par[HHD_P_DELTAT] + i); p.Vup = __ldg(P.par[HHD_P_VUP] + i); p.tauw = __ldg(P.par[HHD_P_TAUW] + i);
+  p.b = __ldg(P.par[HHD_P_B] + i); p.Vr = __ldg(P.par[HHD_P_VR] + i); p.VT = __ldg(P.par[HHD_P_VT] + i);
+  p.Iref = __ldg(P.par[HHD_P_IREF] + i); p.Vdep = __ldg(P.par[HHD_P_VDEP] + i); p.IDC = __ldg(P.par[HHD_P_IDC] + i);
+  return p;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/*
+ * METHOD: 0 euler, 1 rk2, 2 rk4.  STEP = false: only finish the previous step (used once at the end of hhd_run so that
+ * the state read back is the state after `resets`/`after_resets`).
+ */
+template <int METHOD, bool STEP>
+__global__ void __launch_bounds__(NEURON_BLOCK) k_neuron(const __grid_constant__ Params P, const int step_offset) {
+  const int i = blockIdx.x * NEURON_BLOCK + threadIdx.x;
+  const bool live = i < P.N;
+  const long long k = *P.base_step + step_offset;
+  const double t = (double)k * P.dt;
+  __shared__ double red[MAX_MON][NEURON_BLOCK / 32];
+  __shared__ unsigned long long cnt_sh[3];
+  if (threadIdx.x < 3) cnt_sh[threadIdx.x] = 0ull;
+
+  double x[8];
+  NeuronPar p;
+  double ls = 0.0;
+  unsigned char f = 0;
+  if (live) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
+    p = load_par(P, i);
+    ls = P.last_spike[P.off + i];
+    f = P.flags[i];
+    /* ---- finish step k-1 ---------------------------------------------------------------------------------- */
+    if (P.accum == HHD_ACCUM_FIXED) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long q = P.pend[(size_t)c * P.N + i];
+        if (q) {
+          const double inc = (double)q * (1.0 / 1099511627776.0);
+          x[2 + 2 * c] += inc;
+          x[3 + 2 * c] += inc;
+          P.pend[(size_t)c * P.N + i] = 0;
+        }
+      }
+    }
+    if (f & FLAG_SPIKED) {           /* slot `resets`: V = V_r; w += b   (codes/CortexNetwork.py:305) */
+      x[0] = p.Vr;
+      x[1] += p.b;
+    }
+    if (f & FLAG_WCROSS) {           /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
+      SubExpr s;
+      hhd_subexpr(P.cc, p, x, s);
+      x[1] = s.w_V - s.D0 / p.tauw;
+    }
+  }
+  if (!STEP) {
+    if (live) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
+      P.flags[i] = 0;
+    }
+    return;
+  }
+
+  /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510) ------------------------ */
+  for (int m = 0; m < P.n_mon; ++m) {
+    const MonDesc md = P.mon[m];
+    if (!md.active) continue;
+    const long long sample = k - md.k0;
+    if (sample < 0 || sample >= md.capacity) {
+      if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+      continue;
+    }
+    int slot = -1;
+    if (live) slot = md.slot ? md.slot[i] : i;
+    double v = 0.0;
+    if (slot >= 0) v = hhd_var_value(P.cc, p, x, md.var, ls);
+    if (md.reduce == HHD_REDUCE_NONE) {
+      if (slot >= 0) md.buf[sample * md.n_idx + slot] = v;
+    } else {
+      const double ws = warp_sum(v);
+      if ((threadIdx.x & 31) == 0) red[m][threadIdx.x >> 5] = ws;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double bsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NEURON_BLOCK / 32; ++q) bsum += red[m][q];
+        atomicAdd(&md.buf[sample], bsum);
+      }
+    }
+  }
+
+  bool spiked = false, wcross = false, bad = false;
+  if (live) {
+    /* ---- slot `groups`: state update (:308-309) ---------------------------------------------------------------- */
+    hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
+    bad = !(isfinite(x[0]) && isfinite(x[1]));
+    /* ---- slot `thresholds` (:304, 306) ------------------------------------------------------------------------- */
+    const int lastk = P.lastspike_step[i];
+    spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
+    SubExpr s;
+    hhd_subexpr(P.cc, p, x, s);
+    wcross = (x[1] > s.w_V - s.D0 / p.tauw) && (x[1] < s.w_V + s.D0 / p.tauw) && (x[0] <= p.VT);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
+    P.flags[i] = (unsigned char)((spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0));
+    if (spiked) P.lastspike_step[i] = (int)k;
+  }
+  /* ---- warp-ballot spike compaction: one atomic per warp that has spikes --------------------------------------- */
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned bal = __ballot_sync(0xffffffffu, spiked);
+  if (bal) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.head, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (spiked) {
+      const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
+      P.spk_neuron[pos] = P.off + i;
+      P.spk_step[pos] = (int)k;
+    }
+  }
+  const unsigned balw = __ballot_sync(0xffffffffu, wcross);
+  const unsigned balb = __ballot_sync(0xffffffffu, bad);
+  __syncthreads();
+  if (lane == 0) {
+    if (bal) atomicAdd(&cnt_sh[0], (unsigned long long)__popc(bal));
+    if (balw) atomicAdd(&cnt_sh[1], (unsigned long long)__popc(balw));
+    if (balb) atomicAdd(&cnt_sh[2], (unsigned long long)__popc(balb));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (cnt_sh[0]) atomicAdd(&P.counters[CNT_SPIKES], cnt_sh[0]);
+    if (cnt_sh[1]) atomicAdd(&P.counters[CNT_WCROSS], cnt_sh[1]);
+    if (cnt_sh[2]) atomicAdd(&P.counters[CNT_NONFINITE], cnt_sh[2]);
+  }
+}
+
+/* Pathways p0..p6 for the synapses of every neuron that spiked in this step. */
+__global__ void __launch_bounds__(STP_BLOCK) k_stp(const __grid_constant__ Params P, const int step_offset) {
+  const long long k = *P.base_step + step_offset;
+  const double t = (double)k * P.dt;
+  const unsigned long long lo = P.step_end[(k + P.W - 1) % P.W];
+  const unsigned long long hi = *P.head;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[k % P.W] = hi;
+  unsigned long long events = 0;
+  for (unsigned long long sp = lo + blockIdx.x; sp < hi; sp += gridDim.x) {
+    const int j = P.spk_neuron[(unsigned)sp & P.cap_mask];
+    const double last = P.last_spike[j];
+    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+    for (long long r = r0 + threadIdx.x; r < r1; r += STP_BLOCK) {
+      double u = P.u[r], R = P.R[r];
+      const int c = P.chan[r];
+      const double amp = hhd_stp_update(u, R, P.U[r], P.tau_rec[r], P.tau_fac[r], P.gmax[r], P.cc.gsyn[c], P.pfail[r], t,
+                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)P.orig[r]),
+                                        (unsigned long long)k);
+      P.u[r] = u;
+      P.R[r] = R;
+      P.amp[r] = amp;
+    }
+    if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
+  }
+  if (threadIdx.x == 0 && events) atomicAdd(&P.counters[CNT_SYN_EVENTS], events);
+}
+
+__device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc) {
+  if (P.accum == HHD_ACCUM_FIXED) {
+    const long long q = __double2ll_rn(inc * 1099511627776.0);
+    atomicAdd((unsigned long long*)&P.pend[(size_t)c * P.N + tgt], (unsigned long long)q);
+  } else {
+    atomicAdd(&P.x[2 + 2 * c][tgt], inc);   /* g_X_on_post  += ... */
+    atomicAdd(&P.x[3 + 2 * c][tgt], inc);   /* g_X_off_post += ... */
+  }
+}
+
+/* Order-7 pathways for every synapse whose delay elapses now, plus `last_spike_pre = t` (p5) and external events. */
+__global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
+  const long long k = *P.base_step + step_offset;
+  const double t = (double)k * P.dt;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long lo = P.step_end[(k + 1) % P.W];   /* head at the end of step k - max_delay - 1 */
+  const unsigned long long hi = *P.head;
+  const unsigned warps = (gridDim.x * DELIVER_BLOCK) >> 5;
+  const unsigned wid = (blockIdx.x * DELIVER_BLOCK + threadIdx.x) >> 5;
+  unsigned long long delivered = 0;
+  for (unsigned long long sp = lo + wid; sp < hi; sp += warps) {
+    const unsigned pos = (unsigned)sp & P.cap_mask;
+    const int j = P.spk_neuron[pos];
+    const long long age = k - (long long)P.spk_step[pos];
+    if (age == 0 && lane == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5; every k_stp read of it is complete */
+    if (age > P.max_delay) continue;
+    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+    for (long long rb = r0; rb < r1; rb += 32) {
+      const long long r = rb + lane;
+      int d = 0x7fffffff;
+      if (r < r1) d = P.delay[r];
+      if (d == (int)age) {
+        const double a = P.amp[r];
+        ++delivered;
+        if (a != 0.0) add_increment(P, P.chan[r], P.tgt[r], a);
+      }
+      if (__all_sync(0xffffffffu, d > (int)age)) break;   /* rows are sorted by delay */
+    }
+  }
+  delivered = (unsigned long long)warp_sum((double)delivered);
+  if (lane == 0 && delivered) atomicAdd(&P.counters[CNT_DELIVERIES], delivered);
+
+  /* SpikeGeneratorGroup events of this step: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
+  if (P.ext_ptr && k >= P.ext_first && k <= P.ext_last) {
+    const int e0 = P.ext_ptr[k - P.ext_first], e1 = P.ext_ptr[k - P.ext_first + 1];
+    for (int e = e0 + blockIdx.x * DELIVER_BLOCK + threadIdx.x; e < e1; e += gridDim.x * DELIVER_BLOCK) {
+      const double failure = hhd_philox_u01(P.seed, (unsigned long long)P.ext_id[e], (unsigned long long)k, 1) < P.ext_pfail[e] ? 1.0 : 0.0;
+      const unsigned char mask = P.ext_mask[e];
+      const double g = P.ext_gmax[e] * (1.0 - failure);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (mask & (1 << c)) add_increment(P, c, P.ext_tgt[e], g * P.cc.gsyn[c]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && e1 > e0) atomicAdd(&P.counters[CNT_EXT], (unsigned long long)(e1 - e0));
+  }
+}
+
+__global__ void k_advance(long long* base_step, int n) { *base_step += n; }
+
+__global__ void k_read_var(const __grid_constant__ Params P, int var, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.N) return;
+  double x[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
+  const NeuronPar p = load_par(P, i);
+  out[i] = hhd_var_value(P.cc, p, x, var, P.last_spike[P.off + i]);
+}
+
+/* ================================================== host side =================================================== */
+struct Monitor {
+  int var, reduce, active;
+  long long n_idx, width, capacity, n_samples, first_step;
+  int* d_slot;
+  double* d_buf;
+};
+
+struct ExtSet {
+  int n_sources;
+  std::vector<int> spk_src;
+  std::vector<long long> spk_step;
+  std::vector<int> syn_src, syn_tgt;
+  std::vector<unsigned char> syn_mask;
+  std::vector<double> syn_gmax, syn_pfail;
+  long long id_base;
+};
+
+struct hhd_engine {
+  hhd_config cfg;
+  std::string err;
+  int N = 0, NG = 0;
+  long long step = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Params P;
+  bool neurons_set = false, channels_set = false, started = false, graph_dirty = true, ext_dirty = false;
+  long long nsyn = 0;
+  std::vector<unsigned int> h_orig;          /* permuted position -> original synapse index */
+  std::vector<unsigned short> h_delay_perm;
+  std::vector<unsigned char> has_out_host;
+  bool has_out_given = false;
+  std::vector<void*> allocs;
+  std::vector<Monitor> mons;
+  std::vector<ExtSet> exts;
+  long long ext_syn_total = 0;
+  void *d_ext_ptr = nullptr, *d_ext_tgt = nullptr, *d_ext_mask = nullptr, *d_ext_gmax = nullptr, *d_ext_pfail = nullptr, *d_ext_id = nullptr;
+  MonDesc* d_mon = nullptr;
+  long long* d_base_step = nullptr;
+  unsigned long long* d_counters = nullptr;
+  unsigned long long ring_cap = 0;
+  long long seg_steps = 0;
+  unsigned long long drained = 0;
+  bool record_spikes = true;
+  std::vector<int> rec_neuron;
+  std::vector<long long> rec_step;
+  cudaGraphExec_t graph_exec = nullptr;
+  hhd_counters cnt;
+  int stp_grid = 0, deliver_grid = 0, sm_count = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(hhd_handle h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                                \
+  do {                                                                                                          \
+    cudaError_t e_ = (call);                                                                                    \
+    if (e_ != cudaSuccess) return fail(h, HHD_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(hhd_handle h, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(h, HHD_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  if (zero) cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream);
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+static void dev_free(hhd_handle h, void* p) {
+  if (!p) return;
+  auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+  if (it != h->allocs.end()) h->allocs.erase(it);
+  cudaFree(p);
+}
+template <typename T>
+static int upload(hhd_handle h, T* dst, const T* src, size_t n) {
+  if (!n) return 0;
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));   /* caller owns src: it may be freed right after the call */
+  return 0;
+}
+
+extern "C" int hhd_abi_version(void) { return HHD_ABI_VERSION; }
+extern "C" const char* hhd_last_error(hhd_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
+  hhd_handle h = nullptr;
+  if (!cfg || !out) return fail(h, HHD_E_ARG, "null argument");
+  if (cfg->abi_version != HHD_ABI_VERSION) return fail(h, HHD_E_ARG, "abi_version %d != %d", cfg->abi_version, HHD_ABI_VERSION);
+  if (cfg->n_neurons <= 0 || !(cfg->dt_ms > 0)) return fail(h, HHD_E_ARG, "n_neurons and dt_ms must be positive");
+  if (cfg->method < HHD_EULER || cfg->method > HHD_RK23_ADAPTIVE) return fail(h, HHD_E_ARG, "unknown method %d", cfg->method);
+  if (cfg->method == HHD_RK23_ADAPTIVE) return fail(h, HHD_E_ARG, "HHD_RK23_ADAPTIVE is not available in the CUDA engine yet");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, HHD_E_CUDA, "no CUDA device: %s (this engine has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, HHD_E_ARG, "device %d out of range (%d visible)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(h, HHD_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(h, HHD_E_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", cfg->device, prop.major, prop.minor);
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(h, HHD_E_CUDA, "cudaSetDevice failed");
+  h = new hhd_engine();
+  h->cfg = *cfg;
+  if (h->cfg.n_ranks <= 0) h->cfg.n_ranks = 1;
+  if (h->cfg.n_global <= 0) h->cfg.n_global = cfg->n_neurons;
+  h->N = cfg->n_neurons;
+  h->NG = h->cfg.n_global;
+  if (h->cfg.global_offset < 0 || h->cfg.global_offset + h->N > h->NG) { delete h; return fail(nullptr, HHD_E_ARG, "partition out of range"); }
+  h->sm_count = prop.multiProcessorCount;
+  memset(&h->cnt, 0, sizeof h->cnt);
+  memset(&h->P, 0, sizeof h->P);
+  h->record_spikes = cfg->record_spikes != 0;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, HHD_E_CUDA, "cudaStreamCreate failed"); }
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  Params& P = h->P;
+  P.N = h->N; P.NG = h->NG; P.off = h->cfg.global_offset; P.dt = cfg->dt_ms; P.accum = cfg->accum; P.seed = cfg->seed;
+  P.refr_steps = (int)hhd_timestep(cfg->refractory_ms, cfg->dt_ms);
+  P.cc.window_ms = cfg->block_window_ms;
+  int rc = 0;
+  for (int p = 0; p < HHD_N_PARAMS && !rc; ++p) rc = dev_alloc(h, &P.par[p], h->N);
+  for (int v = 0; v < 8 && !rc; ++v) rc = dev_alloc(h, &P.x[v], h->N);
+  if (!rc) rc = dev_alloc(h, &P.last_spike, h->NG, false);
+  if (!rc) rc = dev_alloc(h, &P.lastspike_step, h->N, false);
+  if (!rc) rc = dev_alloc(h, &P.flags, h->N);
+  unsigned char* ho = nullptr;
+  if (!rc) rc = dev_alloc(h, &ho, h->NG);
+  P.has_out = ho;
+  if (!rc) rc = dev_alloc(h, &P.pend, (size_t)3 * h->N);
+  long long* rp = nullptr;
+  if (!rc) rc = dev_alloc(h, &rp, (size_t)h->NG + 1);
+  P.row_ptr = rp;
+  if (!rc) rc = dev_alloc(h, &P.head, 1);
+  if (!rc) rc = dev_alloc(h, &h->d_base_step, 1);
+  if (!rc) rc = dev_alloc(h, &h->d_counters, CNT_N);
+  if (!rc) rc = dev_alloc(h, &h->d_mon, MAX_MON);
+  if (rc) { std::string m = h->err; hhd_destroy(h); g_create_err = m; return rc; }
+  P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
+  {
+    std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms);
+    std::vector<int> lk((size_t)h->N, INT32_MIN / 2);
+    cudaMemcpyAsync(P.last_spike, ls.data(), ls.size() * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(P.lastspike_step, lk.data(), lk.size() * 4, cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  h->has_out_host.assign((size_t)h->NG, 0);
+  *out = h;
+  return HHD_OK;
+}
+
+extern "C" void hhd_destroy(hhd_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int hhd_set_neurons(hhd_handle h, const double* const* params, const double* V0, const double* w0) {
+  if (!h || !params || !V0 || !w0) return fail(h, HHD_E_ARG, "null argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_neurons after run");
+  cudaSetDevice(h->cfg.device);
+  for (int p = 0; p < HHD_N_PARAMS; ++p) if (!params[p]) return fail(h, HHD_E_ARG, "params[%d] is null", p);
+  for (int i = 0; i < h->N; ++i)
+    if (!(params[HHD_P_C][i] > 0) || !(params[HHD_P_GL][i] > 0) || !(params[HHD_P_DELTAT][i] > 0) || !(params[HHD_P_TAUW][i] > 0))
+      return fail(h, HHD_E_ARG, "neuron %d: C, g_L, delta_T and tau_w must be positive", i);
+  for (int p = 0; p < HHD_N_PARAMS; ++p) { int rc = upload(h, h->P.par[p], params[p], (size_t)h->N); if (rc) return rc; }
+  int rc = upload(h, h->P.x[0], V0, (size_t)h->N);
+  if (!rc) rc = upload(h, h->P.x[1], w0, (size_t)h->N);
+  if (rc) return rc;
+  h->neurons_set = true;
+  return HHD_OK;
+}
+
+extern "C" int hhd_set_has_outgoing(hhd_handle h, const uint8_t* has_out_global) {
+  if (!h || !has_out_global) return fail(h, HHD_E_ARG, "null argument");
+  cudaSetDevice(h->cfg.device);
+  h->has_out_host.assign(has_out_global, has_out_global + h->NG);
+  h->has_out_given = true;
+  return upload(h, const_cast<unsigned char*>(h->P.has_out), h->has_out_host.data(), (size_t)h->NG);
+}
+
+extern "C" int hhd_set_channels(hhd_handle h, const double tau_on[3], const double tau_off[3], const double E_rev[3],
+                                const double gsyn[3], double mg_fac, double mg_slope, double mg_half) {
+  if (!h || !tau_on || !tau_off || !E_rev || !gsyn) return fail(h, HHD_E_ARG, "null argument");
+  for (int c = 0; c < 3; ++c) {
+    if (!(tau_on[c] > 0) || !(tau_off[c] > 0)) return fail(h, HHD_E_ARG, "channel %d: time constants must be positive", c);
+    h->P.cc.inv_tau_on[c] = 1.0 / tau_on[c];
+    h->P.cc.inv_tau_off[c] = 1.0 / tau_off[c];
+    h->P.cc.E[c] = E_rev[c];
+    h->P.cc.gsyn[c] = gsyn[c];
+  }
+  h->P.cc.mg_fac = mg_fac; h->P.cc.mg_slope = mg_slope; h->P.cc.mg_half = mg_half;
+  h->channels_set = true;
+  h->graph_dirty = true;
+  return HHD_OK;
+}
+
+template <typename T>
+static int upload_permuted(hhd_handle h, const T** slot, const T* src, const std::vector<unsigned int>& perm) {
+  std::vector<T> tmp(perm.size());
+  for (size_t r = 0; r < perm.size(); ++r) tmp[r] = src[perm[r]];
+  T* d = nullptr;
+  int rc = dev_alloc(h, &d, perm.size(), false);
+  if (rc) return rc;
+  *slot = d;
+  return upload(h, d, tmp.data(), perm.size());
+}
+
+extern "C" int hhd_set_synapses(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
+                                const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
+                                const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
+  if (!h || nsyn < 0) return fail(h, HHD_E_ARG, "bad argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_synapses after run");
+  if (h->nsyn) return fail(h, HHD_E_STATE, "synapses already set");
+  if (nsyn && (!src || !tgt || !chan || !g_max || !U || !tau_rec || !tau_fac || !p_fail || !delay_ms)) return fail(h, HHD_E_ARG, "null argument");
+  if (nsyn >= (1ll << 32)) return fail(h, HHD_E_ARG, "at most 2^32-1 synapses per handle");
+  cudaSetDevice(h->cfg.device);
+  const int lo = h->cfg.global_offset, hi = lo + h->N;
+  std::vector<unsigned short> dsteps((size_t)nsyn);
+  std::vector<long long> row((size_t)h->NG + 1, 0);
+  int maxd = 0;
+  for (int64_t k = 0; k < nsyn; ++k) {
+    if (src[k] < 0 || src[k] >= h->NG) return fail(h, HHD_E_ARG, "synapse %lld: source %d out of range", (long long)k, src[k]);
+    if (tgt[k] < lo || tgt[k] >= hi) return fail(h, HHD_E_ARG, "synapse %lld: target %d is not local", (long long)k, tgt[k]);
+    if (chan[k] > 2) return fail(h, HHD_E_ARG, "synapse %lld: channel %d", (long long)k, chan[k]);
+    if (!(delay_ms[k] >= 0)) return fail(h, HHD_E_ARG, "synapse %lld: negative delay", (long long)k);
+    if (!(tau_rec[k] > 0) || !(tau_fac[k] > 0)) return fail(h, HHD_E_ARG, "synapse %lld: tau_rec/tau_fac must be positive", (long long)k);
+    const int64_t d = hhd_delay_steps(delay_ms[k], h->cfg.dt_ms);
+    if (d > 65535) return fail(h, HHD_E_ARG, "synapse %lld: delay of %lld steps exceeds 65535", (long long)k, (long long)d);
+    dsteps[k] = (unsigned short)d;
+    maxd = std::max(maxd, (int)d);
+    row[src[k] + 1]++;
+    if (!h->has_out_given) h->has_out_host[src[k]] = 1;
+  }
+  for (int j = 0; j < h->NG; ++j) row[j + 1] += row[j];
+  /* permutation: by source (counting sort, stable), then inside each row by (delay, original index) */
+  std::vector<unsigned int> perm((size_t)nsyn);
+  {
+    std::vector<long long> fill(row.begin(), row.end() - 1);
+    for (int64_t k = 0; k < nsyn; ++k) perm[fill[src[k]]++] = (unsigned int)k;
+    for (int j = 0; j < h->NG; ++j)
+      std::stable_sort(perm.begin() + row[j], perm.begin() + row[j + 1],
+                       [&](unsigned int a, unsigned int b) { return dsteps[a] < dsteps[b]; });
+  }
+  Params& P = h->P;
+  int rc = upload(h, const_cast<long long*>(P.row_ptr), row.data(), row.size());
+  if (!rc) rc = upload(h, const_cast<unsigned char*>(P.has_out), h->has_out_host.data(), (size_t)h->NG);
+  {
+    std::vector<int> t((size_t)nsyn);
+    for (size_t r = 0; r < perm.size(); ++r) t[r] = tgt[perm[r]] - lo;
+    int* d = nullptr;
+    if (!rc) rc = dev_alloc(h, &d, (size_t)nsyn, false);
+    if (!rc) rc = upload(h, d, t.data(), (size_t)nsyn);
+    P.tgt = d;
+  }
+  if (!rc) rc = upload_permuted(h, &P.delay, dsteps.data(), perm);
+  if (!rc) rc = upload_permuted(h, &P.chan, chan, perm);
+  if (!rc) rc = upload_permuted(h, &P.gmax, g_max, perm);
+  if (!rc) rc = upload_permuted(h, &P.U, U, perm);
+  if (!rc) rc = upload_permuted(h, &P.tau_rec, tau_rec, perm);
+  if (!rc) rc = upload_permuted(h, &P.tau_fac, tau_fac, perm);
+  if (!rc) rc = upload_permuted(h, &P.pfail, p_fail, perm);
+  {
+    const double* du = nullptr;
+    if (!rc) rc = upload_permuted(h, &du, U, perm);                 /* u = U   (codes/CortexNetwork.py:422) */
+    P.u = const_cast<double*>(du);
+    std::vector<double> ones((size_t)nsyn, 1.0);
+    if (!rc) rc = dev_alloc(h, &P.R, (size_t)nsyn, false);          /* R = 1   (:424) */
+    if (!rc) rc = upload(h, P.R, ones.data(), (size_t)nsyn);
+    if (!rc) rc = dev_alloc(h, &P.amp, (size_t)nsyn, true);
+    unsigned int* dorig = nullptr;
+    if (!rc) rc = dev_alloc(h, &dorig, (size_t)nsyn, false);
+    if (!rc) rc = upload(h, dorig, perm.data(), (size_t)nsyn);
+    P.orig = dorig;
+  }
+  if (rc) return rc;
+  h->h_orig.swap(perm);
+  h->h_delay_perm.resize((size_t)nsyn);
+  for (size_t r = 0; r < h->h_orig.size(); ++r) h->h_delay_perm[r] = dsteps[h->h_orig[r]];
+  P.max_delay = maxd;
+  P.syn_id_base = syn_id_base;
+  h->nsyn = nsyn;
+  h->graph_dirty = true;
+  return HHD_OK;
+}
+
+extern "C" int hhd_add_spike_source(hhd_handle h, int32_t n_sources, int64_t nspk, const int32_t* spk_src, const double* spk_t_ms,
+                                    int64_t nsyn, const int32_t* syn_src, const int32_t* syn_tgt, const uint8_t* syn_chanmask,
+                                    const double* syn_gmax, const double* syn_pfail) {
+  if (!h || n_sources <= 0 || nspk < 0 || nsyn < 0) return fail(h, HHD_E_ARG, "bad argument");
+  ExtSet e;
+  e.n_sources = n_sources;
+  for (int64_t k = 0; k < nspk; ++k) {
+    if (spk_src[k] < 0 || spk_src[k] >= n_sources) return fail(h, HHD_E_ARG, "spike %lld: source out of range", (long long)k);
+    const long long st = hhd_timestep(spk_t_ms[k], h->cfg.dt_ms);
+    if (st < h->step) return fail(h, HHD_E_ARG, "spike %lld lies in the past", (long long)k);
+    e.spk_src.push_back(spk_src[k]);
+    e.spk_step.push_back(st);
+  }
+  for (int64_t k = 0; k < nsyn; ++k) {
+    if (syn_src[k] < 0 || syn_src[k] >= n_sources) return fail(h, HHD_E_ARG, "input synapse %lld: source out of range", (long long)k);
+    if (syn_tgt[k] < 0 || syn_tgt[k] >= h->N) return fail(h, HHD_E_ARG, "input synapse %lld: target out of range", (long long)k);
+    if (syn_chanmask[k] == 0 || syn_chanmask[k] > 7) return fail(h, HHD_E_ARG, "input synapse %lld: channel mask", (long long)k);
+  }
+  e.syn_src.assign(syn_src, syn_src + nsyn);
+  e.syn_tgt.assign(syn_tgt, syn_tgt + nsyn);
+  e.syn_mask.assign(syn_chanmask, syn_chanmask + nsyn);
+  e.syn_gmax.assign(syn_gmax, syn_gmax + nsyn);
+  e.syn_pfail.assign(syn_pfail, syn_pfail + nsyn);
+  e.id_base = h->ext_syn_total;
+  h->ext_syn_total += nsyn;
+  h->exts.push_back(std::move(e));
+  h->ext_dirty = true;
+  return HHD_OK;
+}
+
+/* Expand (spike, input synapse) pairs of all source sets, grouped by step, and upload them. */
+static int rebuild_ext(hhd_handle h) {
+  struct Ev { long long step; int tgt; unsigned char mask; double gmax, pfail; unsigned int id; };
+  std::vector<Ev> evs;
+  for (const ExtSet& e : h->exts) {
+    std::vector<std::vector<int>> by_src((size_t)e.n_sources);
+    for (size_t s = 0; s < e.syn_src.size(); ++s) by_src[e.syn_src[s]].push_back((int)s);
+    for (size_t q = 0; q < e.spk_src.size(); ++q) {
+      if (e.spk_step[q] < h->step) continue;
+      for (int s : by_src[e.spk_src[q]])
+        evs.push_back({e.spk_step[q], e.syn_tgt[s], e.syn_mask[s], e.syn_gmax[s], e.syn_pfail[s], (unsigned int)(e.id_base + s)});
+    }
+  }
+  std::stable_sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.step < b.step; });
+  dev_free(h, h->d_ext_ptr); dev_free(h, h->d_ext_tgt); dev_free(h, h->d_ext_mask);
+  dev_free(h, h->d_ext_gmax); dev_free(h, h->d_ext_pfail); dev_free(h, h->d_ext_id);
+  h->d_ext_ptr = h->d_ext_tgt = h->d_ext_mask = h->d_ext_gmax = h->d_ext_pfail = h->d_ext_id = nullptr;
+  Params& P = h->P;
+  P.ext_ptr = nullptr;
+  h->ext_dirty = false;
+  h->graph_dirty = true;
+  if (evs.empty()) return 0;
+  if (evs.size() >= (1ull << 31)) return fail(h, HHD_E_ARG, "too many external events");
+  const long long first = evs.front().step, last = evs.back().step;
+  std::vector<int> ptr((size_t)(last - first + 2), 0);
+  for (const Ev& e : evs) ptr[(size_t)(e.step - first + 1)]++;
+  for (size_t q = 1; q < ptr.size(); ++q) ptr[q] += ptr[q - 1];
+  std::vector<int> tgt(evs.size());
+  std::vector<unsigned char> mask(evs.size());
+  std::vector<double> gmax(evs.size()), pfail(evs.size());
+  std::vector<unsigned int> id(evs.size());
+  for (size_t q = 0; q < evs.size(); ++q) { tgt[q] = evs[q].tgt; mask[q] = evs[q].mask; gmax[q] = evs[q].gmax; pfail[q] = evs[q].pfail; id[q] = evs[q].id; }
+  int *dp = nullptr, *dt = nullptr; unsigned char* dm = nullptr; double *dg = nullptr, *df = nullptr; unsigned int* di = nullptr;
+  int rc = dev_alloc(h, &dp, ptr.size(), false);
+  if (!rc) rc = dev_alloc(h, &dt, evs.size(), false);
+  if (!rc) rc = dev_alloc(h, &dm, evs.size(), false);
+  if (!rc) rc = dev_alloc(h, &dg, evs.size(), false);
+  if (!rc) rc = dev_alloc(h, &df, evs.size(), false);
+  if (!rc) rc = dev_alloc(h, &di, evs.size(), false);
+  if (!rc) rc = upload(h, dp, ptr.data(), ptr.size());
+  if (!rc) rc = upload(h, dt, tgt.data(), tgt.size());
+  if (!rc) rc = upload(h, dm, mask.data(), mask.size());
+  if (!rc) rc = upload(h, dg, gmax.data(), gmax.size());
+  if (!rc) rc = upload(h, df, pfail.data(), pfail.size());
+  if (!rc) rc = upload(h, di, id.data(), id.size());
+  if (rc) return rc;
+  h->d_ext_ptr = dp; h->d_ext_tgt = dt; h->d_ext_mask = dm; h->d_ext_gmax = dg; h->d_ext_pfail = df; h->d_ext_id = di;
+  P.ext_ptr = dp; P.ext_first = first; P.ext_last = last; P.ext_tgt = dt; P.ext_mask = dm; P.ext_gmax = dg; P.ext_pfail = df; P.ext_id = di;
+  return 0;
+}
+
+/* ---- monitors ---------------------------------------------------------------------------------------------------- */
+extern "C" int hhd_add_state_monitor(hhd_handle h, int32_t var, int64_t n_idx, const int32_t* idx, int32_t reduce,
+                                     int64_t capacity_steps, int32_t* mon_id) {
+  if (!h || var < 0 || var >= HHD_N_VARS || reduce < 0 || reduce > 2) return fail(h, HHD_E_ARG, "bad argument");
+  if ((int)h->mons.size() >= MAX_MON) return fail(h, HHD_E_CAPACITY, "at most %d state monitors", MAX_MON);
+  cudaSetDevice(h->cfg.device);
+  Monitor m;
+  memset(&m, 0, sizeof m);
+  m.var = var; m.reduce = reduce; m.active = 1; m.first_step = -1;
+  m.n_idx = idx ? n_idx : h->N;
+  m.width = reduce == HHD_REDUCE_NONE ? m.n_idx : 1;
+  if (idx) {
+    std::vector<int> slot((size_t)h->N, -1);
+    for (int64_t q = 0; q < n_idx; ++q) {
+      if (idx[q] < 0 || idx[q] >= h->N) return fail(h, HHD_E_ARG, "monitor index out of range");
+      if (slot[idx[q]] >= 0) return fail(h, HHD_E_ARG, "monitor index %d listed twice", idx[q]);
+      slot[idx[q]] = (int)q;
+    }
+    int rc = dev_alloc(h, &m.d_slot, (size_t)h->N, false);
+    if (!rc) rc = upload(h, m.d_slot, slot.data(), slot.size());
+    if (rc) return rc;
+  }
+  m.capacity = std::max<long long>(capacity_steps, 0);
+  if (m.capacity) { int rc = dev_alloc(h, &m.d_buf, (size_t)(m.capacity * m.width), true); if (rc) return rc; }
+  h->mons.push_back(m);
+  h->graph_dirty = true;
+  if (mon_id) *mon_id = (int)h->mons.size() - 1;
+  return HHD_OK;
+}
+
+extern "C" int hhd_set_monitor_active(hhd_handle h, int32_t mon_id, int32_t active) {
+  if (!h || mon_id < -1 || mon_id >= (int)h->mons.size()) return fail(h, HHD_E_ARG, "bad monitor id");
+  if (mon_id == -1) h->record_spikes = active != 0; else h->mons[mon_id].active = active != 0;
+  return HHD_OK;
+}
+
+extern "C" int hhd_monitor_samples(hhd_handle h, int32_t mon_id, int64_t* n_samples, int64_t* first_step) {
+  if (!h || mon_id < 0 || mon_id >= (int)h->mons.size()) return fail(h, HHD_E_ARG, "bad monitor id");
+  if (n_samples) *n_samples = h->mons[mon_id].n_samples;
+  if (first_step) *first_step = h->mons[mon_id].first_step;
+  return HHD_OK;
+}
+
+extern "C" int hhd_read_monitor(hhd_handle h, int32_t mon_id, double* out, int64_t cap_values, int64_t* n_samples) {
+  if (!h || mon_id < 0 || mon_id >= (int)h->mons.size()) return fail(h, HHD_E_ARG, "bad monitor id");
+  cudaSetDevice(h->cfg.device);
+  Monitor& m = h->mons[mon_id];
+  const long long nv = m.n_samples * m.width;
+  if (nv > cap_values) return fail(h, HHD_E_CAPACITY, "output buffer too small: need %lld values", nv);
+  if (nv) {
+    CU(cudaMemcpyAsync(out, m.d_buf, (size_t)nv * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (m.reduce == HHD_REDUCE_MEAN && m.n_idx) for (long long q = 0; q < nv; ++q) out[q] /= (double)m.n_idx;
+  }
+  if (n_samples) *n_samples = m.n_samples;
+  return HHD_OK;
+}
+
+extern "C" int hhd_read_monitor_dev(hhd_handle h, int32_t mon_id, const double** dev_ptr, int64_t* n_samples) {
+  if (!h || mon_id < 0 || mon_id >= (int)h->mons.size() || !dev_ptr) return fail(h, HHD_E_ARG, "bad argument");
+  *dev_ptr = h->mons[mon_id].d_buf;
+  if (n_samples) *n_samples = h->mons[mon_id].n_samples;
+  return HHD_OK;
+}
+
+extern "C" int hhd_clear_monitor(hhd_handle h, int32_t mon_id) {
+  if (!h || mon_id < -1 || mon_id >= (int)h->mons.size()) return fail(h, HHD_E_ARG, "bad monitor id");
+  cudaSetDevice(h->cfg.device);
+  if (mon_id == -1) { h->rec_neuron.clear(); h->rec_step.clear(); return HHD_OK; }
+  Monitor& m = h->mons[mon_id];
+  if (m.d_buf && m.n_samples) CU(cudaMemsetAsync(m.d_buf, 0, (size_t)(m.n_samples * m.width) * 8, h->stream));
+  m.n_samples = 0;
+  m.first_step = -1;
+  return HHD_OK;
+}
+
+/* ---- run --------------------------------------------------------------------------------------------------------- */
+static unsigned long long next_pow2(unsigned long long v) { unsigned long long p = 1; while (p < v) p <<= 1; return p; }
+
+static int finalize_setup(hhd_handle h) {
+  Params& P = h->P;
+  if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
+  if (!h->channels_set) return fail(h, HHD_E_STATE, "hhd_set_channels has not been called");
+  if (h->cfg.n_ranks > 1) return fail(h, HHD_E_STATE, "multi-rank runs need hhd_comm_init (not built into this plan yet)");
+  if (!h->nsyn) {   /* empty network: arrays must still be valid pointers for the kernels */
+    P.max_delay = 0;
+  }
+  P.W = P.max_delay + 2;
+  int rc = dev_alloc(h, &P.step_end, (size_t)P.W, true);
+  if (rc) return rc;
+  /* Spike ring: a neuron fires at most once per refractory period, so between two host drains (seg_steps apart) plus
+   * the delivery window (max_delay) at most NG * per_neuron entries are live. */
+  h->seg_steps = 2000;
+  const long long refr = std::max(P.refr_steps, 1);
+  const long long per_neuron = (h->seg_steps + P.max_delay + 1 + refr - 1) / refr + 2;
+  h->ring_cap = next_pow2((unsigned long long)h->NG * (unsigned long long)per_neuron);
+  if (h->ring_cap > (1ull << 31)) return fail(h, HHD_E_NOMEM, "spike ring too large");
+  rc = dev_alloc(h, &P.spk_neuron, (size_t)h->ring_cap, false);
+  if (!rc) rc = dev_alloc(h, &P.spk_step, (size_t)h->ring_cap, false);
+  if (rc) return rc;
+  P.cap_mask = (unsigned int)(h->ring_cap - 1);
+  h->stp_grid = h->sm_count * 4;
+  h->deliver_grid = h->sm_count * 4;
+  h->started = true;
+  return 0;
+}
+
+template <bool STEP>
+static void launch_neuron(hhd_handle h, int offset) {
+  const int grid = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+  switch (h->cfg.method) {
+    case HHD_EULER: k_neuron<0, STEP><<<grid, NEURON_BLOCK, 0, h->stream>>>(h->P, offset); break;
+    case HHD_RK2: k_neuron<1, STEP><<<grid, NEURON_BLOCK, 0, h->stream>>>(h->P, offset); break;
+    default: k_neuron<2, STEP><<<grid, NEURON_BLOCK, 0, h->stream>>>(h->P, offset); break;
+  }
+}
+
+static void launch_step(hhd_handle h, int offset) {
+  launch_neuron<true>(h, offset);
+  if (h->nsyn) k_stp<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, offset);
+  else k_stp<<<1, 32, 0, h->stream>>>(h->P, offset);          /* still records step_end */
+  k_deliver<<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+}
+
+static int build_graph(hhd_handle h) {
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  for (int s = 0; s < STEPS_PER_GRAPH; ++s) launch_step(h, s);
+  k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, STEPS_PER_GRAPH);
+  CU(cudaStreamEndCapture(h->stream, &g));
+  cudaError_t e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  h->graph_dirty = false;
+  return 0;
+}
+
+/* Copy the spikes appended since the last drain out of the ring (local neurons only when partitioned). */
+static int drain_spikes(hhd_handle h) {
+  unsigned long long head = 0;
+  CU(cudaMemcpyAsync(&head, h->P.head, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const unsigned long long n = head - h->drained;
+  if (n > h->ring_cap) return fail(h, HHD_E_CAPACITY, "spike ring overflow (%llu spikes in one segment, capacity %llu)", n, h->ring_cap);
+  if (h->record_spikes && n) {
+    std::vector<int> nb((size_t)n), sb((size_t)n);
+    const unsigned long long p0 = h->drained & (h->ring_cap - 1);
+    const unsigned long long first = std::min(n, h->ring_cap - p0);
+    CU(cudaMemcpyAsync(nb.data(), h->P.spk_neuron + p0, (size_t)first * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(sb.data(), h->P.spk_step + p0, (size_t)first * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (first < n) {
+      CU(cudaMemcpyAsync(nb.data() + first, h->P.spk_neuron, (size_t)(n - first) * 4, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(sb.data() + first, h->P.spk_step, (size_t)(n - first) * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    const int lo = h->cfg.global_offset, hi = lo + h->N;
+    /* ring order is (step, arrival); SpikeMonitor order is (step, neuron): sort each step's run */
+    std::vector<std::pair<long long, int>> tmp;
+    tmp.reserve((size_t)n);
+    for (size_t q = 0; q < (size_t)n; ++q) if (nb[q] >= lo && nb[q] < hi) tmp.emplace_back((long long)sb[q], nb[q]);
+    std::sort(tmp.begin(), tmp.end());
+    for (auto& pr : tmp) { h->rec_step.push_back(pr.first); h->rec_neuron.push_back(pr.second); }
+  }
+  h->drained = head;
+  return 0;
+}
+
+static int grow_monitors(hhd_handle h, long long n_steps) {
+  for (Monitor& m : h->mons) {
+    if (!m.active) continue;
+    const long long need = m.n_samples + n_steps;
+    if (need > m.capacity) {
+      const long long ncap = std::max(need, m.capacity * 2);
+      double* nb = nullptr;
+      int rc = dev_alloc(h, &nb, (size_t)(ncap * m.width), true);
+      if (rc) return rc;
+      if (m.n_samples) CU(cudaMemcpyAsync(nb, m.d_buf, (size_t)(m.n_samples * m.width) * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      dev_free(h, m.d_buf);
+      m.d_buf = nb;
+      m.capacity = ncap;
+    }
+  }
+  return 0;
+}
+
+static int push_monitor_descs(hhd_handle h) {
+  MonDesc d[MAX_MON];
+  memset(d, 0, sizeof d);
+  for (size_t q = 0; q < h->mons.size(); ++q) {
+    const Monitor& m = h->mons[q];
+    d[q].var = m.var; d[q].reduce = m.reduce; d[q].active = m.active; d[q].n_idx = m.n_idx;
+    d[q].k0 = h->step - m.n_samples; d[q].capacity = m.capacity; d[q].slot = m.d_slot; d[q].buf = m.d_buf;
+  }
+  CU(cudaMemcpyAsync(h->d_mon, d, sizeof d, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->P.n_mon = (int)h->mons.size();
+  return 0;
+}
+
+extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
+  if (!h || n_steps < 0) return fail(h, HHD_E_ARG, "bad argument");
+  cudaSetDevice(h->cfg.device);
+  int rc = 0;
+  if (!h->started && (rc = finalize_setup(h))) return rc;
+  if (n_steps == 0) return HHD_OK;
+  if (h->step + n_steps >= (1ll << 31) - 1) return fail(h, HHD_E_ARG, "step index would exceed 2^31");
+  if (h->ext_dirty && (rc = rebuild_ext(h))) return rc;
+  if ((rc = grow_monitors(h, n_steps))) return rc;
+  const int prev_n_mon = h->P.n_mon;
+  if ((rc = push_monitor_descs(h))) return rc;
+  if (prev_n_mon != h->P.n_mon) h->graph_dirty = true;
+  for (Monitor& m : h->mons) if (m.active && m.first_step < 0) m.first_step = h->step;
+  CU(cudaMemcpyAsync(h->d_base_step, &h->step, 8, cudaMemcpyHostToDevice, h->stream));
+  if (h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
+
+  CU(cudaEventRecord(h->ev0, h->stream));
+  long long done = 0;
+  while (done < n_steps) {
+    const long long seg = std::min<long long>(h->seg_steps, n_steps - done);
+    long long s = 0;
+    while (seg - s >= STEPS_PER_GRAPH && h->graph_exec && !h->graph_dirty) {
+      CU(cudaGraphLaunch(h->graph_exec, h->stream));
+      h->cnt.kernel_launches += 3 * STEPS_PER_GRAPH + 1;
+      s += STEPS_PER_GRAPH;
+    }
+    const int rem = (int)(seg - s);
+    for (int q = 0; q < rem; ++q) launch_step(h, q);
+    if (rem) { k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, rem); h->cnt.kernel_launches += 3 * rem + 1; }
+    done += seg;
+    if (done == n_steps) { launch_neuron<false>(h, 0); h->cnt.kernel_launches += 1; }
+    CU(cudaGetLastError());
+    if ((rc = drain_spikes(h))) return rc;
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->cnt.run_ms_device += ms;
+  for (Monitor& m : h->mons) if (m.active) m.n_samples += n_steps;
+  h->step += n_steps;
+  h->cnt.steps += n_steps;
+  h->cnt.neuron_updates += n_steps * (long long)h->N;
+  unsigned long long c[CNT_N];
+  CU(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+  if (c[CNT_OVERFLOW]) return fail(h, HHD_E_CAPACITY, "a monitor buffer overflowed on the device");
+  h->cnt.syn_events = (long long)c[CNT_SYN_EVENTS]; h->cnt.syn_deliveries = (long long)c[CNT_DELIVERIES];
+  h->cnt.ext_events = (long long)c[CNT_EXT]; h->cnt.spikes = (long long)c[CNT_SPIKES];
+  h->cnt.w_crossings = (long long)c[CNT_WCROSS]; h->cnt.nonfinite = (long long)c[CNT_NONFINITE];
+  return HHD_OK;
+}
+
+/* ---- results ----------------------------------------------------------------------------------------------------- */
+extern "C" int hhd_spike_count(hhd_handle h, int64_t* n) {
+  if (!h || !n) return fail(h, HHD_E_ARG, "null argument");
+  *n = (int64_t)h->rec_neuron.size();
+  return HHD_OK;
+}
+
+extern "C" int hhd_read_spikes(hhd_handle h, int32_t* neuron, int64_t* step, int64_t cap, int64_t* n_out) {
+  if (!h) return HHD_E_ARG;
+  const int64_t n = (int64_t)h->rec_neuron.size();
+  if (n > cap) return fail(h, HHD_E_CAPACITY, "output buffer too small: need %lld", (long long)n);
+  if (n) { memcpy(neuron, h->rec_neuron.data(), (size_t)n * 4); memcpy(step, h->rec_step.data(), (size_t)n * 8); }
+  if (n_out) *n_out = n;
+  return HHD_OK;
+}
+
+extern "C" int hhd_read_state(hhd_handle h, int32_t var, double* out) {
+  if (!h || !out || var < 0 || var >= HHD_N_VARS) return fail(h, HHD_E_ARG, "bad argument");
+  cudaSetDevice(h->cfg.device);
+  double* tmp = nullptr;
+  int rc = dev_alloc(h, &tmp, (size_t)h->N, false);
+  if (rc) return rc;
+  k_read_var<<<(h->N + 127) / 128, 128, 0, h->stream>>>(h->P, var, tmp);
+  cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  dev_free(h, tmp);
+  if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "read_state failed: %s", cudaGetErrorString(e));
+  return HHD_OK;
+}
+
+extern "C" int hhd_write_state(hhd_handle h, int32_t var, const double* in) {
+  if (!h || !in) return fail(h, HHD_E_ARG, "null argument");
+  cudaSetDevice(h->cfg.device);
+  if (var >= 0 && var < 8) return upload(h, h->P.x[var], in, (size_t)h->N);
+  if (var == HHD_LAST_SPIKE) return upload(h, h->P.last_spike + h->cfg.global_offset, in, (size_t)h->N);
+  return fail(h, HHD_E_ARG, "variable %d is not writable", var);
+}
+
+extern "C" int hhd_read_syn_state(hhd_handle h, int32_t which, double* out) {
+  if (!h || !out) return fail(h, HHD_E_ARG, "null argument");
+  cudaSetDevice(h->cfg.device);
+  if (!h->nsyn) return HHD_OK;
+  if (which == HHD_SYN_DELAY_STEPS) {
+    for (size_t r = 0; r < h->h_orig.size(); ++r) out[h->h_orig[r]] = (double)h->h_delay_perm[r];
+    return HHD_OK;
+  }
+  const double* src = which == HHD_SYN_U ? h->P.u : which == HHD_SYN_R ? h->P.R : which == HHD_SYN_A ? h->P.amp : nullptr;
+  if (!src) return fail(h, HHD_E_ARG, "unknown synapse variable %d", which);
+  std::vector<double> tmp((size_t)h->nsyn);
+  CU(cudaMemcpyAsync(tmp.data(), src, (size_t)h->nsyn * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (size_t r = 0; r < tmp.size(); ++r) out[h->h_orig[r]] = tmp[r];
+  return HHD_OK;
+}
+
+extern "C" int hhd_get_counters(hhd_handle h, hhd_counters* out) {
+  if (!h || !out) return fail(h, HHD_E_ARG, "null argument");
+  *out = h->cnt;
+  return HHD_OK;
+}
+
+extern "C" int hhd_current_step(hhd_handle h, int64_t* step) {
+  if (!h || !step) return fail(h, HHD_E_ARG, "null argument");
+  *step = h->step;
+  return HHD_OK;
+}
+
+extern "C" int hhd_comm_unique_id(uint8_t out_id[128]) { memset(out_id, 0, 128); return HHD_E_COMM; }
+extern "C" int hhd_comm_init(hhd_handle h, const uint8_t id[128]) { (void)id; return fail(h, HHD_E_COMM, "NCCL exchange is not built into this library yet"); }

@@ -1,0 +1,154 @@
+/*
+ * hhd_model.cuh — device-side arithmetic of the simplified-AdEx neuron and its synapses, shared by the grid-wide
+ * (hhd_engine.cu) and cluster-resident (hhd_resident.cu) kernels.
+ *
+ * Every expression keeps the operand order of the reference's equation strings (codes/CortexNetwork.py:233-302 for the
+ * neuron, :360-372 for the synapse pathways) and is compiled with -fmad=false, so a neuron's trajectory is bit-identical
+ * to the CPU oracle's (oracle/hhd_oracle.c, gcc -ffp-contract=off).  exp() is hhd_exp from hhd_math.h on both sides.
+ */
+#ifndef HHD_MODEL_CUH_
+#define HHD_MODEL_CUH_
+
+#include "hhd_math.h"
+
+struct ChannelConst {
+  double inv_tau_on[3], inv_tau_off[3];   /* 1/tau (codes/CortexNetwork.py:256-263 write -(1/tau)*g) */
+  double E[3], gsyn[3];
+  double mg_fac, mg_slope, mg_half;
+  double window_ms;                        /* `t - last_spike < 5*ms` (:251) */
+};
+
+struct NeuronPar {
+  double C, gL, EL, dT, Vup, tauw, b, Vr, VT, Iref, Vdep, IDC;
+};
+
+struct SubExpr {
+  double I_AMPA, I_GABA, I_NMDA, I_syn, I_inj, I_tot, I_exp, w_V, D0, dD0, ex, g[3];
+};
+
+/* state order: V, w, gA_on, gA_off, gG_on, gG_off, gN_on, gN_off (= HHD_V .. HHD_G_NMDA_OFF) */
+__device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const NeuronPar& p, const double x[8], SubExpr& s) {
+  const double V = x[0];
+  s.g[0] = x[3] - x[2];
+  s.g[1] = x[5] - x[4];
+  s.g[2] = x[7] - x[6];
+  s.I_AMPA = s.g[0] * (cc.E[0] - V);
+  const double Mg = 1.0 / (1.0 + cc.mg_fac * hhd_exp(cc.mg_slope * (cc.mg_half - V)));
+  s.I_GABA = s.g[1] * (cc.E[1] - V);
+  s.I_NMDA = (s.g[2] * (cc.E[2] - V)) * Mg;
+  s.I_syn = (s.I_AMPA + s.I_NMDA) + s.I_GABA;
+  s.I_inj = p.IDC + 0.0;
+  s.I_tot = s.I_syn + s.I_inj;
+  s.ex = hhd_exp((V - p.VT) / p.dT);
+  s.I_exp = (p.gL * p.dT) * s.ex;
+  s.w_V = (s.I_tot + s.I_exp) - p.gL * (V - p.EL);
+  s.D0 = (p.C / p.gL) * s.w_V;
+  s.dD0 = p.C * (s.ex - 1.0);
+}
+
+__device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t,
+                                          double ls, double d[8]) {
+  SubExpr s;
+  hhd_subexpr(cc, p, x, s);
+  const double V = x[0], w = x[1];
+  const double a = ((s.I_tot >= p.Iref) ? 1.0 : 0.0) * ((t - ls < cc.window_ms) ? 1.0 : 0.0);
+  const double dV = (a * (-p.gL / p.C)) * (V - p.Vdep) + ((1.0 - a) * (s.w_V - w)) / p.C;
+  const double gate = ((w > s.w_V - s.D0 / p.tauw) ? 1.0 : 0.0) * ((w < s.w_V + s.D0 / p.tauw) ? 1.0 : 0.0) *
+                      ((V <= p.VT) ? 1.0 : 0.0) * ((s.I_tot < p.Iref) ? 1.0 : 0.0);
+  d[0] = dV;
+  d[1] = (gate * -(p.gL * (1.0 - s.ex) + s.dD0 / p.tauw)) * dV;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    d[2 + 2 * c] = -(cc.inv_tau_on[c] * x[2 + 2 * c]);
+    d[3 + 2 * c] = -(cc.inv_tau_off[c] * x[3 + 2 * c]);
+  }
+}
+
+/* Brian 2's ExplicitStateUpdaters: METHOD 0 euler, 1 rk2 (midpoint), 2 rk4. */
+template <int METHOD>
+__device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t,
+                                              double ls, double dt) {
+  double k1[8], y[8];
+  hhd_deriv(cc, p, x, t, ls, k1);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) k1[v] = dt * k1[v];
+  if (METHOD == 0) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = x[v] + k1[v];
+    return;
+  }
+  double k2[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) y[v] = x[v] + k1[v] * 0.5;
+  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k2);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) k2[v] = dt * k2[v];
+  if (METHOD == 1) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = x[v] + k2[v];
+    return;
+  }
+  double k3[8], k4[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) y[v] = x[v] + k2[v] * 0.5;
+  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k3);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) k3[v] = dt * k3[v];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) y[v] = x[v] + k3[v];
+  hhd_deriv(cc, p, y, t + dt, ls, k4);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) x[v] = x[v] + (((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v]) / 6.0;
+}
+
+/* Value of a monitored / derived variable (ids of include/hhd.h) from the state. */
+__device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const NeuronPar& p, const double x[8], int var,
+                                                double last_spike) {
+  switch (var) {   /* constant indices keep x[] in registers */
+    case 0: return x[0];
+    case 1: return x[1];
+    case 2: return x[2];
+    case 3: return x[3];
+    case 4: return x[4];
+    case 5: return x[5];
+    case 6: return x[6];
+    case 7: return x[7];
+    case 20: return last_spike;
+  }
+  SubExpr s;
+  hhd_subexpr(cc, p, x, s);
+  switch (var) {
+    case 8: return s.g[0];
+    case 9: return s.g[1];
+    case 10: return s.g[2];
+    case 11: return s.I_AMPA;
+    case 12: return s.I_GABA;
+    case 13: return s.I_NMDA;
+    case 14: return s.I_syn;
+    case 15: return s.I_inj;
+    case 16: return s.I_tot;
+    case 17: return s.I_AMPA + s.I_NMDA;
+    case 18: return (s.I_AMPA + s.I_NMDA) + s.I_inj;
+    case 19: return s.I_exp;
+  }
+  return 0.0;
+}
+
+/* Pathways p0..p6 for one synapse at presynaptic spike time t (codes/CortexNetwork.py:360-366); returns the amplitude
+ * ((g_max*a_syn)*(1-failure))*Gsyn that the order-7 pathways add when the delay has elapsed (:367-372). */
+__device__ __forceinline__ double hhd_stp_update(double& u, double& R, double U, double tau_rec, double tau_fac,
+                                                 double gmax, double gsyn, double pfail, double t, double last,
+                                                 unsigned long long seed, unsigned long long syn_index,
+                                                 unsigned long long step) {
+  const double failure = hhd_philox_u01(seed, syn_index, step, 0) < pfail ? 1.0 : 0.0;
+  const double u1 = U + (u * (1.0 - U)) * hhd_exp(-(t - last) / tau_fac);
+  const double R1 = 1.0 + ((R - u * R) - 1.0) * hhd_exp(-(t - last) / tau_rec);
+  u = u1;
+  R = R1;
+  const double a_syn = u1 * R1;
+  return ((gmax * a_syn) * (1.0 - failure)) * gsyn;
+}
+
+#endif /* HHD_MODEL_CUH_ */
