@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the simulation hot path (BASELINE.json metric: neuron-updates/s + synaptic events/s,
+realtime factor) on B200, with the HBM roofline of the state-update kernel and a CPU baseline timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload columns|column]
+                    [--columns C] [--method euler|rk2|rk4] [--window S]
+
+A bench "step" = one window of S consecutive time steps (default 100 ms of biological time) of the whole network:
+`value` times hhd_run on the device with everything resident in HBM; `e2e` times the user-facing call sequence with
+host buffers — upload this window's background current (H2D), run, read back the window's spikes, the summed-current
+LFP trace and the counters (D2H).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_NEURON_UPDATE = 240.0   # DESIGN.md §4 / SURVEY §8d: 8 state r+w (128) + 12 params (96) + last_spike, lastspike, flag (16)
+BYTES_PER_SYN_EVENT = 96.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="columns", choices=["columns", "column"])
+    ap.add_argument("--columns", type=int, default=0, help="columns in the scaled network (0 = workload default)")
+    ap.add_argument("--method", default="euler", choices=["euler", "rk2", "rk4"])
+    ap.add_argument("--dt", type=float, default=0.05)
+    ap.add_argument("--window", type=int, default=2000, help="time steps per bench step")
+    ap.add_argument("--accum", default="fp64", choices=["fp64", "fixed"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---- workload ----------------------------------------------------------------------------------------------------
+def one_column():
+    """The one-column template: the reference's own NetworkSetup output (bit-exact golden fixture)."""
+    from oracle_binding import default_idc, load_golden   # fixture loader only (no oracle code runs here)
+    g = load_golden("net_n200_s0")
+    return dict(NeuPar=g["NeuPar"], V0=g["V0"], STypPar=g["STypPar"], SynPar=g["SynPar"], source_arr=g["source_arr"],
+                target_arr=g["target_arr"], I_DC=default_idc(g), name="net_n200_s0 (207 neurons, 12662 synapses)")
+
+
+def build_workload(args, rank, world):
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_columns
+    col = one_column()
+    if args.workload == "column":
+        ncol = 1
+    else:
+        ncol = args.columns or 512
+    per_rank = ncol // world if args.workload == "columns" else 1
+    net = tile_columns(col["NeuPar"], col["V0"], col["SynPar"], col["source_arr"], col["target_arr"], col["I_DC"], per_rank)
+    net["STypPar"] = col["STypPar"]
+    net["columns_total"] = per_rank * world
+    net["columns_rank"] = per_rank
+    net["template"] = col["name"]
+    return net
+
+
+def make_engine(cls, net, args, seed, **kw):
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import load_codes_network
+    n = net["NeuPar"].shape[1]
+    e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
+    load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+    return e
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the CPU arm ---------------------------------------------------------------------------------------------------
+def cpu_sample(net, args, seconds, threads):
+    """Time the CPU oracle (kind 'port': Brian 2, the reference's engine, cannot be installed here) on a bounded
+    number of time steps of the same network."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle_binding import OracleEngine
+    e = make_engine(OracleEngine, net, args, seed=1, record_spikes=True)
+    n = net["NeuPar"].shape[1]
+    t0 = time.perf_counter()
+    e.run(2)
+    per = max((time.perf_counter() - t0) / 2, 1e-7)
+    nsteps = int(max(4, min(args.window * 2, seconds / per)))
+    t0 = time.perf_counter()
+    e.run(nsteps)
+    el = time.perf_counter() - t0
+    c = e.counters()
+    e.close()
+    return dict(value=n * nsteps / el, unit="neuron-updates/s", cores=threads, kind="port",
+                sample="%d time steps of the same %d-neuron network from rest (%.1f s wall), C oracle%s" %
+                       (nsteps, n, el, " with OpenMP over neurons" if threads > 1 else ", single thread"),
+                syn_events_per_s=c["syn_events"] / el, ms_per_time_step=el / nsteps * 1e3), nsteps, el
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    net = build_workload(args, 0, 1 if args.workload == "column" else world)
+    n = net["NeuPar"].shape[1]
+    threads = os.cpu_count() or 1
+    # one bench step = one bounded sample; K steps + W warm-ups must end within a few minutes
+    budget = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
+    vals, ms = [], []
+    info = None
+    for it in range(args.warmup + args.steps):
+        info, nsteps, el = cpu_sample(net, args, budget, threads)
+        if it >= args.warmup:
+            vals.append(info["value"])
+            ms.append(el * 1e3)
+    v = float(np.mean(vals))
+    info["value"] = v
+    out = dict(metric="neuron_updates_per_s", value=v, unit="neuron-updates/s", n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f64", data="synthetic", impl="reference", config=workload_config(args, net, world),
+               cpu_baseline=info, e2e=dict(value=v, unit="neuron-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, net, world):
+    n = net["NeuPar"].shape[1]
+    return dict(workload=("%d-column PFC network (%s tiled, block-diagonal)" % (net["columns_total"], net["template"])
+                          if args.workload == "columns" else "one PFC column (%s)" % net["template"]),
+                neurons=n * (world if args.workload == "columns" else 1), synapses=int(net["SynPar"].shape[1]) * (world if args.workload == "columns" else 1),
+                method=args.method, dt_ms=args.dt, time_steps_per_step=args.window, accumulate=args.accum,
+                monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
+                l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
+                parallelism="%d GPU(s), columns partitioned" % world)
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+
+    net = build_workload(args, rank, world)
+    n = net["NeuPar"].shape[1]
+    t_setup = time.perf_counter()
+    eng = make_engine(Engine, net, args, seed=1 + rank, device=local_rank)
+    lfp = eng.add_state_monitor("I_tot", None, reduce="sum")
+    setup_s = time.perf_counter() - t_setup
+    S = args.window
+    idc = torch.from_numpy(np.ascontiguousarray(net["I_DC"])).pin_memory()   # this window's input, pinned host memory
+    idc_np = idc.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def window_device():
+        eng.run(S)
+        eng.clear_monitor(lfp)
+        eng.clear_monitor(-1)
+
+    def window_e2e():
+        eng.set_idc(idc_np)                   # H2D: background drive of this window
+        eng.run(S)
+        i, s = eng.spikes()                   # D2H: the window's spikes (SpikeMonitor.i / .t)
+        trace = eng.read_monitor(lfp)         # D2H: summed I_tot per time step
+        c = eng.counters()
+        eng.clear_monitor(lfp)
+        eng.clear_monitor(-1)
+        return len(i), trace.nbytes, c
+
+    for _ in range(args.warmup):
+        window_device()
+    # ---- device-timed leg: inputs resident, CUDA events inside hhd_run on the engine's stream ----------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    c0 = eng.counters()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        window_device()
+    barrier()
+    wall_dev = time.perf_counter() - w0
+    c1 = eng.counters()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = c1["run_ms_device"] - c0["run_ms_device"]
+    # ---- end-to-end leg ------------------------------------------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        window_e2e()
+    barrier()
+    e0 = time.perf_counter()
+    nspk_tot, d2h = 0, 0
+    for _ in range(args.steps):
+        nspk, tb, c2 = window_e2e()
+        nspk_tot += nspk
+        d2h += nspk * 8 + tb + 128
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    # ---- per-kernel times for the roofline (CUDA events between launches on the engine's stream) ----------------
+    prof = eng.profile_kernels(min(S, 200))
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(c1["syn_events"] - c0["syn_events"]), float(c1["spikes"] - c0["spikes"]),
+                      float(c1["kernel_launches"] - c0["kernel_launches"]), float(n)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms = mx[0].item(), mx[1].item()
+        syn_ev, spikes, launches, n_total = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item()
+    else:
+        dev_ms, e2e_ms, syn_ev, spikes, launches, n_total = [x.item() for x in t]
+    if rank != 0:
+        return
+    updates = n_total * S * args.steps
+    value = updates / (dev_ms * 1e-3)
+    e2e_value = updates / (e2e_ms * 1e-3)
+    bio_s = S * args.steps * args.dt * 1e-3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = BYTES_PER_NEURON_UPDATE * n / (prof["k_neuron"] * 1e-6) / 1e9
+    out = dict(
+        metric="neuron_updates_per_s", value=value, unit="neuron-updates/s", n_gpus=world, steps=args.steps,
+        warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f64", data="synthetic", config=workload_config(args, net, world),
+        syn_events_per_s=syn_ev / (dev_ms * 1e-3), realtime_factor=bio_s / (dev_ms * 1e-3),
+        mean_rate_hz=spikes / n_total / bio_s, us_per_time_step=dev_ms * 1e3 / (S * args.steps),
+        roofline=dict(bound="hbm", kernel="k_neuron<%s>" % args.method, achieved=achieved, peak=peak, unit="GB/s",
+                      frac=achieved / peak, traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                      algorithmic_bytes_per_launch=BYTES_PER_NEURON_UPDATE * n,
+                      us_per_launch=prof, note="mean of %d launches, CUDA events between kernels on the engine's stream" % min(S, 200)),
+        e2e=dict(value=e2e_value, unit="neuron-updates/s", h2d_bytes_per_step=int(n * 8), d2h_bytes_per_step=int(d2h / args.steps),
+                 ms_per_step=e2e_ms / args.steps),
+        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, wall_s_device_leg=wall_dev)
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"], _, _ = cpu_sample(net, args, args.cpu_seconds, 1)
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,10 @@ int hhd_set_has_outgoing(hhd_handle h, const uint8_t* has_out_global);
 int hhd_set_channels(hhd_handle h, const double tau_on[3], const double tau_off[3], const double E_rev[3],
                      const double gsyn[3], double mg_fac, double mg_slope, double mg_half);
 
+/* Replace the background current row (I_DC, pA) between runs: the per-window drive of a long simulation
+ * (`group.I_DC[...] = constant_current` codes/CortexNetwork.py:314-318; step-wise stand-in for TimedArray I_AC :137-151). */
+int hhd_set_idc(hhd_handle h, const double* idc);
+
 /* ---- synapses: replaces Synapses(...).connect(i,j) + per-synapse assignments + delays/orders,
  *      codes/CortexNetwork.py:343-482 (revision: CortexSetup.py:62-91,239-308) ---------------------------------- */
 /* src, tgt are GLOBAL neuron ids; every tgt must be local to this handle.  chan in {0,1,2}.  delay_ms -> steps as
@@ -176,6 +180,11 @@ int hhd_clear_monitor(hhd_handle h, int32_t mon_id);
 
 /* ---- run: replaces Network.run(t), codes/CortexNetwork.py:729; revision CortexSetup.py:172 -------------------- */
 int hhd_run(hhd_handle h, int64_t n_steps);          /* continues from the current step; callable repeatedly */
+
+/* Measurement aid (bench.py roofline): runs n_steps like hhd_run but launches the kernels one by one with a CUDA event
+ * between them on the handle's stream and returns the mean device time per launch of each kernel in microseconds:
+ * us[0] state update (k_neuron), us[1] spike-time STP (k_stp), us[2] delivery (k_deliver). */
+int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]);
 
 /* ---- results ---------------------------------------------------------------------------------------------------- */
 int hhd_spike_count(hhd_handle h, int64_t* n);       /* recorded spikes so far (SpikeMonitor.num_spikes) */

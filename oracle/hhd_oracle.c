@@ -48,6 +48,8 @@
 #define hhd_read_monitor_dev hhdo_read_monitor_dev
 #define hhd_clear_monitor hhdo_clear_monitor
 #define hhd_run hhdo_run
+#define hhd_set_idc hhdo_set_idc
+#define hhd_profile_kernels hhdo_profile_kernels
 #define hhd_spike_count hhdo_spike_count
 #define hhd_read_spikes hhdo_read_spikes
 #define hhd_read_state hhdo_read_state
@@ -220,6 +222,12 @@ int hhd_set_neurons(hhd_handle h, const double* const* params, const double* V0,
   memcpy(h->x[HHD_V], V0, (size_t)h->N * sizeof(double));   /* codes/CortexNetwork.py:335 */
   memcpy(h->x[HHD_W], w0, (size_t)h->N * sizeof(double));   /* :336 */
   h->neurons_set = 1;
+  return HHD_OK;
+}
+
+int hhd_set_idc(hhd_handle h, const double* idc) {
+  if (!h || !idc) return fail(h, HHD_E_ARG, "null argument");
+  memcpy(h->par[HHD_P_IDC], idc, (size_t)h->N * sizeof(double));
   return HHD_OK;
 }
 
@@ -520,6 +528,10 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
   }
 
   /* slot `groups`: state update of all 8 variables (codes/CortexNetwork.py:308-309) */
+  int64_t bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+#endif
   for (int i = 0; i < h->N; ++i) {
     npar p = load_par(h, i);
     double x[8];
@@ -527,8 +539,9 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
     if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i]);
     else integrate_fixed(h, &p, x, t, h->last_spike[off + i]);
     for (int v = 0; v < 8; ++v) h->x[v][i] = x[v];
-    if (!isfinite(x[HHD_V]) || !isfinite(x[HHD_W])) h->cnt.nonfinite++;
+    if (!isfinite(x[HHD_V]) || !isfinite(x[HHD_W])) bad++;
   }
+  h->cnt.nonfinite += bad;
 
   /* slot `thresholds`: spike = V > V_up and not_refractory (:304); w_crossing (:306) evaluated on the same state */
   h->n_cur_spikes = 0;
@@ -676,6 +689,11 @@ int hhd_run(hhd_handle h, int64_t n_steps) {
   clock_gettime(CLOCK_MONOTONIC, &t1);
   h->cnt.run_ms_device += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
   return HHD_OK;
+}
+
+int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) {
+  (void)n_steps; (void)us;
+  return fail(h, HHD_E_STATE, "the CPU oracle has no kernels to profile");
 }
 
 /* ---- monitors & results ------------------------------------------------------------------------------------------ */

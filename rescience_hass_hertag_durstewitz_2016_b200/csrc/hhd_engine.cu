@@ -525,6 +525,13 @@ extern "C" int hhd_set_neurons(hhd_handle h, const double* const* params, const 
   return HHD_OK;
 }
 
+extern "C" int hhd_set_idc(hhd_handle h, const double* idc) {
+  if (!h || !idc) return fail(h, HHD_E_ARG, "null argument");
+  if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
+  cudaSetDevice(h->cfg.device);
+  return upload(h, h->P.par[HHD_P_IDC], idc, (size_t)h->N);
+}
+
 extern "C" int hhd_set_has_outgoing(hhd_handle h, const uint8_t* has_out_global) {
   if (!h || !has_out_global) return fail(h, HHD_E_ARG, "null argument");
   cudaSetDevice(h->cfg.device);
@@ -672,6 +679,9 @@ extern "C" int hhd_add_spike_source(hhd_handle h, int32_t n_sources, int64_t nsp
 static int rebuild_ext(hhd_handle h) {
   struct Ev { long long step; int tgt; unsigned char mask; double gmax, pfail; unsigned int id; };
   std::vector<Ev> evs;
+  h->exts.erase(std::remove_if(h->exts.begin(), h->exts.end(), [&](const ExtSet& e) {
+                  for (long long st : e.spk_step) if (st >= h->step) return false;
+                  return true; }), h->exts.end());
   for (const ExtSet& e : h->exts) {
     std::vector<std::vector<int>> by_src((size_t)e.n_sources);
     for (size_t s = 0; s < e.syn_src.size(); ++s) by_src[e.syn_src[s]].push_back((int)s);
@@ -969,6 +979,53 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   h->cnt.syn_events = (long long)c[CNT_SYN_EVENTS]; h->cnt.syn_deliveries = (long long)c[CNT_DELIVERIES];
   h->cnt.ext_events = (long long)c[CNT_EXT]; h->cnt.spikes = (long long)c[CNT_SPIKES];
   h->cnt.w_crossings = (long long)c[CNT_WCROSS]; h->cnt.nonfinite = (long long)c[CNT_NONFINITE];
+  return HHD_OK;
+}
+
+extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) {
+  if (!h || n_steps <= 0 || !us) return fail(h, HHD_E_ARG, "bad argument");
+  cudaSetDevice(h->cfg.device);
+  int rc = 0;
+  if (!h->started && (rc = finalize_setup(h))) return rc;
+  if (n_steps > h->seg_steps) n_steps = h->seg_steps;
+  if (h->ext_dirty && (rc = rebuild_ext(h))) return rc;
+  if ((rc = grow_monitors(h, n_steps))) return rc;
+  const int prev_n_mon = h->P.n_mon;
+  if ((rc = push_monitor_descs(h))) return rc;
+  if (prev_n_mon != h->P.n_mon) h->graph_dirty = true;
+  for (Monitor& m : h->mons) if (m.active && m.first_step < 0) m.first_step = h->step;
+  CU(cudaMemcpyAsync(h->d_base_step, &h->step, 8, cudaMemcpyHostToDevice, h->stream));
+  std::vector<cudaEvent_t> ev((size_t)n_steps * 3 + 1);
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  CU(cudaEventRecord(ev[0], h->stream));
+  const int grid = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+  (void)grid;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    launch_neuron<true>(h, (int)s);
+    CU(cudaEventRecord(ev[3 * s + 1], h->stream));
+    k_stp<<<h->nsyn ? h->stp_grid : 1, h->nsyn ? STP_BLOCK : 32, 0, h->stream>>>(h->P, (int)s);
+    CU(cudaEventRecord(ev[3 * s + 2], h->stream));
+    k_deliver<<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    CU(cudaEventRecord(ev[3 * s + 3], h->stream));
+  }
+  k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, (int)n_steps);
+  launch_neuron<false>(h, 0);
+  h->cnt.kernel_launches += 3 * n_steps + 2;
+  CU(cudaGetLastError());
+  if ((rc = drain_spikes(h))) return rc;
+  double acc[3] = {0, 0, 0};
+  for (int64_t s = 0; s < n_steps; ++s)
+    for (int q = 0; q < 3; ++q) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[3 * s + q], ev[3 * s + q + 1]);
+      acc[q] += ms;
+    }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int q = 0; q < 3; ++q) us[q] = acc[q] * 1e3 / (double)n_steps;
+  for (Monitor& m : h->mons) if (m.active) m.n_samples += n_steps;
+  h->step += n_steps;
+  h->cnt.steps += n_steps;
+  h->cnt.neuron_updates += n_steps * (long long)h->N;
   return HHD_OK;
 }
 

@@ -27,7 +27,7 @@ FUNCTIONS = [
     "abi_version", "create", "destroy", "last_error", "set_neurons", "set_has_outgoing", "set_channels", "set_synapses",
     "add_spike_source", "add_state_monitor", "set_monitor_active", "monitor_samples", "read_monitor",
     "read_monitor_dev", "clear_monitor", "run", "spike_count", "read_spikes", "read_state", "write_state",
-    "read_syn_state", "get_counters", "current_step", "comm_unique_id", "comm_init",
+    "read_syn_state", "get_counters", "current_step", "comm_unique_id", "comm_init", "profile_kernels", "set_idc",
 ]
 
 
@@ -159,6 +159,10 @@ class Engine:
         w0 = _f64(w0, n)
         self._check(self._fn("set_neurons")(self._h, arr, _ptr(V0, _dp), _ptr(w0, _dp)))
 
+    def set_idc(self, idc):
+        a = _f64(idc, self.n_neurons)
+        self._check(self._fn("set_idc")(self._h, _ptr(a, _dp)))
+
     def set_has_outgoing(self, has_out_global):
         a = np.ascontiguousarray(has_out_global, dtype=np.uint8)
         if a.size != self.n_global:
@@ -237,6 +241,12 @@ class Engine:
     # -- run and results -------------------------------------------------------------------------------------------
     def run(self, n_steps):
         self._check(self._fn("run")(self._h, C.c_int64(int(n_steps))))
+
+    def profile_kernels(self, n_steps):
+        """Run n_steps with a CUDA event between kernels -> mean microseconds per launch (neuron, stp, deliver)."""
+        us = (C.c_double * 3)()
+        self._check(self._fn("profile_kernels")(self._h, C.c_int64(int(n_steps)), us))
+        return {"k_neuron": us[0], "k_stp": us[1], "k_deliver": us[2]}
 
     def spike_count(self):
         n = C.c_int64(0)
