@@ -1,0 +1,83 @@
+"""hhd_exp / Philox / step-rounding helpers (csrc/hhd_math.h), exercised through the oracle's plain exports."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from oracle_binding import oracle_lib
+
+
+def _lib():
+    lib = oracle_lib()
+    lib.hhdo_exp.restype = C.c_double
+    lib.hhdo_exp.argtypes = [C.c_double]
+    lib.hhdo_philox_u01.restype = C.c_double
+    lib.hhdo_philox_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.hhdo_delay_steps.restype = C.c_int64
+    lib.hhdo_delay_steps.argtypes = [C.c_double, C.c_double]
+    lib.hhdo_timestep.restype = C.c_int64
+    lib.hhdo_timestep.argtypes = [C.c_double, C.c_double]
+    return lib
+
+
+def test_exp_within_one_ulp_of_libm():
+    lib = _lib()
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-745, 709, 20000), rng.uniform(-40, 40, 20000), rng.uniform(-1e-3, 1e-3, 2000),
+                         [0.0, 1.0, -1.0, 709.78, -708.4, -744.0, 1e-300, -1e-300, 0.34657359, -0.34657359]])
+    worst = 0.0
+    for x in xs:
+        got, ref = lib.hhdo_exp(float(x)), math.exp(float(x))
+        if ref == 0.0 or math.isinf(ref):
+            assert got == ref
+            continue
+        ulp = math.ulp(ref)
+        worst = max(worst, abs(got - ref) / ulp)
+    assert worst <= 1.0, worst
+
+
+def test_exp_special_values():
+    lib = _lib()
+    assert lib.hhdo_exp(0.0) == 1.0
+    assert lib.hhdo_exp(710.0) == math.inf
+    assert lib.hhdo_exp(float("inf")) == math.inf
+    assert lib.hhdo_exp(-746.0) == 0.0
+    assert lib.hhdo_exp(float("-inf")) == 0.0
+    assert math.isnan(lib.hhdo_exp(float("nan")))
+    assert 0.0 < lib.hhdo_exp(-740.0) < 1e-320          # subnormal result, rounded once
+
+
+def _expected_u01(w0, w1):
+    return float((((w0 >> 5) << 26) | (w1 >> 6))) / 9007199254740992.0
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors: philox4x32-10 of counter/key all 0 and all ff."""
+    lib = _lib()
+    assert lib.hhdo_philox_u01(0, 0, 0, 0) == _expected_u01(0x6627e8d5, 0xe169c58d)
+    allf = 0xFFFFFFFFFFFFFFFF
+    assert lib.hhdo_philox_u01(allf, allf, 0x00FFFFFFFFFFFFFF, 0xFF) == _expected_u01(0x408f276d, 0x41c83b0e)
+
+
+def test_philox_uniformity_and_independence():
+    lib = _lib()
+    u = np.array([lib.hhdo_philox_u01(42, i, 7, 0) for i in range(20000)])
+    assert 0.0 <= u.min() and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 0.01 and abs((u < 0.3).mean() - 0.3) < 0.01
+    v = np.array([lib.hhdo_philox_u01(42, i, 8, 0) for i in range(20000)])
+    assert abs(np.corrcoef(u, v)[0, 1]) < 0.03
+    assert lib.hhdo_philox_u01(42, 5, 7, 0) != lib.hhdo_philox_u01(42, 5, 7, 1)
+
+
+def test_step_rounding_rules():
+    lib = _lib()
+    # Brian's C++ SpikeQueue: int(delay/dt + 0.5)
+    assert lib.hhdo_delay_steps(0.0, 0.05) == 0
+    assert lib.hhdo_delay_steps(0.0249, 0.05) == 0
+    assert lib.hhdo_delay_steps(0.0251, 0.05) == 1
+    assert lib.hhdo_delay_steps(1.57, 0.05) == 31
+    assert lib.hhdo_delay_steps(3.6, 0.01) == 360
+    # Brian's timestep(): int((t + 1e-3*dt)/dt): refractory 5 ms -> 100 steps at 0.05, 500 at 0.01
+    assert lib.hhdo_timestep(5.0, 0.05) == 100
+    assert lib.hhdo_timestep(5.0, 0.01) == 500
+    assert lib.hhdo_timestep(0.3, 0.1) == 3          # 0.3/0.1 = 2.9999999999999996 without the epsilon
