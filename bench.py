@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="columns", choices=["columns", "column"])
     ap.add_argument("--columns", type=int, default=0, help="columns in the scaled network (0 = workload default)")
+    ap.add_argument("--template", default="n1000", choices=["n1000", "n200"], help="one-column fixture that is tiled")
     ap.add_argument("--method", default="euler", choices=["euler", "rk2", "rk4"])
     ap.add_argument("--dt", type=float, default=0.05)
     ap.add_argument("--window", type=int, default=2000, help="time steps per bench step")
@@ -47,23 +48,33 @@ def parse():
 
 
 # ---- workload ----------------------------------------------------------------------------------------------------
-def one_column():
+def one_column(template):
     """The one-column template: the reference's own NetworkSetup output (bit-exact golden fixture)."""
     from oracle_binding import default_idc, load_golden   # fixture loader only (no oracle code runs here)
-    g = load_golden("net_n200_s0")
+    name = {"n1000": "net_n1000_s0_full", "n200": "net_n200_s0"}[template]
+    if not os.path.exists(os.path.join(ROOT, "tests", "golden", name + ".npz")):
+        name = "net_n200_s0"
+    g = load_golden(name)
     return dict(NeuPar=g["NeuPar"], V0=g["V0"], STypPar=g["STypPar"], SynPar=g["SynPar"], source_arr=g["source_arr"],
-                target_arr=g["target_arr"], I_DC=default_idc(g), name="net_n200_s0 (207 neurons, 12662 synapses)")
+                target_arr=g["target_arr"], I_DC=default_idc(g),
+                name="%s: %d neurons, %d synapses" % (name, g["NeuPar"].shape[1], g["SynPar"].shape[1]))
 
 
-def build_workload(args, rank, world):
+def build_workload(args, rank, world, device_synapses=False):
     from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_columns
-    col = one_column()
+    col = one_column(args.template)
     if args.workload == "column":
         ncol = 1
     else:
-        ncol = args.columns or 512
+        ncol = args.columns or 1000
     per_rank = ncol // world if args.workload == "columns" else 1
-    net = tile_columns(col["NeuPar"], col["V0"], col["SynPar"], col["source_arr"], col["target_arr"], col["I_DC"], per_rank)
+    if device_synapses:
+        # neurons on the host (96 B each), synapses generated straight into HBM by make_engine
+        net = tile_columns(col["NeuPar"], col["V0"], np.zeros((7, 0)), [], [], col["I_DC"], per_rank)
+        net["col"] = col
+    else:
+        net = tile_columns(col["NeuPar"], col["V0"], col["SynPar"], col["source_arr"], col["target_arr"], col["I_DC"], per_rank)
+    net["nsyn"] = int(col["SynPar"].shape[1]) * per_rank
     net["STypPar"] = col["STypPar"]
     net["columns_total"] = per_rank * world
     net["columns_rank"] = per_rank
@@ -76,6 +87,11 @@ def make_engine(cls, net, args, seed, **kw):
     n = net["NeuPar"].shape[1]
     e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
     load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+    if "col" in net:
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_synapses_device
+        col = net["col"]
+        dev = "cuda:%d" % kw.get("device", 0)
+        e.set_synapses_dev(*tile_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], net["columns_rank"], net["n_per_column"], dev))
     return e
 
 
@@ -128,16 +144,26 @@ class ClockSampler:
 
 
 # ---- the CPU arm ---------------------------------------------------------------------------------------------------
-def cpu_sample(net, args, seconds, threads):
+CPU_SAMPLE_COLUMNS = 16
+
+
+def cpu_sample(args, seconds, threads):
     """Time the CPU oracle (kind 'port': Brian 2, the reference's engine, cannot be installed here) on a bounded
-    number of time steps of the same network."""
+    sample of the same workload: the first CPU_SAMPLE_COLUMNS columns (columns of the tiled network are independent,
+    and CPU cost is linear in neurons) for a bounded number of time steps."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle_binding import OracleEngine
+    import copy
+    a2 = copy.copy(args)
+    if args.workload == "columns":
+        a2.columns = min(args.columns or 1000, CPU_SAMPLE_COLUMNS)
+    net = build_workload(a2, 0, 1)
     e = make_engine(OracleEngine, net, args, seed=1, record_spikes=True)
     n = net["NeuPar"].shape[1]
+    e.run(3)                                   # first touch
     t0 = time.perf_counter()
-    e.run(2)
-    per = max((time.perf_counter() - t0) / 2, 1e-7)
+    e.run(5)
+    per = max((time.perf_counter() - t0) / 5, 1e-7)
     nsteps = int(max(4, min(args.window * 2, seconds / per)))
     t0 = time.perf_counter()
     e.run(nsteps)
@@ -145,23 +171,22 @@ def cpu_sample(net, args, seconds, threads):
     c = e.counters()
     e.close()
     return dict(value=n * nsteps / el, unit="neuron-updates/s", cores=threads, kind="port",
-                sample="%d time steps of the same %d-neuron network from rest (%.1f s wall), C oracle%s" %
-                       (nsteps, n, el, " with OpenMP over neurons" if threads > 1 else ", single thread"),
+                sample="%d time steps of %d column(s) (%d neurons, %d synapses) of the same network from rest (%.1f s wall), C oracle%s" %
+                       (nsteps, net["columns_total"], n, net["nsyn"], el, " with OpenMP over neurons" if threads > 1 else ", single thread"),
                 syn_events_per_s=c["syn_events"] / el, ms_per_time_step=el / nsteps * 1e3), nsteps, el
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    net = build_workload(args, 0, 1 if args.workload == "column" else world)
-    n = net["NeuPar"].shape[1]
+    net = build_workload(args, 0, 1 if args.workload == "column" else world, device_synapses=True)   # config only
     threads = os.cpu_count() or 1
     # one bench step = one bounded sample; K steps + W warm-ups must end within a few minutes
     budget = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
     vals, ms = [], []
     info = None
     for it in range(args.warmup + args.steps):
-        info, nsteps, el = cpu_sample(net, args, budget, threads)
+        info, nsteps, el = cpu_sample(args, budget, threads)
         if it >= args.warmup:
             vals.append(info["value"])
             ms.append(el * 1e3)
@@ -178,7 +203,7 @@ def workload_config(args, net, world):
     n = net["NeuPar"].shape[1]
     return dict(workload=("%d-column PFC network (%s tiled, block-diagonal)" % (net["columns_total"], net["template"])
                           if args.workload == "columns" else "one PFC column (%s)" % net["template"]),
-                neurons=n * (world if args.workload == "columns" else 1), synapses=int(net["SynPar"].shape[1]) * (world if args.workload == "columns" else 1),
+                neurons=n * (world if args.workload == "columns" else 1), synapses=net["nsyn"] * (world if args.workload == "columns" else 1),
                 method=args.method, dt_ms=args.dt, time_steps_per_step=args.window, accumulate=args.accum,
                 monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
                 l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
@@ -206,7 +231,7 @@ def main():
         dist.barrier()
     torch.cuda.set_device(local_rank)
 
-    net = build_workload(args, rank, world)
+    net = build_workload(args, rank, world, device_synapses=True)
     n = net["NeuPar"].shape[1]
     t_setup = time.perf_counter()
     eng = make_engine(Engine, net, args, seed=1 + rank, device=local_rank)
@@ -305,7 +330,7 @@ def main():
                  ms_per_step=e2e_ms / args.steps),
         gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, wall_s_device_leg=wall_dev)
     if not args.no_cpu_baseline:
-        out["cpu_baseline"], _, _ = cpu_sample(net, args, args.cpu_seconds, 1)
+        out["cpu_baseline"], _, _ = cpu_sample(args, args.cpu_seconds, 1)
     print(json.dumps(out), flush=True)
 
 

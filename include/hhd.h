@@ -153,6 +153,11 @@ int hhd_set_synapses(hhd_handle h, int64_t nsyn, const int32_t* src, const int32
                      const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
                      const double* p_fail, const double* delay_ms, int64_t syn_id_base);
 
+/* Same with DEVICE pointers (e.g. torch CUDA tensors): for networks whose synapse arrays are generated on the GPU. */
+int hhd_set_synapses_dev(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
+                         const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
+                         const double* p_fail, const double* delay_ms, int64_t syn_id_base);
+
 /* ---- external input: replaces SpikeGeneratorGroup + input Synapses (no STP, no delay, order 0),
  *      codes/CortexNetwork.py:525-719 (revision CortexSetup.py:370-500) ----------------------------------------- */
 /* nspk spikes (source id, time in ms; binned like Brian: step = int((t + 1e-3*dt)/dt)); nsyn input synapses

@@ -40,6 +40,7 @@
 #define hhd_set_has_outgoing hhdo_set_has_outgoing
 #define hhd_set_channels hhdo_set_channels
 #define hhd_set_synapses hhdo_set_synapses
+#define hhd_set_synapses_dev hhdo_set_synapses_dev
 #define hhd_add_spike_source hhdo_add_spike_source
 #define hhd_add_state_monitor hhdo_add_state_monitor
 #define hhd_set_monitor_active hhdo_set_monitor_active
@@ -295,6 +296,13 @@ int hhd_set_synapses(hhd_handle h, int64_t nsyn, const int32_t* src, const int32
   h->nsyn = nsyn;
   h->syn_id_base = syn_id_base;
   return HHD_OK;
+}
+
+int hhd_set_synapses_dev(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
+                         const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
+                         const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
+  (void)nsyn; (void)src; (void)tgt; (void)chan; (void)g_max; (void)U; (void)tau_rec; (void)tau_fac; (void)p_fail; (void)delay_ms; (void)syn_id_base;
+  return fail(h, HHD_E_STATE, "the CPU oracle takes host arrays only");
 }
 
 int hhd_add_spike_source(hhd_handle h, int32_t n_sources, int64_t nspk, const int32_t* spk_src, const double* spk_t_ms,

@@ -24,6 +24,7 @@
  * u, R, amplitude, original index uint32 (≈ 75 B).
  */
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -364,8 +365,6 @@ struct hhd_engine {
   Params P;
   bool neurons_set = false, channels_set = false, started = false, graph_dirty = true, ext_dirty = false;
   long long nsyn = 0;
-  std::vector<unsigned int> h_orig;          /* permuted position -> original synapse index */
-  std::vector<unsigned short> h_delay_perm;
   std::vector<unsigned char> has_out_host;
   bool has_out_given = false;
   std::vector<void*> allocs;
@@ -556,93 +555,191 @@ extern "C" int hhd_set_channels(hhd_handle h, const double tau_on[3], const doub
   return HHD_OK;
 }
 
-template <typename T>
-static int upload_permuted(hhd_handle h, const T** slot, const T* src, const std::vector<unsigned int>& perm) {
-  std::vector<T> tmp(perm.size());
-  for (size_t r = 0; r < perm.size(); ++r) tmp[r] = src[perm[r]];
-  T* d = nullptr;
-  int rc = dev_alloc(h, &d, perm.size(), false);
-  if (rc) return rc;
-  *slot = d;
-  return upload(h, d, tmp.data(), perm.size());
+/* ---- synapse setup on the device: validate, sort by (source, delay) with a stable radix sort, gather into CSR ----- */
+enum { SYNERR_SRC = 1, SYNERR_TGT = 2, SYNERR_CHAN = 4, SYNERR_DELAY = 8, SYNERR_TAU = 16, SYNERR_DELAY_BIG = 32 };
+
+__global__ void k_syn_keys(long long nsyn, const int* src, const int* tgt, const unsigned char* chan, const double* tau_rec,
+                           const double* tau_fac, const double* delay_ms, double dt, int NG, int lo, int hi,
+                           unsigned long long* keys, unsigned int* vals, unsigned int* err, int* maxd) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nsyn) return;
+  unsigned int e = 0;
+  const int s = src[k];
+  if (s < 0 || s >= NG) e |= SYNERR_SRC;
+  if (tgt[k] < lo || tgt[k] >= hi) e |= SYNERR_TGT;
+  if (chan[k] > 2) e |= SYNERR_CHAN;
+  if (!(delay_ms[k] >= 0)) e |= SYNERR_DELAY;
+  if (!(tau_rec[k] > 0) || !(tau_fac[k] > 0)) e |= SYNERR_TAU;
+  long long d = e & SYNERR_DELAY ? 0 : hhd_delay_steps(delay_ms[k], dt);
+  if (d > 65535) { e |= SYNERR_DELAY_BIG; d = 65535; }
+  if (e) atomicOr(err, e);
+  atomicMax(maxd, (int)d);
+  keys[k] = ((unsigned long long)(unsigned int)(e & SYNERR_SRC ? 0 : s) << 16) | (unsigned long long)d;
+  vals[k] = (unsigned int)k;
 }
 
-extern "C" int hhd_set_synapses(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
-                                const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
-                                const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
-  if (!h || nsyn < 0) return fail(h, HHD_E_ARG, "bad argument");
-  if (h->started) return fail(h, HHD_E_STATE, "set_synapses after run");
-  if (h->nsyn) return fail(h, HHD_E_STATE, "synapses already set");
-  if (nsyn && (!src || !tgt || !chan || !g_max || !U || !tau_rec || !tau_fac || !p_fail || !delay_ms)) return fail(h, HHD_E_ARG, "null argument");
-  if (nsyn >= (1ll << 32)) return fail(h, HHD_E_ARG, "at most 2^32-1 synapses per handle");
-  cudaSetDevice(h->cfg.device);
-  const int lo = h->cfg.global_offset, hi = lo + h->N;
-  std::vector<unsigned short> dsteps((size_t)nsyn);
-  std::vector<long long> row((size_t)h->NG + 1, 0);
-  int maxd = 0;
-  for (int64_t k = 0; k < nsyn; ++k) {
-    if (src[k] < 0 || src[k] >= h->NG) return fail(h, HHD_E_ARG, "synapse %lld: source %d out of range", (long long)k, src[k]);
-    if (tgt[k] < lo || tgt[k] >= hi) return fail(h, HHD_E_ARG, "synapse %lld: target %d is not local", (long long)k, tgt[k]);
-    if (chan[k] > 2) return fail(h, HHD_E_ARG, "synapse %lld: channel %d", (long long)k, chan[k]);
-    if (!(delay_ms[k] >= 0)) return fail(h, HHD_E_ARG, "synapse %lld: negative delay", (long long)k);
-    if (!(tau_rec[k] > 0) || !(tau_fac[k] > 0)) return fail(h, HHD_E_ARG, "synapse %lld: tau_rec/tau_fac must be positive", (long long)k);
-    const int64_t d = hhd_delay_steps(delay_ms[k], h->cfg.dt_ms);
-    if (d > 65535) return fail(h, HHD_E_ARG, "synapse %lld: delay of %lld steps exceeds 65535", (long long)k, (long long)d);
-    dsteps[k] = (unsigned short)d;
-    maxd = std::max(maxd, (int)d);
-    row[src[k] + 1]++;
-    if (!h->has_out_given) h->has_out_host[src[k]] = 1;
+__global__ void k_syn_gather(long long nsyn, const unsigned long long* keys, const unsigned int* perm, const int* tgt,
+                             const unsigned char* chan, const double* gmax, const double* U, const double* tau_rec,
+                             const double* tau_fac, const double* pfail, int lo, int* o_tgt, unsigned short* o_delay,
+                             unsigned char* o_chan, double* o_gmax, double* o_U, double* o_tau_rec, double* o_tau_fac,
+                             double* o_pfail, double* o_u, double* o_R, double* o_amp) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nsyn) return;
+  const unsigned int o = perm[r];
+  o_tgt[r] = tgt[o] - lo;
+  o_delay[r] = (unsigned short)(keys[r] & 0xffffull);
+  o_chan[r] = chan[o];
+  o_gmax[r] = gmax[o];
+  const double u0 = U[o];
+  o_U[r] = u0;
+  o_tau_rec[r] = tau_rec[o];
+  o_tau_fac[r] = tau_fac[o];
+  o_pfail[r] = pfail[o];
+  o_u[r] = u0;       /* u = U   (codes/CortexNetwork.py:422) */
+  o_R[r] = 1.0;      /* R = 1   (:424) */
+  o_amp[r] = 0.0;
+}
+
+/* row_ptr[j] = first sorted position whose source is >= j */
+__global__ void k_syn_rows(long long nsyn, const unsigned long long* keys, int NG, long long* row_ptr, unsigned char* has_out, int set_has_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > NG) return;
+  long long lo = 0, hi = nsyn;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)(keys[mid] >> 16) < (long long)j) lo = mid + 1; else hi = mid;
   }
-  for (int j = 0; j < h->NG; ++j) row[j + 1] += row[j];
-  /* permutation: by source (counting sort, stable), then inside each row by (delay, original index) */
-  std::vector<unsigned int> perm((size_t)nsyn);
-  {
-    std::vector<long long> fill(row.begin(), row.end() - 1);
-    for (int64_t k = 0; k < nsyn; ++k) perm[fill[src[k]]++] = (unsigned int)k;
-    for (int j = 0; j < h->NG; ++j)
-      std::stable_sort(perm.begin() + row[j], perm.begin() + row[j + 1],
-                       [&](unsigned int a, unsigned int b) { return dsteps[a] < dsteps[b]; });
+  row_ptr[j] = lo;
+  if (set_has_out && j < NG) {
+    long long lo2 = lo, hi2 = nsyn;
+    const bool any = lo2 < hi2 && (long long)(keys[lo2] >> 16) == (long long)j;
+    has_out[j] = any ? 1 : 0;
   }
+}
+
+static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
+                               const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
+                               const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
   Params& P = h->P;
-  int rc = upload(h, const_cast<long long*>(P.row_ptr), row.data(), row.size());
-  if (!rc) rc = upload(h, const_cast<unsigned char*>(P.has_out), h->has_out_host.data(), (size_t)h->NG);
-  {
-    std::vector<int> t((size_t)nsyn);
-    for (size_t r = 0; r < perm.size(); ++r) t[r] = tgt[perm[r]] - lo;
-    int* d = nullptr;
-    if (!rc) rc = dev_alloc(h, &d, (size_t)nsyn, false);
-    if (!rc) rc = upload(h, d, t.data(), (size_t)nsyn);
-    P.tgt = d;
-  }
-  if (!rc) rc = upload_permuted(h, &P.delay, dsteps.data(), perm);
-  if (!rc) rc = upload_permuted(h, &P.chan, chan, perm);
-  if (!rc) rc = upload_permuted(h, &P.gmax, g_max, perm);
-  if (!rc) rc = upload_permuted(h, &P.U, U, perm);
-  if (!rc) rc = upload_permuted(h, &P.tau_rec, tau_rec, perm);
-  if (!rc) rc = upload_permuted(h, &P.tau_fac, tau_fac, perm);
-  if (!rc) rc = upload_permuted(h, &P.pfail, p_fail, perm);
-  {
-    const double* du = nullptr;
-    if (!rc) rc = upload_permuted(h, &du, U, perm);                 /* u = U   (codes/CortexNetwork.py:422) */
-    P.u = const_cast<double*>(du);
-    std::vector<double> ones((size_t)nsyn, 1.0);
-    if (!rc) rc = dev_alloc(h, &P.R, (size_t)nsyn, false);          /* R = 1   (:424) */
-    if (!rc) rc = upload(h, P.R, ones.data(), (size_t)nsyn);
-    if (!rc) rc = dev_alloc(h, &P.amp, (size_t)nsyn, true);
-    unsigned int* dorig = nullptr;
-    if (!rc) rc = dev_alloc(h, &dorig, (size_t)nsyn, false);
-    if (!rc) rc = upload(h, dorig, perm.data(), (size_t)nsyn);
-    P.orig = dorig;
-  }
+  const int lo = h->cfg.global_offset, hi = lo + h->N;
+  unsigned long long *keys = nullptr, *keys2 = nullptr;
+  unsigned int *vals = nullptr, *vals2 = nullptr, *derr = nullptr;
+  int* dmaxd = nullptr;
+  int rc = dev_alloc(h, &keys, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &keys2, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &vals, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &vals2, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &derr, 1, true);
+  if (!rc) rc = dev_alloc(h, &dmaxd, 1, true);
   if (rc) return rc;
-  h->h_orig.swap(perm);
-  h->h_delay_perm.resize((size_t)nsyn);
-  for (size_t r = 0; r < h->h_orig.size(); ++r) h->h_delay_perm[r] = dsteps[h->h_orig[r]];
+  const int T = 256;
+  const unsigned grid = (unsigned)((nsyn + T - 1) / T);
+  if (nsyn) k_syn_keys<<<grid, T, 0, h->stream>>>(nsyn, src, tgt, chan, tau_rec, tau_fac, delay_ms, h->cfg.dt_ms, h->NG, lo, hi, keys, vals, derr, dmaxd);
+  unsigned int err = 0;
+  int maxd = 0;
+  CU(cudaMemcpyAsync(&err, derr, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&maxd, dmaxd, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (err) {
+    dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, vals2); dev_free(h, derr); dev_free(h, dmaxd);
+    return fail(h, HHD_E_ARG, "invalid synapse arrays:%s%s%s%s%s%s", err & SYNERR_SRC ? " source out of range;" : "",
+                err & SYNERR_TGT ? " target is not local;" : "", err & SYNERR_CHAN ? " channel > 2;" : "",
+                err & SYNERR_DELAY ? " negative delay;" : "", err & SYNERR_TAU ? " tau_rec/tau_fac must be positive;" : "",
+                err & SYNERR_DELAY_BIG ? " delay exceeds 65535 steps;" : "");
+  }
+  int bits = 16;
+  while ((1ll << (bits - 16)) < (long long)h->NG) ++bits;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (long long)nsyn, 0, bits, h->stream);
+  unsigned char* tmp = nullptr;
+  rc = dev_alloc(h, &tmp, tmp_bytes, false);
+  if (rc) return rc;
+  if (nsyn) {
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (long long)nsyn, 0, bits, h->stream);
+    if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "radix sort failed: %s", cudaGetErrorString(e));
+  }
+  int* o_tgt = nullptr; unsigned short* o_delay = nullptr; unsigned char* o_chan = nullptr;
+  double *o_gmax = nullptr, *o_U = nullptr, *o_trec = nullptr, *o_tfac = nullptr, *o_pf = nullptr;
+  rc = dev_alloc(h, &o_tgt, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_delay, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_chan, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_gmax, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_U, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_trec, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_tfac, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &o_pf, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &P.u, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &P.R, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &P.amp, (size_t)nsyn, false);
+  if (rc) return rc;
+  if (nsyn) k_syn_gather<<<grid, T, 0, h->stream>>>(nsyn, keys2, vals2, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, lo, o_tgt, o_delay,
+                                                     o_chan, o_gmax, o_U, o_trec, o_tfac, o_pf, P.u, P.R, P.amp);
+  k_syn_rows<<<(h->NG + 1 + T - 1) / T, T, 0, h->stream>>>(nsyn, keys2, h->NG, const_cast<long long*>(P.row_ptr),
+                                                            const_cast<unsigned char*>(P.has_out), h->has_out_given ? 0 : 1);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  P.tgt = o_tgt; P.delay = o_delay; P.chan = o_chan; P.gmax = o_gmax; P.U = o_U; P.tau_rec = o_trec; P.tau_fac = o_tfac; P.pfail = o_pf;
+  P.orig = vals2;
+  dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, derr); dev_free(h, dmaxd); dev_free(h, tmp);
   P.max_delay = maxd;
   P.syn_id_base = syn_id_base;
   h->nsyn = nsyn;
   h->graph_dirty = true;
   return HHD_OK;
+}
+
+static int check_set_synapses(hhd_handle h, int64_t nsyn, const void* a, const void* b, const void* c, const void* d, const void* e,
+                              const void* f, const void* g, const void* i, const void* j) {
+  if (!h || nsyn < 0) return fail(h, HHD_E_ARG, "bad argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_synapses after run");
+  if (h->nsyn) return fail(h, HHD_E_STATE, "synapses already set");
+  if (nsyn && (!a || !b || !c || !d || !e || !f || !g || !i || !j)) return fail(h, HHD_E_ARG, "null argument");
+  if (nsyn >= (1ll << 32)) return fail(h, HHD_E_ARG, "at most 2^32-1 synapses per handle");
+  if (h->NG > (1 << 30)) return fail(h, HHD_E_ARG, "too many neurons");
+  return 0;
+}
+
+extern "C" int hhd_set_synapses_dev(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
+                                    const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
+                                    const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
+  int rc = check_set_synapses(h, nsyn, src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms);
+  if (rc) return rc;
+  cudaSetDevice(h->cfg.device);
+  CU(cudaDeviceSynchronize());   /* the caller's producer kernels (e.g. torch ops on another stream) must be complete */
+  return set_synapses_device(h, nsyn, src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms, syn_id_base);
+}
+
+template <typename T>
+static int stage(hhd_handle h, const T** slot, const T* src, size_t n) {
+  T* d = nullptr;
+  int rc = dev_alloc(h, &d, n, false);
+  if (rc) return rc;
+  *slot = d;
+  return upload(h, d, src, n);
+}
+
+extern "C" int hhd_set_synapses(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
+                                const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
+                                const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
+  int rc = check_set_synapses(h, nsyn, src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms);
+  if (rc) return rc;
+  cudaSetDevice(h->cfg.device);
+  const int32_t *dsrc = nullptr, *dtgt = nullptr; const uint8_t* dchan = nullptr;
+  const double *dg = nullptr, *dU = nullptr, *dtr = nullptr, *dtf = nullptr, *dpf = nullptr, *ddl = nullptr;
+  const size_t n = (size_t)nsyn;
+  rc = stage(h, &dsrc, src, n);
+  if (!rc) rc = stage(h, &dtgt, tgt, n);
+  if (!rc) rc = stage(h, &dchan, chan, n);
+  if (!rc) rc = stage(h, &dg, g_max, n);
+  if (!rc) rc = stage(h, &dU, U, n);
+  if (!rc) rc = stage(h, &dtr, tau_rec, n);
+  if (!rc) rc = stage(h, &dtf, tau_fac, n);
+  if (!rc) rc = stage(h, &dpf, p_fail, n);
+  if (!rc) rc = stage(h, &ddl, delay_ms, n);
+  if (!rc) rc = set_synapses_device(h, nsyn, dsrc, dtgt, dchan, dg, dU, dtr, dtf, dpf, ddl, syn_id_base);
+  dev_free(h, (void*)dsrc); dev_free(h, (void*)dtgt); dev_free(h, (void*)dchan); dev_free(h, (void*)dg); dev_free(h, (void*)dU);
+  dev_free(h, (void*)dtr); dev_free(h, (void*)dtf); dev_free(h, (void*)dpf); dev_free(h, (void*)ddl);
+  return rc;
 }
 
 extern "C" int hhd_add_spike_source(hhd_handle h, int32_t n_sources, int64_t nspk, const int32_t* spk_src, const double* spk_t_ms,
@@ -1071,8 +1168,13 @@ extern "C" int hhd_read_syn_state(hhd_handle h, int32_t which, double* out) {
   if (!h || !out) return fail(h, HHD_E_ARG, "null argument");
   cudaSetDevice(h->cfg.device);
   if (!h->nsyn) return HHD_OK;
+  std::vector<unsigned int> orig((size_t)h->nsyn);
+  CU(cudaMemcpyAsync(orig.data(), h->P.orig, (size_t)h->nsyn * 4, cudaMemcpyDeviceToHost, h->stream));
   if (which == HHD_SYN_DELAY_STEPS) {
-    for (size_t r = 0; r < h->h_orig.size(); ++r) out[h->h_orig[r]] = (double)h->h_delay_perm[r];
+    std::vector<unsigned short> d((size_t)h->nsyn);
+    CU(cudaMemcpyAsync(d.data(), h->P.delay, (size_t)h->nsyn * 2, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (size_t r = 0; r < d.size(); ++r) out[orig[r]] = (double)d[r];
     return HHD_OK;
   }
   const double* src = which == HHD_SYN_U ? h->P.u : which == HHD_SYN_R ? h->P.R : which == HHD_SYN_A ? h->P.amp : nullptr;
@@ -1080,7 +1182,7 @@ extern "C" int hhd_read_syn_state(hhd_handle h, int32_t which, double* out) {
   std::vector<double> tmp((size_t)h->nsyn);
   CU(cudaMemcpyAsync(tmp.data(), src, (size_t)h->nsyn * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  for (size_t r = 0; r < tmp.size(); ++r) out[h->h_orig[r]] = tmp[r];
+  for (size_t r = 0; r < tmp.size(); ++r) out[orig[r]] = tmp[r];
   return HHD_OK;
 }
 

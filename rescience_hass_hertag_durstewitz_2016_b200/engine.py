@@ -27,7 +27,7 @@ FUNCTIONS = [
     "abi_version", "create", "destroy", "last_error", "set_neurons", "set_has_outgoing", "set_channels", "set_synapses",
     "add_spike_source", "add_state_monitor", "set_monitor_active", "monitor_samples", "read_monitor",
     "read_monitor_dev", "clear_monitor", "run", "spike_count", "read_spikes", "read_state", "write_state",
-    "read_syn_state", "get_counters", "current_step", "comm_unique_id", "comm_init", "profile_kernels", "set_idc",
+    "read_syn_state", "get_counters", "current_step", "comm_unique_id", "comm_init", "profile_kernels", "set_idc", "set_synapses_dev",
 ]
 
 
@@ -184,6 +184,18 @@ class Engine:
             raise ValueError("synapse arrays differ in length")
         self._check(self._fn("set_synapses")(self._h, C.c_int64(n), _ptr(src, _ip), _ptr(tgt, _ip), _ptr(chan, _bp),
                                               *[_ptr(x, _dp) for x in d], C.c_int64(syn_id_base)))
+        self.nsyn = n
+
+    def set_synapses_dev(self, src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms, syn_id_base=0):
+        """Same as set_synapses with torch CUDA tensors (int32, int32, uint8, 6 x float64) that already live on the GPU."""
+        import torch
+        ts = [src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms]
+        want = [torch.int32, torch.int32, torch.uint8] + [torch.float64] * 6
+        n = src.numel()
+        for t, w in zip(ts, want):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == w and t.numel() == n):
+                raise ValueError("set_synapses_dev needs contiguous CUDA tensors of dtype %s and equal length" % w)
+        self._check(self._fn("set_synapses_dev")(self._h, C.c_int64(n), *[C.c_void_p(t.data_ptr()) for t in ts], C.c_int64(syn_id_base)))
         self.nsyn = n
 
     def add_spike_source(self, n_sources, spk_src, spk_t_ms, syn_src, syn_tgt, syn_chanmask, syn_gmax, syn_pfail):
