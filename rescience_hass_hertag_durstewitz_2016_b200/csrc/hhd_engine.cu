@@ -40,16 +40,18 @@
 #include "hhd_model.cuh"
 
 #define MAX_MON 16
+#define MAX_RED 4   /* reduced (sum/mean) monitors: their per-thread accumulators live in registers */
 #define NEURON_BLOCK 128
 #define STP_BLOCK 128
 #define DELIVER_BLOCK 128
 #define STEPS_PER_GRAPH 50
+#define DELAY_BUCKETS 16
 
 enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_N };
 enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2 };
 
 struct MonDesc {
-  int var, reduce, active;
+  int var, reduce, active, red_slot;
   long long n_idx;
   long long k0;          /* sample index of step k is k - k0 */
   long long capacity;    /* samples */
@@ -65,8 +67,7 @@ struct Params {
   double* par[HHD_N_PARAMS];
   double* x[8];
   double* last_spike;          /* [NG] */
-  int* lastspike_step;         /* [N]  */
-  unsigned char* flags;        /* [N]  */
+  int* meta;                   /* [N] lastspike_step * 4 + flags of the previous step */
   const unsigned char* has_out;/* [NG] */
   long long* pend;             /* [3][N] fixed-point increments (HHD_ACCUM_FIXED) */
   /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
@@ -77,6 +78,8 @@ struct Params {
   const double *gmax, *U, *tau_rec, *tau_fac, *pfail;
   double *u, *R, *amp;
   const unsigned int* orig;
+  const unsigned int* row_bkt; /* [NG][DELAY_BUCKETS] offset inside the row of the first synapse with delay >= b*bkt_width */
+  int bkt_width;
   long long syn_id_base;
   /* spike ring */
   int* spk_neuron;             /* global ids */
@@ -112,132 +115,232 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+/* ---- cp.async (LDGSTS) helpers: global -> shared without staging through registers ----------------------------- */
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+#ifndef HHD_NEURON_PREFETCH
+#define HHD_NEURON_PREFETCH 1     /* 1: cp.async double-buffered tiles in shared memory; 0: plain global loads */
+#endif
+#ifndef HHD_NEURON_MINBLOCKS_EULER
+#define HHD_NEURON_MINBLOCKS_EULER 5
+#endif
+#define NEURON_FIELDS 21   /* 8 state + 12 parameters + last_spike */
+struct NeuronStage {
+  double f[NEURON_FIELDS][NEURON_BLOCK];
+  int meta[NEURON_BLOCK];
+};
+#define NEURON_STAGES 2
+#define NEURON_SMEM (HHD_NEURON_PREFETCH ? NEURON_STAGES * (int)sizeof(NeuronStage) : 0)
+
 /*
+ * State update, persistent over tiles of NEURON_BLOCK neurons.  Each thread owns one neuron per tile and prefetches the
+ * 21 doubles + meta word of its NEXT tile into shared memory with cp.async while it integrates the current one, so the
+ * HBM stream (240 B per neuron-update) and the fp64 pipe (≈350 instructions per euler update) overlap inside every warp
+ * instead of alternating; a thread only ever reads the shared slots it filled itself, so no block barrier is needed.
  * METHOD: 0 euler, 1 rk2, 2 rk4.  STEP = false: only finish the previous step (used once at the end of hhd_run so that
  * the state read back is the state after `resets`/`after_resets`).
+ * meta = lastspike_step * 4 + flags (FLAG_SPIKED | FLAG_WCROSS of the previous step).
  */
 template <int METHOD, bool STEP>
-__global__ void __launch_bounds__(NEURON_BLOCK) k_neuron(const __grid_constant__ Params P, const int step_offset) {
-  const int i = blockIdx.x * NEURON_BLOCK + threadIdx.x;
-  const bool live = i < P.N;
-  const long long k = *P.base_step + step_offset;
-  const double t = (double)k * P.dt;
+__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NeuronStage* st = reinterpret_cast<NeuronStage*>(smem_raw);
   __shared__ double red[MAX_MON][NEURON_BLOCK / 32];
   __shared__ unsigned long long cnt_sh[3];
-  if (threadIdx.x < 3) cnt_sh[threadIdx.x] = 0ull;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31;
+  const long long k = *P.base_step + step_offset;
+  const double t = (double)k * P.dt;
+  const int ntiles = (P.N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+  if (tid < 3) cnt_sh[tid] = 0ull;
 
-  double x[8];
-  NeuronPar p;
-  double ls = 0.0;
-  unsigned char f = 0;
-  if (live) {
+  auto issue = [&](int tile, int s) {
+    const int i = tile * NEURON_BLOCK + tid;
+    if (tile < ntiles && i < P.N) {
 #pragma unroll
-    for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
-    p = load_par(P, i);
-    ls = P.last_spike[P.off + i];
-    f = P.flags[i];
-    /* ---- finish step k-1 ---------------------------------------------------------------------------------- */
-    if (P.accum == HHD_ACCUM_FIXED) {
+      for (int v = 0; v < 8; ++v) cp_async8(&st[s].f[v][tid], P.x[v] + i);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const long long q = P.pend[(size_t)c * P.N + i];
-        if (q) {
-          const double inc = (double)q * (1.0 / 1099511627776.0);
-          x[2 + 2 * c] += inc;
-          x[3 + 2 * c] += inc;
-          P.pend[(size_t)c * P.N + i] = 0;
+      for (int q = 0; q < HHD_N_PARAMS; ++q) cp_async8(&st[s].f[8 + q][tid], P.par[q] + i);
+      cp_async8(&st[s].f[20][tid], P.last_spike + P.off + i);
+      cp_async4(&st[s].meta[tid], P.meta + i);
+    }
+    cp_async_commit();
+  };
+
+  double mon_acc[MAX_RED];
+#pragma unroll
+  for (int r = 0; r < MAX_RED; ++r) mon_acc[r] = 0.0;
+  unsigned n_spk = 0, n_wc = 0, n_bad = 0;
+
+  int tile = blockIdx.x;
+#if HHD_NEURON_PREFETCH
+  issue(tile, 0);
+#endif
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int i = tile * NEURON_BLOCK + tid;
+    const bool live = i < P.N;
+    double x[8];
+    NeuronPar p;
+    double ls = 0.0;
+    int meta = 0;
+#if !HHD_NEURON_PREFETCH
+    if (live) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
+      p = load_par(P, i);
+      ls = P.last_spike[P.off + i];
+      meta = P.meta[i];
+    }
+    if (false) {
+      const int s = 0;
+#else
+    const int s = it & 1;
+    issue(tile + gridDim.x, s ^ 1);
+    cp_async_wait<1>();
+    if (live) {
+#endif
+#pragma unroll
+      for (int v = 0; v < 8; ++v) x[v] = st[s].f[v][tid];
+      p.C = st[s].f[8 + HHD_P_C][tid]; p.gL = st[s].f[8 + HHD_P_GL][tid]; p.EL = st[s].f[8 + HHD_P_EL][tid];
+      p.dT = st[s].f[8 + HHD_P_DELTAT][tid]; p.Vup = st[s].f[8 + HHD_P_VUP][tid]; p.tauw = st[s].f[8 + HHD_P_TAUW][tid];
+      p.b = st[s].f[8 + HHD_P_B][tid]; p.Vr = st[s].f[8 + HHD_P_VR][tid]; p.VT = st[s].f[8 + HHD_P_VT][tid];
+      p.Iref = st[s].f[8 + HHD_P_IREF][tid]; p.Vdep = st[s].f[8 + HHD_P_VDEP][tid]; p.IDC = st[s].f[8 + HHD_P_IDC][tid];
+      ls = st[s].f[20][tid];
+      meta = st[s].meta[tid];
+    }
+    if (live) {
+      /* ---- finish step k-1 -------------------------------------------------------------------------------- */
+      if (P.accum == HHD_ACCUM_FIXED) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const long long q = P.pend[(size_t)c * P.N + i];
+          if (q) {
+            const double inc = (double)q * (1.0 / 1099511627776.0);
+            x[2 + 2 * c] += inc;
+            x[3 + 2 * c] += inc;
+            P.pend[(size_t)c * P.N + i] = 0;
+          }
+        }
+      }
+      if (meta & FLAG_SPIKED) {        /* slot `resets`: V = V_r; w += b   (codes/CortexNetwork.py:305) */
+        x[0] = p.Vr;
+        x[1] += p.b;
+      }
+      if (meta & FLAG_WCROSS) {        /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
+        SubExpr sx;
+        hhd_subexpr(P.cc, p, x, sx);
+        x[1] = sx.w_V - hhd_div(sx.D0, p.tauw);
+      }
+    }
+    if (!STEP) {
+      if (live) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
+        P.meta[i] = meta & ~3;
+      }
+      continue;
+    }
+
+    /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510) --------------------- */
+    for (int m = 0; m < P.n_mon; ++m) {
+      const MonDesc md = P.mon[m];
+      if (!md.active) continue;
+      const long long sample = k - md.k0;
+      if (sample < 0 || sample >= md.capacity) {
+        if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+        continue;
+      }
+      int slot = -1;
+      if (live) slot = md.slot ? md.slot[i] : i;
+      if (slot >= 0) {
+        const double v = hhd_var_value(P.cc, p, x, md.var, ls);
+        if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
+        else {
+#pragma unroll
+          for (int r = 0; r < MAX_RED; ++r) if (r == md.red_slot) mon_acc[r] += v;
         }
       }
     }
-    if (f & FLAG_SPIKED) {           /* slot `resets`: V = V_r; w += b   (codes/CortexNetwork.py:305) */
-      x[0] = p.Vr;
-      x[1] += p.b;
-    }
-    if (f & FLAG_WCROSS) {           /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
-      SubExpr s;
-      hhd_subexpr(P.cc, p, x, s);
-      x[1] = s.w_V - s.D0 / p.tauw;
-    }
-  }
-  if (!STEP) {
+
+    bool spiked = false, wcross = false, bad = false;
     if (live) {
+      /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
+      bad = !(isfinite(x[0]) && isfinite(x[1]));
+      /* ---- slot `thresholds` (:304, 306) --------------------------------------------------------------------- */
+      const int lastk = meta >> 2;
+      spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
+      SubExpr sx;
+      hhd_subexpr(P.cc, p, x, sx);
+      const double band = hhd_div(sx.D0, p.tauw);
+      wcross = (x[1] > sx.w_V - band) && (x[1] < sx.w_V + band) && (x[0] <= p.VT);
 #pragma unroll
       for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
-      P.flags[i] = 0;
+      P.meta[i] = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0);
     }
-    return;
-  }
-
-  /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510) ------------------------ */
-  for (int m = 0; m < P.n_mon; ++m) {
-    const MonDesc md = P.mon[m];
-    if (!md.active) continue;
-    const long long sample = k - md.k0;
-    if (sample < 0 || sample >= md.capacity) {
-      if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
-      continue;
-    }
-    int slot = -1;
-    if (live) slot = md.slot ? md.slot[i] : i;
-    double v = 0.0;
-    if (slot >= 0) v = hhd_var_value(P.cc, p, x, md.var, ls);
-    if (md.reduce == HHD_REDUCE_NONE) {
-      if (slot >= 0) md.buf[sample * md.n_idx + slot] = v;
-    } else {
-      const double ws = warp_sum(v);
-      if ((threadIdx.x & 31) == 0) red[m][threadIdx.x >> 5] = ws;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double bsum = 0.0;
-#pragma unroll
-        for (int q = 0; q < NEURON_BLOCK / 32; ++q) bsum += red[m][q];
-        atomicAdd(&md.buf[sample], bsum);
+    /* ---- warp-ballot spike compaction: one atomic per warp that has spikes ----------------------------------- */
+    const unsigned bal = __ballot_sync(0xffffffffu, spiked);
+    if (bal) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(P.head, (unsigned long long)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (spiked) {
+        const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
+        P.spk_neuron[pos] = P.off + i;
+        P.spk_step[pos] = (int)k;
       }
     }
+    n_spk += spiked;
+    n_wc += wcross;
+    n_bad += bad;
   }
+  cp_async_wait<0>();
+  if (!STEP) return;
 
-  bool spiked = false, wcross = false, bad = false;
-  if (live) {
-    /* ---- slot `groups`: state update (:308-309) ---------------------------------------------------------------- */
-    hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
-    bad = !(isfinite(x[0]) && isfinite(x[1]));
-    /* ---- slot `thresholds` (:304, 306) ------------------------------------------------------------------------- */
-    const int lastk = P.lastspike_step[i];
-    spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
-    SubExpr s;
-    hhd_subexpr(P.cc, p, x, s);
-    wcross = (x[1] > s.w_V - s.D0 / p.tauw) && (x[1] < s.w_V + s.D0 / p.tauw) && (x[0] <= p.VT);
+  /* ---- once per CTA: reduced monitors (LFP) and counters ------------------------------------------------------- */
+  for (int m = 0; m < P.n_mon; ++m) {
+    const MonDesc md = P.mon[m];
+    if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
+    const long long sample = k - md.k0;
+    if (sample < 0 || sample >= md.capacity) continue;
+    double mine = 0.0;
 #pragma unroll
-    for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
-    P.flags[i] = (unsigned char)((spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0));
-    if (spiked) P.lastspike_step[i] = (int)k;
+    for (int r = 0; r < MAX_RED; ++r) if (r == md.red_slot) mine = mon_acc[r];
+    const double ws = warp_sum(mine);
+    if (lane == 0) red[m][tid >> 5] = ws;
   }
-  /* ---- warp-ballot spike compaction: one atomic per warp that has spikes --------------------------------------- */
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned bal = __ballot_sync(0xffffffffu, spiked);
-  if (bal) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.head, (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (spiked) {
-      const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
-      P.spk_neuron[pos] = P.off + i;
-      P.spk_step[pos] = (int)k;
-    }
-  }
-  const unsigned balw = __ballot_sync(0xffffffffu, wcross);
-  const unsigned balb = __ballot_sync(0xffffffffu, bad);
+  n_spk = __reduce_add_sync(0xffffffffu, n_spk);
+  n_wc = __reduce_add_sync(0xffffffffu, n_wc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
   __syncthreads();
   if (lane == 0) {
-    if (bal) atomicAdd(&cnt_sh[0], (unsigned long long)__popc(bal));
-    if (balw) atomicAdd(&cnt_sh[1], (unsigned long long)__popc(balw));
-    if (balb) atomicAdd(&cnt_sh[2], (unsigned long long)__popc(balb));
+    if (n_spk) atomicAdd(&cnt_sh[0], (unsigned long long)n_spk);
+    if (n_wc) atomicAdd(&cnt_sh[1], (unsigned long long)n_wc);
+    if (n_bad) atomicAdd(&cnt_sh[2], (unsigned long long)n_bad);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     if (cnt_sh[0]) atomicAdd(&P.counters[CNT_SPIKES], cnt_sh[0]);
     if (cnt_sh[1]) atomicAdd(&P.counters[CNT_WCROSS], cnt_sh[1]);
     if (cnt_sh[2]) atomicAdd(&P.counters[CNT_NONFINITE], cnt_sh[2]);
+    for (int m = 0; m < P.n_mon; ++m) {
+      const MonDesc md = P.mon[m];
+      if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
+      const long long sample = k - md.k0;
+      if (sample < 0 || sample >= md.capacity) continue;
+      double bsum = 0.0;
+#pragma unroll
+      for (int q = 0; q < NEURON_BLOCK / 32; ++q) bsum += red[m][q];
+      atomicAdd(&md.buf[sample], bsum);
+    }
   }
 }
 
@@ -278,33 +381,87 @@ __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, d
   }
 }
 
-/* Order-7 pathways for every synapse whose delay elapses now, plus `last_spike_pre = t` (p5) and external events. */
+__device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc);
+
+/*
+ * Spike delivery.  Order-7 pathways (`g_X_post += ...` after `delay = dtax`, codes/CortexNetwork.py:367-372,463-468) for
+ * every synapse whose delay elapses now, `last_spike_pre = t` (p5), and the SpikeGeneratorGroup events of this step.
+ * One warp per ACTIVE spike: the spike history is the delay queue.  A row is sorted by delay and carries a 16-entry
+ * bucket index, so the warp reads only the ~1/16 of the row that can be due and compares its uint16 delay column with
+ * the spike's age.
+ * FUSED = true: this kernel handles only spikes of EARLIER steps while k_spike_new (p0..p6 + zero-delay deliveries of
+ * this step's spikes) runs concurrently on a second stream; legal only while max_delay < refractory steps, because then
+ * no neuron can have a new spike and an undelivered older one at once, so no delivery can read an amplitude that
+ * another CTA is rewriting.  Otherwise the host launches k_stp, then this kernel with FUSED = false.
+ */
+/* Pathways p0..p6 + the zero-delay deliveries + p5 for the spikes of THIS step, one CTA per new spike (fused mode). */
+__global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
+  const long long k = *P.base_step + step_offset;
+  const double t = (double)k * P.dt;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];
+  const unsigned long long hi = *P.head;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[k % P.W] = hi;
+  unsigned long long events = 0, delivered0 = 0;
+  for (unsigned long long sp = lo_new + blockIdx.x; sp < hi; sp += gridDim.x) {
+    const int j = P.spk_neuron[(unsigned)sp & P.cap_mask];
+    const double last = P.last_spike[j];
+    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+    for (long long r = r0 + threadIdx.x; r < r1; r += STP_BLOCK) {
+      double u = P.u[r], R = P.R[r];
+      const int c = P.chan[r];
+      const double amp = hhd_stp_update(u, R, P.U[r], P.tau_rec[r], P.tau_fac[r], P.gmax[r], P.cc.gsyn[c], P.pfail[r], t,
+                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)P.orig[r]),
+                                        (unsigned long long)k);
+      P.u[r] = u;
+      P.R[r] = R;
+      P.amp[r] = amp;
+      if (P.delay[r] == 0) {
+        ++delivered0;
+        if (amp != 0.0) add_increment(P, c, P.tgt[r], amp);
+      }
+    }
+    if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
+    __syncthreads();                                           /* every thread has read last_spike[j] */
+    if (threadIdx.x == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5 */
+  }
+  if (threadIdx.x == 0 && events) atomicAdd(&P.counters[CNT_SYN_EVENTS], events);
+  delivered0 = (unsigned long long)warp_sum((double)delivered0);
+  if (lane == 0 && delivered0) atomicAdd(&P.counters[CNT_DELIVERIES], delivered0);
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
   const long long k = *P.base_step + step_offset;
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long lo = P.step_end[(k + 1) % P.W];   /* head at the end of step k - max_delay - 1 */
   const unsigned long long hi = *P.head;
+  /* fused mode: the spikes of this step belong to k_spike_new, which runs concurrently on the second stream */
+  const unsigned long long old_hi = FUSED ? P.step_end[(k + P.W - 1) % P.W] : hi;
   const unsigned warps = (gridDim.x * DELIVER_BLOCK) >> 5;
   const unsigned wid = (blockIdx.x * DELIVER_BLOCK + threadIdx.x) >> 5;
   unsigned long long delivered = 0;
-  for (unsigned long long sp = lo + wid; sp < hi; sp += warps) {
+  for (unsigned long long sp = lo + wid; sp < old_hi; sp += warps) {
     const unsigned pos = (unsigned)sp & P.cap_mask;
     const int j = P.spk_neuron[pos];
-    const long long age = k - (long long)P.spk_step[pos];
-    if (age == 0 && lane == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5; every k_stp read of it is complete */
+    const int age = (int)(k - (long long)P.spk_step[pos]);
+    if (!FUSED && age == 0 && lane == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5; every k_stp read of it is complete */
     if (age > P.max_delay) continue;
-    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-    for (long long rb = r0; rb < r1; rb += 32) {
+    const long long r0 = P.row_ptr[j];
+    const int b = age / P.bkt_width;
+    const long long s0 = r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b];
+    const long long s1 = b + 1 < DELAY_BUCKETS ? r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b + 1] : P.row_ptr[j + 1];
+    for (long long rb = s0; rb < s1; rb += 32) {
       const long long r = rb + lane;
       int d = 0x7fffffff;
-      if (r < r1) d = P.delay[r];
-      if (d == (int)age) {
+      if (r < s1) d = P.delay[r];
+      if (d == age) {
         const double a = P.amp[r];
         ++delivered;
         if (a != 0.0) add_increment(P, P.chan[r], P.tgt[r], a);
       }
-      if (__all_sync(0xffffffffu, d > (int)age)) break;   /* rows are sorted by delay */
+      if (__all_sync(0xffffffffu, d > age)) break;            /* rows are sorted by delay */
     }
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
@@ -360,7 +517,8 @@ struct hhd_engine {
   std::string err;
   int N = 0, NG = 0;
   long long step = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Params P;
   bool neurons_set = false, channels_set = false, started = false, graph_dirty = true, ext_dirty = false;
@@ -383,7 +541,9 @@ struct hhd_engine {
   std::vector<long long> rec_step;
   cudaGraphExec_t graph_exec = nullptr;
   hhd_counters cnt;
-  int stp_grid = 0, deliver_grid = 0, sm_count = 0;
+  int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
+  bool fused = false;          /* spike-time STP runs inside k_deliver (max_delay < refractory steps) */
+  int kernels_per_step = 3;
 };
 
 static thread_local std::string g_create_err;
@@ -459,8 +619,11 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   memset(&h->P, 0, sizeof h->P);
   h->record_spikes = cfg->record_spikes != 0;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, HHD_E_CUDA, "cudaStreamCreate failed"); }
+  cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   Params& P = h->P;
   P.N = h->N; P.NG = h->NG; P.off = h->cfg.global_offset; P.dt = cfg->dt_ms; P.accum = cfg->accum; P.seed = cfg->seed;
   P.refr_steps = (int)hhd_timestep(cfg->refractory_ms, cfg->dt_ms);
@@ -469,8 +632,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   for (int p = 0; p < HHD_N_PARAMS && !rc; ++p) rc = dev_alloc(h, &P.par[p], h->N);
   for (int v = 0; v < 8 && !rc; ++v) rc = dev_alloc(h, &P.x[v], h->N);
   if (!rc) rc = dev_alloc(h, &P.last_spike, h->NG, false);
-  if (!rc) rc = dev_alloc(h, &P.lastspike_step, h->N, false);
-  if (!rc) rc = dev_alloc(h, &P.flags, h->N);
+  if (!rc) rc = dev_alloc(h, &P.meta, h->N, false);
   unsigned char* ho = nullptr;
   if (!rc) rc = dev_alloc(h, &ho, h->NG);
   P.has_out = ho;
@@ -486,9 +648,9 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
   {
     std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms);
-    std::vector<int> lk((size_t)h->N, INT32_MIN / 2);
+    std::vector<int> lk((size_t)h->N, -(1 << 30));   /* lastspike = -2^28 steps, no flags */
     cudaMemcpyAsync(P.last_spike, ls.data(), ls.size() * 8, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(P.lastspike_step, lk.data(), lk.size() * 4, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(P.meta, lk.data(), lk.size() * 4, cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
   }
   h->has_out_host.assign((size_t)h->NG, 0);
@@ -502,6 +664,9 @@ extern "C" void hhd_destroy(hhd_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -617,6 +782,21 @@ __global__ void k_syn_rows(long long nsyn, const unsigned long long* keys, int N
   }
 }
 
+/* row_bkt[j][b] = offset inside row j of the first synapse whose delay is >= b * width (rows are sorted by delay) */
+__global__ void k_syn_buckets(int NG, const long long* row_ptr, const unsigned short* delay, int width, unsigned int* row_bkt) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)NG * DELAY_BUCKETS) return;
+  const int j = (int)(q / DELAY_BUCKETS), b = (int)(q % DELAY_BUCKETS);
+  const long long r0 = row_ptr[j], r1 = row_ptr[j + 1];
+  const int want = b * width;
+  long long lo = r0, hi = r1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((int)delay[mid] < want) lo = mid + 1; else hi = mid;
+  }
+  row_bkt[q] = (unsigned int)(lo - r0);
+}
+
 static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
                                const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
                                const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
@@ -678,6 +858,17 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
                                                             const_cast<unsigned char*>(P.has_out), h->has_out_given ? 0 : 1);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
+  {
+    unsigned int* bkt = nullptr;
+    rc = dev_alloc(h, &bkt, (size_t)h->NG * DELAY_BUCKETS, true);
+    if (rc) return rc;
+    P.bkt_width = (maxd + 1 + DELAY_BUCKETS - 1) / DELAY_BUCKETS;
+    const long long nq = (long long)h->NG * DELAY_BUCKETS;
+    k_syn_buckets<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, o_delay, P.bkt_width, bkt);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    P.row_bkt = bkt;
+  }
   P.tgt = o_tgt; P.delay = o_delay; P.chan = o_chan; P.gmax = o_gmax; P.U = o_U; P.tau_rec = o_trec; P.tau_fac = o_tfac; P.pfail = o_pf;
   P.orig = vals2;
   dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, derr); dev_free(h, dmaxd); dev_free(h, tmp);
@@ -831,6 +1022,11 @@ extern "C" int hhd_add_state_monitor(hhd_handle h, int32_t var, int64_t n_idx, c
                                      int64_t capacity_steps, int32_t* mon_id) {
   if (!h || var < 0 || var >= HHD_N_VARS || reduce < 0 || reduce > 2) return fail(h, HHD_E_ARG, "bad argument");
   if ((int)h->mons.size() >= MAX_MON) return fail(h, HHD_E_CAPACITY, "at most %d state monitors", MAX_MON);
+  if (reduce != HHD_REDUCE_NONE) {
+    int nred = 0;
+    for (const Monitor& q : h->mons) nred += q.reduce != HHD_REDUCE_NONE;
+    if (nred >= MAX_RED) return fail(h, HHD_E_CAPACITY, "at most %d reduced (sum/mean) monitors", MAX_RED);
+  }
   cudaSetDevice(h->cfg.device);
   Monitor m;
   memset(&m, 0, sizeof m);
@@ -927,27 +1123,63 @@ static int finalize_setup(hhd_handle h) {
   if (!rc) rc = dev_alloc(h, &P.spk_step, (size_t)h->ring_cap, false);
   if (rc) return rc;
   P.cap_mask = (unsigned int)(h->ring_cap - 1);
+  {
+    /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than tiles */
+    int per_sm[6] = {0, 0, 0, 0, 0, 0};
+    const void* fn[6] = {(const void*)k_neuron<0, true>, (const void*)k_neuron<1, true>, (const void*)k_neuron<2, true>,
+                         (const void*)k_neuron<0, false>, (const void*)k_neuron<1, false>, (const void*)k_neuron<2, false>};
+    for (int q = 0; q < 6; ++q) {
+      CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[q], fn[q], NEURON_BLOCK, NEURON_SMEM));
+    }
+    const int m = h->cfg.method == HHD_EULER ? 0 : h->cfg.method == HHD_RK2 ? 1 : 2;
+    const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+    const char* env = getenv("HHD_NEURON_CTAS_PER_SM");
+    int cps = std::max(1, per_sm[m]);
+    if (env && atoi(env) > 0) cps = std::min(cps, atoi(env));
+    h->neuron_grid = std::max(1, std::min(tiles, h->sm_count * cps));
+    if (!HHD_NEURON_PREFETCH && !getenv("HHD_NEURON_PERSISTENT")) h->neuron_grid = tiles;
+  }
   h->stp_grid = h->sm_count * 4;
-  h->deliver_grid = h->sm_count * 4;
+  h->deliver_grid = h->sm_count * 16;          /* 16 CTAs x 128 threads = one full wave; >= 1 warp per active spike at 1M neurons */
+  if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
+  h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
+  h->kernels_per_step = 3;
+  if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
+    unsigned int* bkt = nullptr;
+    rc = dev_alloc(h, &bkt, (size_t)h->NG * DELAY_BUCKETS, true);
+    if (rc) return rc;
+    P.row_bkt = bkt;
+    P.bkt_width = 1;
+  }
   h->started = true;
   return 0;
 }
 
 template <bool STEP>
 static void launch_neuron(hhd_handle h, int offset) {
-  const int grid = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+  const int grid = h->neuron_grid;
   switch (h->cfg.method) {
-    case HHD_EULER: k_neuron<0, STEP><<<grid, NEURON_BLOCK, 0, h->stream>>>(h->P, offset); break;
-    case HHD_RK2: k_neuron<1, STEP><<<grid, NEURON_BLOCK, 0, h->stream>>>(h->P, offset); break;
-    default: k_neuron<2, STEP><<<grid, NEURON_BLOCK, 0, h->stream>>>(h->P, offset); break;
+    case HHD_EULER: k_neuron<0, STEP><<<grid, NEURON_BLOCK, NEURON_SMEM, h->stream>>>(h->P, offset); break;
+    case HHD_RK2: k_neuron<1, STEP><<<grid, NEURON_BLOCK, NEURON_SMEM, h->stream>>>(h->P, offset); break;
+    default: k_neuron<2, STEP><<<grid, NEURON_BLOCK, NEURON_SMEM, h->stream>>>(h->P, offset); break;
   }
 }
 
 static void launch_step(hhd_handle h, int offset) {
   launch_neuron<true>(h, offset);
-  if (h->nsyn) k_stp<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, offset);
-  else k_stp<<<1, 32, 0, h->stream>>>(h->P, offset);          /* still records step_end */
-  k_deliver<<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+  if (h->fused) {
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    k_spike_new<<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
+    cudaEventRecord(h->ev_join, h->stream2);
+    k_deliver<true><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  } else {
+    if (h->nsyn) k_stp<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, offset);
+    else k_stp<<<1, 32, 0, h->stream>>>(h->P, offset);          /* still records step_end */
+    k_deliver<false><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+  }
 }
 
 static int build_graph(hhd_handle h) {
@@ -1016,8 +1248,10 @@ static int grow_monitors(hhd_handle h, long long n_steps) {
 static int push_monitor_descs(hhd_handle h) {
   MonDesc d[MAX_MON];
   memset(d, 0, sizeof d);
+  int nred = 0;
   for (size_t q = 0; q < h->mons.size(); ++q) {
     const Monitor& m = h->mons[q];
+    d[q].red_slot = m.reduce != HHD_REDUCE_NONE ? nred++ : -1;
     d[q].var = m.var; d[q].reduce = m.reduce; d[q].active = m.active; d[q].n_idx = m.n_idx;
     d[q].k0 = h->step - m.n_samples; d[q].capacity = m.capacity; d[q].slot = m.d_slot; d[q].buf = m.d_buf;
   }
@@ -1033,7 +1267,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   int rc = 0;
   if (!h->started && (rc = finalize_setup(h))) return rc;
   if (n_steps == 0) return HHD_OK;
-  if (h->step + n_steps >= (1ll << 31) - 1) return fail(h, HHD_E_ARG, "step index would exceed 2^31");
+  if (h->step + n_steps >= (1ll << 29) - 1) return fail(h, HHD_E_ARG, "step index would exceed 2^29");
   if (h->ext_dirty && (rc = rebuild_ext(h))) return rc;
   if ((rc = grow_monitors(h, n_steps))) return rc;
   const int prev_n_mon = h->P.n_mon;
@@ -1050,12 +1284,12 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
     long long s = 0;
     while (seg - s >= STEPS_PER_GRAPH && h->graph_exec && !h->graph_dirty) {
       CU(cudaGraphLaunch(h->graph_exec, h->stream));
-      h->cnt.kernel_launches += 3 * STEPS_PER_GRAPH + 1;
+      h->cnt.kernel_launches += h->kernels_per_step * STEPS_PER_GRAPH + 1;
       s += STEPS_PER_GRAPH;
     }
     const int rem = (int)(seg - s);
     for (int q = 0; q < rem; ++q) launch_step(h, q);
-    if (rem) { k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, rem); h->cnt.kernel_launches += 3 * rem + 1; }
+    if (rem) { k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, rem); h->cnt.kernel_launches += h->kernels_per_step * rem + 1; }
     done += seg;
     if (done == n_steps) { launch_neuron<false>(h, 0); h->cnt.kernel_launches += 1; }
     CU(cudaGetLastError());
@@ -1095,19 +1329,19 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
   std::vector<cudaEvent_t> ev((size_t)n_steps * 3 + 1);
   for (auto& e : ev) CU(cudaEventCreate(&e));
   CU(cudaEventRecord(ev[0], h->stream));
-  const int grid = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
-  (void)grid;
   for (int64_t s = 0; s < n_steps; ++s) {
     launch_neuron<true>(h, (int)s);
     CU(cudaEventRecord(ev[3 * s + 1], h->stream));
-    k_stp<<<h->nsyn ? h->stp_grid : 1, h->nsyn ? STP_BLOCK : 32, 0, h->stream>>>(h->P, (int)s);
+    if (!h->fused) k_stp<<<h->nsyn ? h->stp_grid : 1, h->nsyn ? STP_BLOCK : 32, 0, h->stream>>>(h->P, (int)s);
+    else k_spike_new<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
     CU(cudaEventRecord(ev[3 * s + 2], h->stream));
-    k_deliver<<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    if (h->fused) k_deliver<true><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    else k_deliver<false><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
     CU(cudaEventRecord(ev[3 * s + 3], h->stream));
   }
   k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, (int)n_steps);
   launch_neuron<false>(h, 0);
-  h->cnt.kernel_launches += 3 * n_steps + 2;
+  h->cnt.kernel_launches += h->kernels_per_step * n_steps + 2;
   CU(cudaGetLastError());
   if ((rc = drain_spikes(h))) return rc;
   double acc[3] = {0, 0, 0};

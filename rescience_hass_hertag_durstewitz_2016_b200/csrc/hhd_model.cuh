@@ -33,16 +33,16 @@ __device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const Neuron
   s.g[1] = x[5] - x[4];
   s.g[2] = x[7] - x[6];
   s.I_AMPA = s.g[0] * (cc.E[0] - V);
-  const double Mg = 1.0 / (1.0 + cc.mg_fac * hhd_exp(cc.mg_slope * (cc.mg_half - V)));
+  const double Mg = hhd_div(1.0, 1.0 + cc.mg_fac * hhd_exp(cc.mg_slope * (cc.mg_half - V)));
   s.I_GABA = s.g[1] * (cc.E[1] - V);
   s.I_NMDA = (s.g[2] * (cc.E[2] - V)) * Mg;
   s.I_syn = (s.I_AMPA + s.I_NMDA) + s.I_GABA;
   s.I_inj = p.IDC + 0.0;
   s.I_tot = s.I_syn + s.I_inj;
-  s.ex = hhd_exp((V - p.VT) / p.dT);
+  s.ex = hhd_exp(hhd_div(V - p.VT, p.dT));
   s.I_exp = (p.gL * p.dT) * s.ex;
   s.w_V = (s.I_tot + s.I_exp) - p.gL * (V - p.EL);
-  s.D0 = (p.C / p.gL) * s.w_V;
+  s.D0 = hhd_div(p.C, p.gL) * s.w_V;
   s.dD0 = p.C * (s.ex - 1.0);
 }
 
@@ -52,11 +52,12 @@ __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPa
   hhd_subexpr(cc, p, x, s);
   const double V = x[0], w = x[1];
   const double a = ((s.I_tot >= p.Iref) ? 1.0 : 0.0) * ((t - ls < cc.window_ms) ? 1.0 : 0.0);
-  const double dV = (a * (-p.gL / p.C)) * (V - p.Vdep) + ((1.0 - a) * (s.w_V - w)) / p.C;
-  const double gate = ((w > s.w_V - s.D0 / p.tauw) ? 1.0 : 0.0) * ((w < s.w_V + s.D0 / p.tauw) ? 1.0 : 0.0) *
+  const double dV = (a * hhd_div(-p.gL, p.C)) * (V - p.Vdep) + hhd_div((1.0 - a) * (s.w_V - w), p.C);
+  const double band = hhd_div(s.D0, p.tauw);
+  const double gate = ((w > s.w_V - band) ? 1.0 : 0.0) * ((w < s.w_V + band) ? 1.0 : 0.0) *
                       ((V <= p.VT) ? 1.0 : 0.0) * ((s.I_tot < p.Iref) ? 1.0 : 0.0);
   d[0] = dV;
-  d[1] = (gate * -(p.gL * (1.0 - s.ex) + s.dD0 / p.tauw)) * dV;
+  d[1] = (gate * -(p.gL * (1.0 - s.ex) + hhd_div(s.dD0, p.tauw))) * dV;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     d[2 + 2 * c] = -(cc.inv_tau_on[c] * x[2 + 2 * c]);
@@ -100,7 +101,7 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
 #pragma unroll
   for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
 #pragma unroll
-  for (int v = 0; v < 8; ++v) x[v] = x[v] + (((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v]) / 6.0;
+  for (int v = 0; v < 8; ++v) x[v] = x[v] + hhd_div(((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v], 6.0);
 }
 
 /* Value of a monitored / derived variable (ids of include/hhd.h) from the state. */
@@ -143,8 +144,8 @@ __device__ __forceinline__ double hhd_stp_update(double& u, double& R, double U,
                                                  unsigned long long seed, unsigned long long syn_index,
                                                  unsigned long long step) {
   const double failure = hhd_philox_u01(seed, syn_index, step, 0) < pfail ? 1.0 : 0.0;
-  const double u1 = U + (u * (1.0 - U)) * hhd_exp(-(t - last) / tau_fac);
-  const double R1 = 1.0 + ((R - u * R) - 1.0) * hhd_exp(-(t - last) / tau_rec);
+  const double u1 = U + (u * (1.0 - U)) * hhd_exp(hhd_div(-(t - last), tau_fac));
+  const double R1 = 1.0 + ((R - u * R) - 1.0) * hhd_exp(hhd_div(-(t - last), tau_rec));
   u = u1;
   R = R1;
   const double a_syn = u1 * R1;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libhhd.so")
+LIB_PATH = os.environ.get("HHD_LIB") or os.path.join(_HERE, "csrc", "libhhd.so")   # HHD_LIB: kernel-variant experiments
 
 ABI_VERSION = 1
 METHODS = {"euler": 0, "rk2": 1, "rk4": 2, "rk23": 3, "gsl_rk2": 3}
