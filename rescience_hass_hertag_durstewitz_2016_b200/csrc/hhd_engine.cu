@@ -59,6 +59,20 @@ struct MonDesc {
   double* buf;           /* [capacity][width] */
 };
 
+/* Synapses are stored row-contiguous (CSR by presynaptic neuron, rows sorted by delay) as two arrays of structs so that
+ * one event touches one 16-byte and one 64-byte record instead of twelve separate arrays: the synapse data of a
+ * 1M-neuron network spans 23 GB, far beyond TLB reach, and every separate array costs its own page walk. */
+struct __align__(16) SynHot {   /* read by every delivery */
+  int tgt;                      /* local target neuron */
+  unsigned short delay;         /* steps */
+  unsigned char chan, pad;
+  double amp;                   /* ((g_max*a_syn)*(1-failure))*Gsyn of the latest presynaptic spike */
+};
+struct __align__(16) SynStp {   /* read and written once per presynaptic spike (pathways p0..p6) */
+  double U, tau_rec, tau_fac, gmax, pfail, u, R;
+  unsigned int orig, pad;       /* original synapse index: RNG key and hhd_read_syn_state order */
+};
+
 struct Params {
   int N, NG, off, refr_steps, accum, n_mon, max_delay, W;
   double dt;
@@ -72,12 +86,8 @@ struct Params {
   long long* pend;             /* [3][N] fixed-point increments (HHD_ACCUM_FIXED) */
   /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
   const long long* row_ptr;    /* [NG+1] */
-  const int* tgt;              /* local target */
-  const unsigned short* delay;
-  const unsigned char* chan;
-  const double *gmax, *U, *tau_rec, *tau_fac, *pfail;
-  double *u, *R, *amp;
-  const unsigned int* orig;
+  SynHot* hot;
+  SynStp* stp;
   const unsigned int* row_bkt; /* [NG][DELAY_BUCKETS] offset inside the row of the first synapse with delay >= b*bkt_width */
   int bkt_width;
   long long syn_id_base;
@@ -126,8 +136,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+/* ---- TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP) + mbarrier transaction counting -------------------------- */
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#ifndef HHD_EXPERIMENT
+#define HHD_EXPERIMENT 0          /* timing experiments only (bit 0: no w_crossing test, bit 1: no integration) */
+#endif
 #ifndef HHD_NEURON_PREFETCH
-#define HHD_NEURON_PREFETCH 1     /* 1: cp.async double-buffered tiles in shared memory; 0: plain global loads */
+#define HHD_NEURON_PREFETCH 2     /* 2: TMA bulk copies + mbarrier, double-buffered tiles in shared memory; 1: per-thread cp.async; 0: plain loads */
 #endif
 #ifndef HHD_NEURON_MINBLOCKS_EULER
 #define HHD_NEURON_MINBLOCKS_EULER 5
@@ -162,6 +199,35 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   const int ntiles = (P.N + NEURON_BLOCK - 1) / NEURON_BLOCK;
   if (tid < 3) cnt_sh[tid] = 0ull;
 
+#if HHD_NEURON_PREFETCH == 2
+  __shared__ __align__(8) unsigned long long full_bar[NEURON_STAGES];
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < NEURON_STAGES; ++q) mbar_init(&full_bar[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  /* Producer = thread 0: twenty 1 KB bulk copies (8 state + 12 parameter rows of the tile; the arrays are padded to whole
+   * tiles) complete on the stage's mbarrier; every thread fetches its own last_spike and meta word with cp.async. */
+  auto issue = [&](int tile, int s) {
+    const int i = tile * NEURON_BLOCK + tid;
+    if (tile < ntiles) {
+      if (tid == 0) {
+        const size_t o = (size_t)tile * NEURON_BLOCK;
+        mbar_expect_tx(&full_bar[s], 20u * NEURON_BLOCK * 8u);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) tma_load_1d(&st[s].f[v][0], P.x[v] + o, NEURON_BLOCK * 8u, &full_bar[s]);
+#pragma unroll
+        for (int q = 0; q < HHD_N_PARAMS; ++q) tma_load_1d(&st[s].f[8 + q][0], P.par[q] + o, NEURON_BLOCK * 8u, &full_bar[s]);
+      }
+      if (i < P.N) {
+        cp_async8(&st[s].f[20][tid], P.last_spike + P.off + i);
+        cp_async4(&st[s].meta[tid], P.meta + i);
+      }
+    }
+    cp_async_commit();
+  };
+#else
   auto issue = [&](int tile, int s) {
     const int i = tile * NEURON_BLOCK + tid;
     if (tile < ntiles && i < P.N) {
@@ -174,6 +240,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     }
     cp_async_commit();
   };
+#endif
 
   double mon_acc[MAX_RED];
 #pragma unroll
@@ -201,6 +268,12 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     }
     if (false) {
       const int s = 0;
+#elif HHD_NEURON_PREFETCH == 2
+    const int s = it & 1;
+    issue(tile + gridDim.x, s ^ 1);   /* stage s^1 was released by the block barrier of the previous iteration */
+    cp_async_wait<1>();
+    mbar_wait(&full_bar[s], (it >> 1) & 1);
+    if (live) {
 #else
     const int s = it & 1;
     issue(tile + gridDim.x, s ^ 1);
@@ -216,6 +289,9 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
       ls = st[s].f[20][tid];
       meta = st[s].meta[tid];
     }
+#if HHD_NEURON_PREFETCH == 2
+    __syncthreads();   /* stage s is free again: thread 0 may aim the next bulk copies at it one iteration from now */
+#endif
     if (live) {
       /* ---- finish step k-1 -------------------------------------------------------------------------------- */
       if (P.accum == HHD_ACCUM_FIXED) {
@@ -273,15 +349,19 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     bool spiked = false, wcross = false, bad = false;
     if (live) {
       /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
+#if !(HHD_EXPERIMENT & 2)
       hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
+#endif
       bad = !(isfinite(x[0]) && isfinite(x[1]));
       /* ---- slot `thresholds` (:304, 306) --------------------------------------------------------------------- */
       const int lastk = meta >> 2;
       spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
+#if !(HHD_EXPERIMENT & 1)
       SubExpr sx;
       hhd_subexpr(P.cc, p, x, sx);
       const double band = hhd_div(sx.D0, p.tauw);
       wcross = (x[1] > sx.w_V - band) && (x[1] < sx.w_V + band) && (x[0] <= p.VT);
+#endif
 #pragma unroll
       for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
       P.meta[i] = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0);
@@ -357,14 +437,14 @@ __global__ void __launch_bounds__(STP_BLOCK) k_stp(const __grid_constant__ Param
     const double last = P.last_spike[j];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
     for (long long r = r0 + threadIdx.x; r < r1; r += STP_BLOCK) {
-      double u = P.u[r], R = P.R[r];
-      const int c = P.chan[r];
-      const double amp = hhd_stp_update(u, R, P.U[r], P.tau_rec[r], P.tau_fac[r], P.gmax[r], P.cc.gsyn[c], P.pfail[r], t,
-                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)P.orig[r]),
+      SynStp sy = P.stp[r];
+      const SynHot sh = P.hot[r];
+      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t,
+                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig),
                                         (unsigned long long)k);
-      P.u[r] = u;
-      P.R[r] = R;
-      P.amp[r] = amp;
+      P.stp[r].u = sy.u;
+      P.stp[r].R = sy.R;
+      P.hot[r].amp = amp;
     }
     if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
   }
@@ -408,17 +488,17 @@ __global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__
     const double last = P.last_spike[j];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
     for (long long r = r0 + threadIdx.x; r < r1; r += STP_BLOCK) {
-      double u = P.u[r], R = P.R[r];
-      const int c = P.chan[r];
-      const double amp = hhd_stp_update(u, R, P.U[r], P.tau_rec[r], P.tau_fac[r], P.gmax[r], P.cc.gsyn[c], P.pfail[r], t,
-                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)P.orig[r]),
+      SynStp sy = P.stp[r];
+      const SynHot sh = P.hot[r];
+      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t,
+                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig),
                                         (unsigned long long)k);
-      P.u[r] = u;
-      P.R[r] = R;
-      P.amp[r] = amp;
-      if (P.delay[r] == 0) {
+      P.stp[r].u = sy.u;
+      P.stp[r].R = sy.R;
+      P.hot[r].amp = amp;
+      if (sh.delay == 0) {
         ++delivered0;
-        if (amp != 0.0) add_increment(P, c, P.tgt[r], amp);
+        if (amp != 0.0) add_increment(P, sh.chan, sh.tgt, amp);
       }
     }
     if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
@@ -455,11 +535,14 @@ __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant
     for (long long rb = s0; rb < s1; rb += 32) {
       const long long r = rb + lane;
       int d = 0x7fffffff;
-      if (r < s1) d = P.delay[r];
+      SynHot sh;
+      if (r < s1) {
+        sh = P.hot[r];                                         /* one 16-byte load: target, delay, channel, amplitude */
+        d = sh.delay;
+      }
       if (d == age) {
-        const double a = P.amp[r];
         ++delivered;
-        if (a != 0.0) add_increment(P, P.chan[r], P.tgt[r], a);
+        if (sh.amp != 0.0) add_increment(P, sh.chan, sh.tgt, sh.amp);
       }
       if (__all_sync(0xffffffffu, d > age)) break;            /* rows are sorted by delay */
     }
@@ -629,8 +712,9 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   P.refr_steps = (int)hhd_timestep(cfg->refractory_ms, cfg->dt_ms);
   P.cc.window_ms = cfg->block_window_ms;
   int rc = 0;
-  for (int p = 0; p < HHD_N_PARAMS && !rc; ++p) rc = dev_alloc(h, &P.par[p], h->N);
-  for (int v = 0; v < 8 && !rc; ++v) rc = dev_alloc(h, &P.x[v], h->N);
+  const size_t n_pad = (size_t)((h->N + NEURON_BLOCK - 1) / NEURON_BLOCK) * NEURON_BLOCK;   /* whole tiles for the bulk copies */
+  for (int p = 0; p < HHD_N_PARAMS && !rc; ++p) rc = dev_alloc(h, &P.par[p], n_pad);
+  for (int v = 0; v < 8 && !rc; ++v) rc = dev_alloc(h, &P.x[v], n_pad);
   if (!rc) rc = dev_alloc(h, &P.last_spike, h->NG, false);
   if (!rc) rc = dev_alloc(h, &P.meta, h->N, false);
   unsigned char* ho = nullptr;
@@ -745,24 +829,31 @@ __global__ void k_syn_keys(long long nsyn, const int* src, const int* tgt, const
 
 __global__ void k_syn_gather(long long nsyn, const unsigned long long* keys, const unsigned int* perm, const int* tgt,
                              const unsigned char* chan, const double* gmax, const double* U, const double* tau_rec,
-                             const double* tau_fac, const double* pfail, int lo, int* o_tgt, unsigned short* o_delay,
-                             unsigned char* o_chan, double* o_gmax, double* o_U, double* o_tau_rec, double* o_tau_fac,
-                             double* o_pfail, double* o_u, double* o_R, double* o_amp) {
+                             const double* tau_fac, const double* pfail, int lo, SynHot* hot, SynStp* stp) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nsyn) return;
   const unsigned int o = perm[r];
-  o_tgt[r] = tgt[o] - lo;
-  o_delay[r] = (unsigned short)(keys[r] & 0xffffull);
-  o_chan[r] = chan[o];
-  o_gmax[r] = gmax[o];
-  const double u0 = U[o];
-  o_U[r] = u0;
-  o_tau_rec[r] = tau_rec[o];
-  o_tau_fac[r] = tau_fac[o];
-  o_pfail[r] = pfail[o];
-  o_u[r] = u0;       /* u = U   (codes/CortexNetwork.py:422) */
-  o_R[r] = 1.0;      /* R = 1   (:424) */
-  o_amp[r] = 0.0;
+  SynHot h;
+  h.tgt = tgt[o] - lo;
+  h.delay = (unsigned short)(keys[r] & 0xffffull);
+  h.chan = chan[o];
+  h.pad = 0;
+  h.amp = 0.0;
+  hot[r] = h;
+  SynStp y;
+  y.U = U[o]; y.tau_rec = tau_rec[o]; y.tau_fac = tau_fac[o]; y.gmax = gmax[o]; y.pfail = pfail[o];
+  y.u = y.U;       /* u = U   (codes/CortexNetwork.py:422) */
+  y.R = 1.0;       /* R = 1   (:424) */
+  y.orig = o; y.pad = 0;
+  stp[r] = y;
+}
+
+/* one field of the synapse records, scattered back to the caller's synapse order (hhd_read_syn_state) */
+__global__ void k_syn_field(long long nsyn, const SynHot* hot, const SynStp* stp, int which, double* out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nsyn) return;
+  const unsigned int o = stp[r].orig;
+  out[o] = which == HHD_SYN_U ? stp[r].u : which == HHD_SYN_R ? stp[r].R : which == HHD_SYN_A ? hot[r].amp : (double)hot[r].delay;
 }
 
 /* row_ptr[j] = first sorted position whose source is >= j */
@@ -783,7 +874,7 @@ __global__ void k_syn_rows(long long nsyn, const unsigned long long* keys, int N
 }
 
 /* row_bkt[j][b] = offset inside row j of the first synapse whose delay is >= b * width (rows are sorted by delay) */
-__global__ void k_syn_buckets(int NG, const long long* row_ptr, const unsigned short* delay, int width, unsigned int* row_bkt) {
+__global__ void k_syn_buckets(int NG, const long long* row_ptr, const SynHot* hot, int width, unsigned int* row_bkt) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (long long)NG * DELAY_BUCKETS) return;
   const int j = (int)(q / DELAY_BUCKETS), b = (int)(q % DELAY_BUCKETS);
@@ -792,7 +883,7 @@ __global__ void k_syn_buckets(int NG, const long long* row_ptr, const unsigned s
   long long lo = r0, hi = r1;
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
-    if ((int)delay[mid] < want) lo = mid + 1; else hi = mid;
+    if ((int)hot[mid].delay < want) lo = mid + 1; else hi = mid;
   }
   row_bkt[q] = (unsigned int)(lo - r0);
 }
@@ -838,22 +929,10 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (long long)nsyn, 0, bits, h->stream);
     if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "radix sort failed: %s", cudaGetErrorString(e));
   }
-  int* o_tgt = nullptr; unsigned short* o_delay = nullptr; unsigned char* o_chan = nullptr;
-  double *o_gmax = nullptr, *o_U = nullptr, *o_trec = nullptr, *o_tfac = nullptr, *o_pf = nullptr;
-  rc = dev_alloc(h, &o_tgt, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_delay, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_chan, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_gmax, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_U, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_trec, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_tfac, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &o_pf, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &P.u, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &P.R, (size_t)nsyn, false);
-  if (!rc) rc = dev_alloc(h, &P.amp, (size_t)nsyn, false);
+  rc = dev_alloc(h, &P.hot, (size_t)nsyn, false);
+  if (!rc) rc = dev_alloc(h, &P.stp, (size_t)nsyn, false);
   if (rc) return rc;
-  if (nsyn) k_syn_gather<<<grid, T, 0, h->stream>>>(nsyn, keys2, vals2, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, lo, o_tgt, o_delay,
-                                                     o_chan, o_gmax, o_U, o_trec, o_tfac, o_pf, P.u, P.R, P.amp);
+  if (nsyn) k_syn_gather<<<grid, T, 0, h->stream>>>(nsyn, keys2, vals2, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, lo, P.hot, P.stp);
   k_syn_rows<<<(h->NG + 1 + T - 1) / T, T, 0, h->stream>>>(nsyn, keys2, h->NG, const_cast<long long*>(P.row_ptr),
                                                             const_cast<unsigned char*>(P.has_out), h->has_out_given ? 0 : 1);
   CU(cudaGetLastError());
@@ -864,14 +943,12 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     if (rc) return rc;
     P.bkt_width = (maxd + 1 + DELAY_BUCKETS - 1) / DELAY_BUCKETS;
     const long long nq = (long long)h->NG * DELAY_BUCKETS;
-    k_syn_buckets<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, o_delay, P.bkt_width, bkt);
+    k_syn_buckets<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, P.bkt_width, bkt);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     P.row_bkt = bkt;
   }
-  P.tgt = o_tgt; P.delay = o_delay; P.chan = o_chan; P.gmax = o_gmax; P.U = o_U; P.tau_rec = o_trec; P.tau_fac = o_tfac; P.pfail = o_pf;
-  P.orig = vals2;
-  dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, derr); dev_free(h, dmaxd); dev_free(h, tmp);
+  dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, vals2); dev_free(h, derr); dev_free(h, dmaxd); dev_free(h, tmp);
   P.max_delay = maxd;
   P.syn_id_base = syn_id_base;
   h->nsyn = nsyn;
@@ -1400,23 +1477,17 @@ extern "C" int hhd_write_state(hhd_handle h, int32_t var, const double* in) {
 
 extern "C" int hhd_read_syn_state(hhd_handle h, int32_t which, double* out) {
   if (!h || !out) return fail(h, HHD_E_ARG, "null argument");
+  if (which < HHD_SYN_U || which > HHD_SYN_DELAY_STEPS) return fail(h, HHD_E_ARG, "unknown synapse variable %d", which);
   cudaSetDevice(h->cfg.device);
   if (!h->nsyn) return HHD_OK;
-  std::vector<unsigned int> orig((size_t)h->nsyn);
-  CU(cudaMemcpyAsync(orig.data(), h->P.orig, (size_t)h->nsyn * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (which == HHD_SYN_DELAY_STEPS) {
-    std::vector<unsigned short> d((size_t)h->nsyn);
-    CU(cudaMemcpyAsync(d.data(), h->P.delay, (size_t)h->nsyn * 2, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    for (size_t r = 0; r < d.size(); ++r) out[orig[r]] = (double)d[r];
-    return HHD_OK;
-  }
-  const double* src = which == HHD_SYN_U ? h->P.u : which == HHD_SYN_R ? h->P.R : which == HHD_SYN_A ? h->P.amp : nullptr;
-  if (!src) return fail(h, HHD_E_ARG, "unknown synapse variable %d", which);
-  std::vector<double> tmp((size_t)h->nsyn);
-  CU(cudaMemcpyAsync(tmp.data(), src, (size_t)h->nsyn * 8, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  for (size_t r = 0; r < tmp.size(); ++r) out[orig[r]] = tmp[r];
+  double* tmp = nullptr;
+  int rc = dev_alloc(h, &tmp, (size_t)h->nsyn, false);
+  if (rc) return rc;
+  k_syn_field<<<(unsigned)((h->nsyn + 255) / 256), 256, 0, h->stream>>>(h->nsyn, h->P.hot, h->P.stp, which, tmp);
+  cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)h->nsyn * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  dev_free(h, tmp);
+  if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "read_syn_state failed: %s", cudaGetErrorString(e));
   return HHD_OK;
 }
 
