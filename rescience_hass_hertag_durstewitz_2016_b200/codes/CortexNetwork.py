@@ -192,7 +192,9 @@ class CortexNetwork:
             for i in range(n_inp):
                 lamb = 1000 / freq
                 n_draw = int(round(2 * (stop - start) / lamb, 0))
-                t = start + np.cumsum(np.clip(-lamb * np.log(1 - np.random.rand(n_draw)), self.time_step, np.nan))
+                # np.clip(x, time_step, np.NaN) in the reference (:547): with the numpy it pins (1.16) a NaN bound is ignored,
+                # i.e. intervals are only bounded below by one time step
+                t = start + np.cumsum(np.maximum(-lamb * np.log(1 - np.random.rand(n_draw)), self.time_step))
                 t = t[t < stop]
                 spk_t.extend(t)
                 spk_src.extend([n_tot + i] * len(t))
