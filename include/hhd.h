@@ -80,7 +80,9 @@ typedef struct {
   int32_t device;             /* CUDA device ordinal */
   int32_t rank, n_ranks;      /* column partition over GPUs; 0,1 for a single GPU */
   int32_t record_spikes;      /* SpikeMonitor active at start    codes/CortexNetwork.py:487 */
-  int32_t reserved[7];
+  int32_t instance_size;      /* > 0: the n_neurons are n_neurons/instance_size INDEPENDENT networks of this many neurons
+                                 (no synapse crosses an instance): BASELINE config 2, one thread-block cluster each */
+  int32_t reserved[6];
 } hhd_config;
 
 /* Per-neuron parameter rows of hhd_set_neurons (each a length-n_neurons fp64 array).

@@ -24,6 +24,7 @@
  * u, R, amplitude, original index uint32 (≈ 75 B).
  */
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -45,9 +46,13 @@
 #define STP_BLOCK 128
 #define DELIVER_BLOCK 128
 #define STEPS_PER_GRAPH 50
+#define RES_BLOCK 128          /* threads (= neurons) per CTA of the cluster-resident plan */
+#define RES_MAX_CLUSTER 16
 #define DELAY_BUCKETS 16
 
 enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_N };
+#define CNT_SLOTS 256   /* the delivery counter is spread over 256 addresses: thousands of warps bump it every step, and
+                           same-address atomics serialise in one L2 slice */
 enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2 };
 
 struct MonDesc {
@@ -106,7 +111,11 @@ struct Params {
   const unsigned int* ext_id;
   MonDesc* mon;                /* [MAX_MON] device */
   unsigned long long* counters;
+  unsigned long long* del_slots;  /* [CNT_SLOTS] */
   const long long* base_step;
+  /* cluster-resident plan: the network is n_inst independent instances of inst_size neurons, one thread-block cluster each */
+  int inst_size, n_inst, res_cap, res_cluster;
+  unsigned int* res_store;     /* [n_inst][2 + W + 2*res_cap] head, pad, end[W], neuron[cap], step[cap]: the instance's spike list between launches */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------- */
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant
     }
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
-  if (lane == 0 && delivered) atomicAdd(&P.counters[CNT_DELIVERIES], delivered);
+  if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
 
   /* SpikeGeneratorGroup events of this step: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
   if (P.ext_ptr && k >= P.ext_first && k <= P.ext_last) {
@@ -562,6 +571,274 @@ __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant
         if (mask & (1 << c)) add_increment(P, c, P.ext_tgt[e], g * P.cc.gsyn[c]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && e1 > e0) atomicAdd(&P.counters[CNT_EXT], (unsigned long long)(e1 - e0));
+  }
+}
+
+
+/* ================================================================================================================== *
+ * Cluster-resident plan (HHD_PLAN_RESIDENT): one thread-block cluster simulates one independent network instance of up
+ * to 16 x 128 neurons for a whole segment of time steps inside ONE launch.  State and parameters live in registers,
+ * pending conductance increments and the instance's active-spike list in (distributed) shared memory, and the two
+ * phases of a step are separated by the hardware cluster barrier (~0.2 us) instead of kernel boundaries (~3 us each).
+ * This is the latency-bound regime: the reference's own 1000-neuron column (BASELINE configs 0-1) and batches of
+ * independent instances (config 2, one cluster per instance).  Same arithmetic, same slot order, same results as the
+ * grid-wide plan.  Requires max_delay < refractory steps (true for any single column).
+ * ================================================================================================================== */
+namespace cg = cooperative_groups;
+
+struct ResList {                 /* lives in the shared memory of CTA 0 of the cluster */
+  unsigned int head;             /* spikes appended so far (monotone) */
+  unsigned int pad;
+};
+
+template <int METHOD>
+__global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant__ Params P, const int n_steps) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  /* layout: pend[3][128] (8 B each) | MonDesc[MAX_MON] | ResList | end[W] | neuron[cap] | step[cap] */
+  unsigned long long* pend_sh = reinterpret_cast<unsigned long long*>(smem_raw);
+  MonDesc* mon_sh = reinterpret_cast<MonDesc*>(pend_sh + 3 * RES_BLOCK);
+  ResList* list_sh = reinterpret_cast<ResList*>(mon_sh + MAX_MON);
+  unsigned int* end_sh = reinterpret_cast<unsigned int*>(list_sh + 1);
+  int* lneuron_sh = reinterpret_cast<int*>(end_sh + P.W);
+  int* lstep_sh = lneuron_sh + P.res_cap;
+
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31;
+  const int CS = P.res_cluster;
+  const int rank = (int)cluster.block_rank();
+  const int inst = blockIdx.x / CS;
+  const int il = rank * RES_BLOCK + tid;                 /* index inside the instance */
+  const bool live = il < P.inst_size;
+  const int i = inst * P.inst_size + il;                 /* local neuron index of this handle */
+  const int cthreads = CS * RES_BLOCK, ctid = rank * RES_BLOCK + tid;
+  const int cwarps = cthreads >> 5, cwid = ctid >> 5;
+  const unsigned cap_mask = (unsigned)P.res_cap - 1u;
+  const long long k0 = *P.base_step;
+
+  /* remote views of CTA 0's list */
+  ResList* L = cluster.map_shared_rank(list_sh, 0);
+  unsigned int* Lend = cluster.map_shared_rank(end_sh, 0);
+  int* Lneuron = cluster.map_shared_rank(lneuron_sh, 0);
+  int* Lstep = cluster.map_shared_rank(lstep_sh, 0);
+
+  for (int q = tid; q < 3 * RES_BLOCK; q += RES_BLOCK) pend_sh[q] = 0ull;
+  if (tid < P.n_mon) mon_sh[tid] = P.mon[tid];
+  unsigned int* store = P.res_store + (size_t)inst * (2 + P.W + 2 * P.res_cap);
+  if (rank == 0) {
+    if (tid == 0) { list_sh->head = store[0]; list_sh->pad = 0; }
+    for (int q = tid; q < P.W; q += RES_BLOCK) end_sh[q] = store[2 + q];
+    for (int q = tid; q < P.res_cap; q += RES_BLOCK) { lneuron_sh[q] = (int)store[2 + P.W + q]; lstep_sh[q] = (int)store[2 + P.W + P.res_cap + q]; }
+  }
+
+  double x[8];
+  NeuronPar p;
+  double ls = 0.0;
+  int meta = 0;
+  bool has_out = false;
+  if (live) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
+    p = load_par(P, i);
+    ls = P.last_spike[P.off + i];
+    meta = P.meta[i];
+    has_out = P.has_out[P.off + i] != 0;
+  }
+  unsigned long long n_events = 0, n_deliv = 0, n_ext = 0;
+  unsigned n_spk = 0, n_wc = 0, n_bad = 0;
+  cluster.sync();
+
+  for (int s = 0; s <= n_steps; ++s) {
+    const long long k = k0 + s;
+    const double t = (double)k * P.dt;
+    /* ---------------- phase 1: finish step k-1, then (if s < n_steps) slots start / groups / thresholds of step k ------ */
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const unsigned long long raw = pend_sh[c * RES_BLOCK + tid];
+        if (raw) {
+          const double inc = P.accum == HHD_ACCUM_FIXED ? (double)(long long)raw * (1.0 / 1099511627776.0) : __longlong_as_double((long long)raw);
+          x[2 + 2 * c] += inc;
+          x[3 + 2 * c] += inc;
+          pend_sh[c * RES_BLOCK + tid] = 0ull;
+        }
+      }
+      if (meta & FLAG_SPIKED) {
+        x[0] = p.Vr;
+        x[1] += p.b;
+        if (has_out) {                                   /* p5: last_spike_pre = t of the spike's step */
+          ls = (double)(k - 1) * P.dt;
+          P.last_spike[P.off + i] = ls;
+        }
+      }
+      if (meta & FLAG_WCROSS) {
+        SubExpr sx;
+        hhd_subexpr(P.cc, p, x, sx);
+        x[1] = sx.w_V - hhd_div(sx.D0, p.tauw);
+      }
+      meta &= ~3;
+    }
+    if (s == n_steps) break;
+
+    for (int m = 0; m < P.n_mon; ++m) {
+      const MonDesc& md = mon_sh[m];
+      if (!md.active) continue;
+      const long long sample = k - md.k0;
+      if (sample < 0 || sample >= md.capacity) {
+        if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+        continue;
+      }
+      int slot = -1;
+      if (live) slot = md.slot ? md.slot[i] : i;
+      double v = 0.0;
+      if (slot >= 0) v = hhd_var_value(P.cc, p, x, md.var, ls);
+      if (md.reduce == HHD_REDUCE_NONE) {
+        if (slot >= 0) md.buf[sample * md.n_idx + slot] = v;
+      } else {
+        const double ws = warp_sum(v);
+        if (lane == 0 && ws != 0.0) atomicAdd(&md.buf[sample], ws);
+      }
+    }
+
+    bool spiked = false, wcross = false;
+    if (live) {
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
+      n_bad += !(isfinite(x[0]) && isfinite(x[1]));
+      const int lastk = meta >> 2;
+      spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
+      SubExpr sx;
+      hhd_subexpr(P.cc, p, x, sx);
+      const double band = hhd_div(sx.D0, p.tauw);
+      wcross = (x[1] > sx.w_V - band) && (x[1] < sx.w_V + band) && (x[0] <= p.VT);
+      meta = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0);
+      n_wc += wcross;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, spiked);
+    if (bal) {
+      /* the instance's list (delivery) and the global ring (SpikeMonitor) */
+      unsigned lbase = 0;
+      unsigned long long gbase = 0;
+      if (lane == 0) {
+        lbase = atomicAdd(&L->head, (unsigned)__popc(bal));
+        gbase = atomicAdd(P.head, (unsigned long long)__popc(bal));
+      }
+      lbase = __shfl_sync(0xffffffffu, lbase, 0);
+      gbase = __shfl_sync(0xffffffffu, gbase, 0);
+      if (spiked) {
+        const unsigned o = __popc(bal & ((1u << lane) - 1u));
+        Lneuron[(lbase + o) & cap_mask] = P.off + i;
+        Lstep[(lbase + o) & cap_mask] = (int)k;
+        const unsigned gpos = (unsigned)(gbase + o) & P.cap_mask;
+        P.spk_neuron[gpos] = P.off + i;
+        P.spk_step[gpos] = (int)k;
+        ++n_spk;
+      }
+    }
+    cluster.sync();
+
+    /* ---------------- phase 2: slot `synapses` of step k, all warps of the cluster ---------------------------------- */
+    const unsigned hi = L->head;
+    const unsigned lo_new = Lend[(k + P.W - 1) % P.W];
+    const unsigned lo = Lend[(k + 1) % P.W];
+    /* spikes of this step: p0..p6 for the whole row (threads of the cluster stride over it), zero-delay deliveries */
+    for (unsigned sp = lo_new; sp != hi; ++sp) {
+      const int j = Lneuron[sp & cap_mask];
+      const double last = P.last_spike[j];
+      const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+      for (long long r = r0 + ctid; r < r1; r += cthreads) {
+        SynStp sy = P.stp[r];
+        const SynHot sh = P.hot[r];
+        const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t,
+                                          last, P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)k);
+        P.stp[r].u = sy.u;
+        P.stp[r].R = sy.R;
+        P.hot[r].amp = amp;
+        if (sh.delay == 0) {
+          ++n_deliv;
+          if (amp != 0.0) {
+            const int tl = sh.tgt - inst * P.inst_size;
+            unsigned long long* dst = cluster.map_shared_rank(pend_sh, tl / RES_BLOCK) + sh.chan * RES_BLOCK + (tl % RES_BLOCK);
+            if (P.accum == HHD_ACCUM_FIXED) atomicAdd(dst, (unsigned long long)__double2ll_rn(amp * 1099511627776.0));
+            else atomicAdd(reinterpret_cast<double*>(dst), amp);
+          }
+        }
+      }
+      if (ctid == 0) n_events += (unsigned long long)(r1 - r0);
+    }
+    /* older spikes: one warp each; bucket index -> due segment of the delay-sorted row */
+    for (unsigned sp = lo + cwid; (int)(lo_new - sp) > 0; sp += cwarps) {
+      const int j = Lneuron[sp & cap_mask];
+      const int age = (int)(k - (long long)Lstep[sp & cap_mask]);
+      if (age > P.max_delay) continue;
+      const long long r0 = P.row_ptr[j];
+      const int b = age / P.bkt_width;
+      const long long s0 = r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b];
+      const long long s1 = b + 1 < DELAY_BUCKETS ? r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b + 1] : P.row_ptr[j + 1];
+      for (long long rb = s0; rb < s1; rb += 32) {
+        const long long r = rb + lane;
+        int d = 0x7fffffff;
+        SynHot sh;
+        if (r < s1) { sh = P.hot[r]; d = sh.delay; }
+        if (d == age) {
+          ++n_deliv;
+          if (sh.amp != 0.0) {
+            const int tl = sh.tgt - inst * P.inst_size;
+            unsigned long long* dst = cluster.map_shared_rank(pend_sh, tl / RES_BLOCK) + sh.chan * RES_BLOCK + (tl % RES_BLOCK);
+            if (P.accum == HHD_ACCUM_FIXED) atomicAdd(dst, (unsigned long long)__double2ll_rn(sh.amp * 1099511627776.0));
+            else atomicAdd(reinterpret_cast<double*>(dst), sh.amp);
+          }
+        }
+        if (__all_sync(0xffffffffu, d > age)) break;
+      }
+    }
+    /* SpikeGeneratorGroup events of this step that target this instance */
+    if (P.ext_ptr && k >= P.ext_first && k <= P.ext_last) {
+      const int e0 = P.ext_ptr[k - P.ext_first], e1 = P.ext_ptr[k - P.ext_first + 1];
+      for (int e = e0 + ctid; e < e1; e += cthreads) {
+        const int tl = P.ext_tgt[e] - inst * P.inst_size;
+        if (tl < 0 || tl >= P.inst_size) continue;
+        const double failure = hhd_philox_u01(P.seed, (unsigned long long)P.ext_id[e], (unsigned long long)k, 1) < P.ext_pfail[e] ? 1.0 : 0.0;
+        const unsigned char mask = P.ext_mask[e];
+        const double g = P.ext_gmax[e] * (1.0 - failure);
+        ++n_ext;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (mask & (1 << c)) {
+            const double inc = g * P.cc.gsyn[c];
+            unsigned long long* dst = cluster.map_shared_rank(pend_sh, tl / RES_BLOCK) + c * RES_BLOCK + (tl % RES_BLOCK);
+            if (P.accum == HHD_ACCUM_FIXED) atomicAdd(dst, (unsigned long long)__double2ll_rn(inc * 1099511627776.0));
+            else atomicAdd(reinterpret_cast<double*>(dst), inc);
+          }
+      }
+    }
+    if (rank == 0 && tid == 0) end_sh[k % P.W] = hi;
+    cluster.sync();
+  }
+
+  /* ---------------- write back ---------------------------------------------------------------------------------------- */
+  if (live) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
+    P.meta[i] = meta;
+  }
+  if (rank == 0) {
+    if (tid == 0) store[0] = list_sh->head;
+    for (int q = tid; q < P.W; q += RES_BLOCK) store[2 + q] = end_sh[q];
+    for (int q = tid; q < P.res_cap; q += RES_BLOCK) { store[2 + P.W + q] = (unsigned)lneuron_sh[q]; store[2 + P.W + P.res_cap + q] = (unsigned)lstep_sh[q]; }
+  }
+  n_events = (unsigned long long)warp_sum((double)n_events);
+  n_deliv = (unsigned long long)warp_sum((double)n_deliv);
+  n_ext = (unsigned long long)warp_sum((double)n_ext);
+  n_spk = __reduce_add_sync(0xffffffffu, n_spk);
+  n_wc = __reduce_add_sync(0xffffffffu, n_wc);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  if (lane == 0) {
+    if (n_events) atomicAdd(&P.counters[CNT_SYN_EVENTS], n_events);
+    if (n_deliv) atomicAdd(&P.del_slots[(blockIdx.x * 4 + (tid >> 5)) & (CNT_SLOTS - 1)], n_deliv);
+    if (n_ext) atomicAdd(&P.counters[CNT_EXT], n_ext);
+    if (n_spk) atomicAdd(&P.counters[CNT_SPIKES], (unsigned long long)n_spk);
+    if (n_wc) atomicAdd(&P.counters[CNT_WCROSS], (unsigned long long)n_wc);
+    if (n_bad) atomicAdd(&P.counters[CNT_NONFINITE], (unsigned long long)n_bad);
   }
 }
 
@@ -625,6 +902,9 @@ struct hhd_engine {
   cudaGraphExec_t graph_exec = nullptr;
   hhd_counters cnt;
   int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
+  bool cross_instance = false; /* some synapse joins two instances: the resident plan is not applicable */
+  bool resident = false;       /* HHD_PLAN_RESIDENT chosen */
+  int res_smem = 0;
   bool fused = false;          /* spike-time STP runs inside k_deliver (max_delay < refractory steps) */
   int kernels_per_step = 3;
 };
@@ -727,6 +1007,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (!rc) rc = dev_alloc(h, &P.head, 1);
   if (!rc) rc = dev_alloc(h, &h->d_base_step, 1);
   if (!rc) rc = dev_alloc(h, &h->d_counters, CNT_N);
+  if (!rc) rc = dev_alloc(h, &P.del_slots, CNT_SLOTS);
   if (!rc) rc = dev_alloc(h, &h->d_mon, MAX_MON);
   if (rc) { std::string m = h->err; hhd_destroy(h); g_create_err = m; return rc; }
   P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
@@ -805,10 +1086,10 @@ extern "C" int hhd_set_channels(hhd_handle h, const double tau_on[3], const doub
 }
 
 /* ---- synapse setup on the device: validate, sort by (source, delay) with a stable radix sort, gather into CSR ----- */
-enum { SYNERR_SRC = 1, SYNERR_TGT = 2, SYNERR_CHAN = 4, SYNERR_DELAY = 8, SYNERR_TAU = 16, SYNERR_DELAY_BIG = 32 };
+enum { SYNERR_SRC = 1, SYNERR_TGT = 2, SYNERR_CHAN = 4, SYNERR_DELAY = 8, SYNERR_TAU = 16, SYNERR_DELAY_BIG = 32, SYNWARN_CROSS = 64 };
 
 __global__ void k_syn_keys(long long nsyn, const int* src, const int* tgt, const unsigned char* chan, const double* tau_rec,
-                           const double* tau_fac, const double* delay_ms, double dt, int NG, int lo, int hi,
+                           const double* tau_fac, const double* delay_ms, double dt, int NG, int lo, int hi, int inst_size,
                            unsigned long long* keys, unsigned int* vals, unsigned int* err, int* maxd) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nsyn) return;
@@ -821,6 +1102,7 @@ __global__ void k_syn_keys(long long nsyn, const int* src, const int* tgt, const
   if (!(tau_rec[k] > 0) || !(tau_fac[k] > 0)) e |= SYNERR_TAU;
   long long d = e & SYNERR_DELAY ? 0 : hhd_delay_steps(delay_ms[k], dt);
   if (d > 65535) { e |= SYNERR_DELAY_BIG; d = 65535; }
+  if (!e && inst_size > 0 && (s - lo) / inst_size != (tgt[k] - lo) / inst_size) e |= SYNWARN_CROSS;
   if (e) atomicOr(err, e);
   atomicMax(maxd, (int)d);
   keys[k] = ((unsigned long long)(unsigned int)(e & SYNERR_SRC ? 0 : s) << 16) | (unsigned long long)d;
@@ -905,12 +1187,13 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
   if (rc) return rc;
   const int T = 256;
   const unsigned grid = (unsigned)((nsyn + T - 1) / T);
-  if (nsyn) k_syn_keys<<<grid, T, 0, h->stream>>>(nsyn, src, tgt, chan, tau_rec, tau_fac, delay_ms, h->cfg.dt_ms, h->NG, lo, hi, keys, vals, derr, dmaxd);
+  if (nsyn) k_syn_keys<<<grid, T, 0, h->stream>>>(nsyn, src, tgt, chan, tau_rec, tau_fac, delay_ms, h->cfg.dt_ms, h->NG, lo, hi, h->cfg.instance_size, keys, vals, derr, dmaxd);
   unsigned int err = 0;
   int maxd = 0;
   CU(cudaMemcpyAsync(&err, derr, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(&maxd, dmaxd, 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (err & SYNWARN_CROSS) { h->cross_instance = true; err &= ~SYNWARN_CROSS; }
   if (err) {
     dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, vals2); dev_free(h, derr); dev_free(h, dmaxd);
     return fail(h, HHD_E_ARG, "invalid synapse arrays:%s%s%s%s%s%s", err & SYNERR_SRC ? " source out of range;" : "",
@@ -1229,7 +1512,58 @@ static int finalize_setup(hhd_handle h) {
     P.row_bkt = bkt;
     P.bkt_width = 1;
   }
+  {
+    const int inst = h->cfg.instance_size > 0 ? h->cfg.instance_size : h->N;
+    const bool can = h->cfg.n_ranks == 1 && P.max_delay < P.refr_steps && inst <= RES_MAX_CLUSTER * RES_BLOCK && h->N % inst == 0 &&
+                     !h->cross_instance && h->NG == h->N;
+    if (h->cfg.plan == HHD_PLAN_RESIDENT && !can)
+      return fail(h, HHD_E_ARG, "HHD_PLAN_RESIDENT needs independent instances of at most %d neurons (instance_size), no synapse "
+                  "between instances, max delay < refractory period and a single rank", RES_MAX_CLUSTER * RES_BLOCK);
+    h->resident = can && (h->cfg.plan == HHD_PLAN_RESIDENT || (h->cfg.plan == HHD_PLAN_AUTO && !getenv("HHD_NO_RESIDENT")));
+    if (h->resident) {
+      P.inst_size = inst;
+      P.n_inst = h->N / inst;
+      int cs = 1;
+      while (cs * RES_BLOCK < inst) cs <<= 1;
+      P.res_cluster = cs;
+      P.res_cap = (int)next_pow2((unsigned long long)std::max(64, 2 * inst));
+      rc = dev_alloc(h, &P.res_store, (size_t)P.n_inst * (2 + P.W + 2 * (size_t)P.res_cap), true);
+      if (rc) return rc;
+      h->res_smem = 3 * RES_BLOCK * 8 + MAX_MON * (int)sizeof(MonDesc) + (int)sizeof(ResList) + P.W * 4 + 2 * P.res_cap * 4 + 16;
+      const void* fn[3] = {(const void*)k_resident<0>, (const void*)k_resident<1>, (const void*)k_resident<2>};
+      for (int q = 0; q < 3; ++q) {
+        CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, h->res_smem));
+        if (cs > 8) CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      }
+    }
+  }
   h->started = true;
+  return 0;
+}
+
+static int launch_resident(hhd_handle h, int n_steps) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof lc);
+  lc.gridDim = dim3((unsigned)(h->P.n_inst * h->P.res_cluster));
+  lc.blockDim = dim3(RES_BLOCK);
+  lc.dynamicSmemBytes = (size_t)h->res_smem;
+  lc.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)h->P.res_cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  cudaError_t e;
+  switch (h->cfg.method) {
+    case HHD_EULER: e = cudaLaunchKernelEx(&lc, k_resident<0>, h->P, n_steps); break;
+    case HHD_RK2: e = cudaLaunchKernelEx(&lc, k_resident<1>, h->P, n_steps); break;
+    default: e = cudaLaunchKernelEx(&lc, k_resident<2>, h->P, n_steps); break;
+  }
+  if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "launch of the cluster-resident kernel failed: %s", cudaGetErrorString(e));
+  k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, n_steps);
+  h->cnt.kernel_launches += 2;
   return 0;
 }
 
@@ -1352,12 +1686,19 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   if (prev_n_mon != h->P.n_mon) h->graph_dirty = true;
   for (Monitor& m : h->mons) if (m.active && m.first_step < 0) m.first_step = h->step;
   CU(cudaMemcpyAsync(h->d_base_step, &h->step, 8, cudaMemcpyHostToDevice, h->stream));
-  if (h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
+  if (!h->resident && h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
 
   CU(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   while (done < n_steps) {
     const long long seg = std::min<long long>(h->seg_steps, n_steps - done);
+    if (h->resident) {
+      if ((rc = launch_resident(h, (int)seg))) return rc;
+      done += seg;
+      CU(cudaGetLastError());
+      if ((rc = drain_spikes(h))) return rc;
+      continue;
+    }
     long long s = 0;
     while (seg - s >= STEPS_PER_GRAPH && h->graph_exec && !h->graph_dirty) {
       CU(cudaGraphLaunch(h->graph_exec, h->stream));
@@ -1384,6 +1725,11 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   unsigned long long c[CNT_N];
   CU(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
   if (c[CNT_OVERFLOW]) return fail(h, HHD_E_CAPACITY, "a monitor buffer overflowed on the device");
+  {
+    unsigned long long slots[CNT_SLOTS];
+    CU(cudaMemcpy(slots, h->P.del_slots, sizeof slots, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < CNT_SLOTS; ++q) c[CNT_DELIVERIES] += slots[q];
+  }
   h->cnt.syn_events = (long long)c[CNT_SYN_EVENTS]; h->cnt.syn_deliveries = (long long)c[CNT_DELIVERIES];
   h->cnt.ext_events = (long long)c[CNT_EXT]; h->cnt.spikes = (long long)c[CNT_SPIKES];
   h->cnt.w_crossings = (long long)c[CNT_WCROSS]; h->cnt.nonfinite = (long long)c[CNT_NONFINITE];
@@ -1403,6 +1749,20 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
   if (prev_n_mon != h->P.n_mon) h->graph_dirty = true;
   for (Monitor& m : h->mons) if (m.active && m.first_step < 0) m.first_step = h->step;
   CU(cudaMemcpyAsync(h->d_base_step, &h->step, 8, cudaMemcpyHostToDevice, h->stream));
+  if (h->resident) {
+    CU(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = launch_resident(h, (int)n_steps))) return rc;
+    CU(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = drain_spikes(h))) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    us[0] = ms * 1e3 / (double)n_steps; us[1] = 0; us[2] = 0;
+    for (Monitor& m : h->mons) if (m.active) m.n_samples += n_steps;
+    h->step += n_steps;
+    h->cnt.steps += n_steps;
+    h->cnt.neuron_updates += n_steps * (long long)h->N;
+    return HHD_OK;
+  }
   std::vector<cudaEvent_t> ev((size_t)n_steps * 3 + 1);
   for (auto& e : ev) CU(cudaEventCreate(&e));
   CU(cudaEventRecord(ev[0], h->stream));

@@ -43,7 +43,7 @@ class Config(C.Structure):
         ("dt_ms", C.c_double), ("method", C.c_int32), ("accum", C.c_int32), ("plan", C.c_int32),
         ("refractory_ms", C.c_double), ("block_window_ms", C.c_double), ("last_spike0_ms", C.c_double),
         ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32), ("n_ranks", C.c_int32),
-        ("record_spikes", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("record_spikes", C.c_int32), ("instance_size", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -90,7 +90,7 @@ class Engine:
 
     def __init__(self, n_neurons, dt_ms, method="rk4", accum="fp64", plan="auto", refractory_ms=5.0,
                  block_window_ms=5.0, last_spike0_ms=-1e8, seed=0, device=0, rank=0, n_ranks=1, n_global=None,
-                 global_offset=0, record_spikes=True, _lib=None, _prefix="hhd_"):
+                 global_offset=0, record_spikes=True, instance_size=0, _lib=None, _prefix="hhd_"):
         self._lib = _lib if _lib is not None else load_library()
         self._prefix = _prefix
         self._h = C.c_void_p()
@@ -110,7 +110,7 @@ class Engine:
             plan=PLANS[plan] if isinstance(plan, str) else int(plan),
             refractory_ms=refractory_ms, block_window_ms=block_window_ms, last_spike0_ms=last_spike0_ms,
             seed=int(seed) & 0xFFFFFFFFFFFFFFFF, device=device, rank=rank, n_ranks=n_ranks,
-            record_spikes=1 if record_spikes else 0)
+            record_spikes=1 if record_spikes else 0, instance_size=int(instance_size))
         rc = self._fn("create")(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             msg = self._fn("last_error", C.c_char_p)(None)

@@ -16,11 +16,19 @@ pytestmark = pytest.mark.gpu
 STATE = ["V", "w", "g_AMPA_on", "g_AMPA_off", "g_GABA_on", "g_GABA_off", "g_NMDA_on", "g_NMDA_off"]
 
 
+PLANS = ["graph", "resident"]     # grid-wide kernels in CUDA graphs / one persistent thread-block cluster per instance
+
+
+def gpu_cpu(g, plan, **kw):
+    return make_engine("gpu", g, plan=plan, **kw), make_engine("cpu", g, **kw)
+
+
+@pytest.mark.parametrize("plan", PLANS)
 @pytest.mark.parametrize("method", ["euler", "rk2", "rk4"])
-def test_uncoupled_neurons_bit_exact(method):
+def test_uncoupled_neurons_bit_exact(method, plan):
     g = load_golden("net_n200_s0")
     idc = default_idc(g) * 1.5          # enough drive that most cells fire without synaptic input
-    gpu, cpu = pair(g, with_synapses=False, idc=idc, method=method)
+    gpu, cpu = gpu_cpu(g, plan, with_synapses=False, idc=idc, method=method)
     for e in (gpu, cpu):
         e.run(3000)
     gi, gs = gpu.spikes()
@@ -34,10 +42,11 @@ def test_uncoupled_neurons_bit_exact(method):
         assert gc[k] == cc[k], k
 
 
+@pytest.mark.parametrize("plan", PLANS)
 @pytest.mark.parametrize("method", ["euler", "rk4"])
-def test_network_fixed_accumulation_bit_exact(method):
+def test_network_fixed_accumulation_bit_exact(method, plan):
     g = load_golden("net_n200_s0")
-    gpu, cpu = pair(g, method=method, accum="fixed", seed=11)
+    gpu, cpu = gpu_cpu(g, plan, method=method, accum="fixed", seed=11)
     for e in (gpu, cpu):
         e.run(12000)
     gi, gs = gpu.spikes()
@@ -69,9 +78,10 @@ def test_multicolumn_long_delays_fixed_bit_exact():
         assert np.array_equal(gpu.read_state(v), cpu.read_state(v)), v
 
 
-def test_network_fp64_accumulation_horizon():
+@pytest.mark.parametrize("plan", PLANS)
+def test_network_fp64_accumulation_horizon(plan):
     g = load_golden("net_n200_s0")
-    gpu, cpu = pair(g, method="rk4", accum="fp64", seed=5)
+    gpu, cpu = gpu_cpu(g, plan, method="rk4", accum="fp64", seed=5)
     # 1) before any target has received two increments in one step the two engines are bit-identical
     for e in (gpu, cpu):
         e.run(400)
@@ -91,12 +101,13 @@ def test_network_fp64_accumulation_horizon():
     assert abs(len(gi) - len(ci)) <= 0.1 * len(ci)
 
 
-def test_monitors_match_oracle():
+@pytest.mark.parametrize("plan", PLANS)
+def test_monitors_match_oracle(plan):
     g = load_golden("net_n200_s0")
     idx = np.array([0, 5, 17, 100, 206], dtype=np.int32)
     res = {}
     for kind in ("gpu", "cpu"):
-        e = make_engine(kind, g, method="rk2", accum="fixed", seed=2)
+        e = make_engine(kind, g, method="rk2", accum="fixed", seed=2, **({"plan": plan} if kind == "gpu" else {}))
         mV = e.add_state_monitor("V", idx)
         mI = e.add_state_monitor("I_tot", None, reduce="sum")
         mA = e.add_state_monitor("g_NMDA", None)
@@ -112,10 +123,11 @@ def test_monitors_match_oracle():
     assert np.allclose(gI, cI, rtol=1e-12, atol=1e-9)   # block-wise summation order differs
 
 
-def test_continue_run_equals_single_run():
+@pytest.mark.parametrize("plan", PLANS)
+def test_continue_run_equals_single_run(plan):
     g = load_golden("net_n200_s0")
-    a = make_engine("gpu", g, method="euler", accum="fixed", seed=9)
-    b = make_engine("gpu", g, method="euler", accum="fixed", seed=9)
+    a = make_engine("gpu", g, method="euler", accum="fixed", seed=9, plan=plan)
+    b = make_engine("gpu", g, method="euler", accum="fixed", seed=9, plan=plan)
     a.run(5000)
     for n in (1, 49, 50, 51, 1849, 3000):
         b.run(n)
@@ -127,7 +139,8 @@ def test_continue_run_equals_single_run():
         assert np.array_equal(a.read_state(v), b.read_state(v)), v
 
 
-def test_external_spike_sources():
+@pytest.mark.parametrize("plan", PLANS)
+def test_external_spike_sources(plan):
     g = load_golden("net_n200_s0")
     groups = golden_groups(g)
     rng = np.random.default_rng(0)
@@ -142,7 +155,7 @@ def test_external_spike_sources():
     pfail = np.full(syn_src.size, 0.3)
     res = {}
     for kind in ("gpu", "cpu"):
-        e = make_engine(kind, g, method="rk2", accum="fixed", seed=4, idc=np.zeros(207))
+        e = make_engine(kind, g, method="rk2", accum="fixed", seed=4, idc=np.zeros(207), **({"plan": plan} if kind == "gpu" else {}))
         e.add_spike_source(n_src, spk_src, spk_t, syn_src, syn_tgt, mask, gmax, pfail)
         e.run(2000)
         res[kind] = (e.spikes(), [e.read_state(v) for v in STATE], e.counters())
@@ -154,11 +167,12 @@ def test_external_spike_sources():
     assert np.array_equal(res["gpu"][0][0], res["cpu"][0][0]) and np.array_equal(res["gpu"][0][1], res["cpu"][0][1])
 
 
-def test_spike_monitor_toggle():
+@pytest.mark.parametrize("plan", PLANS)
+def test_spike_monitor_toggle(plan):
     g = load_golden("net_n200_s0")
     res = {}
     for kind in ("gpu", "cpu"):
-        e = make_engine(kind, g, method="euler", accum="fixed", seed=1, record_spikes=False)
+        e = make_engine(kind, g, method="euler", accum="fixed", seed=1, record_spikes=False, **({"plan": plan} if kind == "gpu" else {}))
         e.run(3000)                                  # transient: spikes not recorded
         assert e.spike_count() == 0
         e.set_spike_monitor_active(True)
@@ -166,3 +180,40 @@ def test_spike_monitor_toggle():
         res[kind] = e.spikes()
     assert len(res["cpu"][0]) > 0 and res["cpu"][1].min() >= 3000
     assert np.array_equal(res["gpu"][0], res["cpu"][0]) and np.array_equal(res["gpu"][1], res["cpu"][1])
+
+
+def test_batched_instances_resident_equals_graph_equals_oracle():
+    """BASELINE config 2: independent instances batched in one engine, one cluster each; every release-failure draw
+    differs between copies (keyed by synapse index), so the copies decorrelate."""
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine, load_codes_network
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_columns
+    from oracle_binding import OracleEngine
+    g = load_golden("net_n200_s0")
+    net = tile_columns(g["NeuPar"], g["V0"], g["SynPar"], g["source_arr"], g["target_arr"], default_idc(g), 5)
+    out = {}
+    for name, cls, kw in (("resident", Engine, dict(plan="resident", instance_size=207)), ("graph", Engine, dict(plan="graph")),
+                          ("cpu", OracleEngine, {})):
+        e = cls(207 * 5, 0.05, method="rk2", accum="fixed", seed=21, **kw)
+        load_codes_network(e, net["NeuPar"], net["V0"], g["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+        m = e.add_state_monitor("I_tot", np.arange(207, 414, dtype=np.int32), reduce="sum")     # LFP of instance 1
+        e.run(6000)
+        out[name] = (e.spikes(), e.read_state("V"), e.read_state("g_NMDA_off"), e.read_monitor(m), e.counters())
+    (ci, cs), cV, cg, clfp, cc = out["cpu"]
+    assert len(ci) > 1000
+    inst = ci // 207
+    assert not np.array_equal(ci[inst == 0] % 207, ci[inst == 1] % 207)         # instances differ
+    for name in ("resident", "graph"):
+        (gi, gs), gV, gg, glfp, gc = out[name]
+        assert np.array_equal(gi, ci) and np.array_equal(gs, cs), name
+        assert np.array_equal(gV, cV) and np.array_equal(gg, cg), name
+        assert np.allclose(glfp, clfp, rtol=1e-12, atol=1e-9), name
+        for k in ("spikes", "syn_events", "syn_deliveries", "w_crossings"):
+            assert gc[k] == cc[k], (name, k)
+
+
+def test_resident_plan_refuses_what_it_cannot_do():
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import HhdError
+    g = load_golden("net_n60x5_s1")          # delays longer than the refractory period
+    e = make_engine("gpu", g, plan="resident")
+    with pytest.raises(HhdError):
+        e.run(10)
