@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--dt", type=float, default=0.05)
     ap.add_argument("--window", type=int, default=2000, help="time steps per bench step")
     ap.add_argument("--accum", default="fp64", choices=["fp64", "fixed"])
+    ap.add_argument("--plan", default="auto", choices=["auto", "graph", "resident"])
+    ap.add_argument("--instances", action="store_true", help="treat every column as an independent instance (config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -85,13 +87,22 @@ def build_workload(args, rank, world, device_synapses=False):
 def make_engine(cls, net, args, seed, **kw):
     from rescience_hass_hertag_durstewitz_2016_b200.engine import load_codes_network
     n = net["NeuPar"].shape[1]
+    if cls.__name__ == "Engine":
+        kw = dict(kw, plan=args.plan, instance_size=net["n_per_column"] if (args.instances or args.workload == "column") else 0)
     e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
     load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
     if "col" in net:
         from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_synapses_device
         col = net["col"]
         dev = "cuda:%d" % kw.get("device", 0)
-        e.set_synapses_dev(*tile_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], net["columns_rank"], net["n_per_column"], dev))
+        off = kw.get("global_offset", 0)
+        if kw.get("n_ranks", 1) > 1:
+            has_out = np.zeros(net["n_per_column"], dtype=np.uint8)
+            has_out[np.unique(col["source_arr"])] = 1
+            e.set_has_outgoing(np.tile(has_out, kw["n_global"] // net["n_per_column"]))
+        e.set_synapses_dev(*tile_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], net["columns_rank"],
+                                                 net["n_per_column"], dev, id_offset=off),
+                           syn_id_base=kw.get("rank", 0) * net["nsyn"])
     return e
 
 
@@ -207,7 +218,7 @@ def workload_config(args, net, world):
                 method=args.method, dt_ms=args.dt, time_steps_per_step=args.window, accumulate=args.accum,
                 monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
                 l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
-                parallelism="%d GPU(s), columns partitioned" % world)
+                parallelism="%d GPU(s), columns partitioned, NCCL all-gather of spike indices every time step" % world if world > 1 else "1 GPU")
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------
@@ -234,7 +245,17 @@ def main():
     net = build_workload(args, rank, world, device_synapses=True)
     n = net["NeuPar"].shape[1]
     t_setup = time.perf_counter()
-    eng = make_engine(Engine, net, args, seed=1 + rank, device=local_rank)
+    if world > 1:
+        # one network partitioned by columns: same seed on every rank, global ids, spike all-gather inside libhhd (NCCL)
+        eng = make_engine(Engine, net, args, seed=1, device=local_rank, rank=rank, n_ranks=world, n_global=n * world,
+                          global_offset=rank * n)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(eng.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        eng.comm_init(bytes(uid.cpu().tolist()))
+    else:
+        eng = make_engine(Engine, net, args, seed=1, device=local_rank)
     lfp = eng.add_state_monitor("I_tot", None, reduce="sum")
     setup_s = time.perf_counter() - t_setup
     S = args.window
@@ -318,7 +339,7 @@ def main():
     achieved = BYTES_PER_NEURON_UPDATE * n / (prof["k_neuron"] * 1e-6) / 1e9
     out = dict(
         metric="neuron_updates_per_s", value=value, unit="neuron-updates/s", n_gpus=world, steps=args.steps,
-        warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype="f64", data="synthetic", config=workload_config(args, net, world),
         syn_events_per_s=syn_ev / (dev_ms * 1e-3), realtime_factor=bio_s / (dev_ms * 1e-3),
         mean_rate_hz=spikes / n_total / bio_s, us_per_time_step=dev_ms * 1e3 / (S * args.steps),

@@ -25,6 +25,9 @@
  */
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#ifdef HHD_WITH_NCCL
+#include <nccl.h>
+#endif
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -113,6 +116,11 @@ struct Params {
   unsigned long long* counters;
   unsigned long long* del_slots;  /* [CNT_SLOTS] */
   const long long* base_step;
+  /* multi-GPU spike exchange (n_ranks > 1): k_neuron appends local spikes to xchg_send = {count, ids...}; after the
+   * all-gather k_append copies every rank's list into the ring */
+  int n_ranks, xchg_cap;
+  int* xchg_send;              /* [1 + xchg_cap] */
+  int* xchg_recv;              /* [n_ranks][1 + xchg_cap] */
   /* cluster-resident plan: the network is n_inst independent instances of inst_size neurons, one thread-block cluster each */
   int inst_size, n_inst, res_cap, res_cluster;
   unsigned int* res_store;     /* [n_inst][2 + W + 2*res_cap] head, pad, end[W], neuron[cap], step[cap]: the instance's spike list between launches */
@@ -378,13 +386,24 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     /* ---- warp-ballot spike compaction: one atomic per warp that has spikes ----------------------------------- */
     const unsigned bal = __ballot_sync(0xffffffffu, spiked);
     if (bal) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(P.head, (unsigned long long)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (spiked) {
-        const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
-        P.spk_neuron[pos] = P.off + i;
-        P.spk_step[pos] = (int)k;
+      if (P.n_ranks > 1) {          /* partitioned network: the step's local spikes go to the all-gather send buffer */
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&P.xchg_send[0], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (spiked) {
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (pos < P.xchg_cap) P.xchg_send[1 + pos] = P.off + i;
+          else atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+        }
+      } else {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.head, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (spiked) {
+          const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
+          P.spk_neuron[pos] = P.off + i;
+          P.spk_step[pos] = (int)k;
+        }
       }
     }
     n_spk += spiked;
@@ -738,8 +757,9 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
 
     /* ---------------- phase 2: slot `synapses` of step k, all warps of the cluster ---------------------------------- */
     const unsigned hi = L->head;
-    const unsigned lo_new = Lend[(k + P.W - 1) % P.W];
-    const unsigned lo = Lend[(k + 1) % P.W];
+    const int kw = (int)((unsigned long long)k % (unsigned)P.W);          /* k mod W once; neighbours by wrap */
+    const unsigned lo_new = Lend[kw == 0 ? P.W - 1 : kw - 1];
+    const unsigned lo = Lend[kw + 1 == P.W ? 0 : kw + 1];
     /* spikes of this step: p0..p6 for the whole row (threads of the cluster stride over it), zero-delay deliveries */
     for (unsigned sp = lo_new; sp != hi; ++sp) {
       const int j = Lneuron[sp & cap_mask];
@@ -811,7 +831,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
           }
       }
     }
-    if (rank == 0 && tid == 0) end_sh[k % P.W] = hi;
+    if (rank == 0 && tid == 0) end_sh[kw] = hi;
     cluster.sync();
   }
 
@@ -839,6 +859,36 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
     if (n_spk) atomicAdd(&P.counters[CNT_SPIKES], (unsigned long long)n_spk);
     if (n_wc) atomicAdd(&P.counters[CNT_WCROSS], (unsigned long long)n_wc);
     if (n_bad) atomicAdd(&P.counters[CNT_NONFINITE], (unsigned long long)n_bad);
+  }
+}
+
+/* After the all-gather: append every rank's spikes of this step to the ring (same order on every rank) and clear the
+ * send counter for the next step.  One CTA. */
+__global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P, const int step_offset) {
+  const long long k = *P.base_step + step_offset;
+  __shared__ unsigned long long base_sh[17];
+  if (threadIdx.x == 0) {
+    unsigned long long b = *P.head;
+    for (int r = 0; r < P.n_ranks; ++r) {
+      base_sh[r] = b;
+      b += (unsigned long long)min(P.xchg_recv[(size_t)r * (1 + P.xchg_cap)], P.xchg_cap);
+    }
+    base_sh[P.n_ranks] = b;
+  }
+  __syncthreads();
+  for (int r = 0; r < P.n_ranks; ++r) {
+    const int* src = P.xchg_recv + (size_t)r * (1 + P.xchg_cap);
+    const int n = min(src[0], P.xchg_cap);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
+      P.spk_neuron[pos] = src[1 + q];
+      P.spk_step[pos] = (int)k;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *P.head = base_sh[P.n_ranks];
+    P.xchg_send[0] = 0;
   }
 }
 
@@ -902,6 +952,10 @@ struct hhd_engine {
   cudaGraphExec_t graph_exec = nullptr;
   hhd_counters cnt;
   int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
+#ifdef HHD_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  bool comm_ready = false;
   bool cross_instance = false; /* some synapse joins two instances: the resident plan is not applicable */
   bool resident = false;       /* HHD_PLAN_RESIDENT chosen */
   int res_smem = 0;
@@ -1028,6 +1082,9 @@ extern "C" void hhd_destroy(hhd_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+#ifdef HHD_WITH_NCCL
+  if (h->comm) ncclCommDestroy(h->comm);
+#endif
   for (void* p : h->allocs) cudaFree(p);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1465,7 +1522,9 @@ static int finalize_setup(hhd_handle h) {
   Params& P = h->P;
   if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
   if (!h->channels_set) return fail(h, HHD_E_STATE, "hhd_set_channels has not been called");
-  if (h->cfg.n_ranks > 1) return fail(h, HHD_E_STATE, "multi-rank runs need hhd_comm_init (not built into this plan yet)");
+  if (h->cfg.n_ranks > 1 && !h->comm_ready) return fail(h, HHD_E_STATE, "n_ranks > 1: call hhd_comm_init on every rank before hhd_run");
+  if (h->cfg.n_ranks > 16) return fail(h, HHD_E_ARG, "at most 16 ranks");
+  P.n_ranks = h->cfg.n_ranks;
   if (!h->nsyn) {   /* empty network: arrays must still be valid pointers for the kernels */
     P.max_delay = 0;
   }
@@ -1483,6 +1542,13 @@ static int finalize_setup(hhd_handle h) {
   if (!rc) rc = dev_alloc(h, &P.spk_step, (size_t)h->ring_cap, false);
   if (rc) return rc;
   P.cap_mask = (unsigned int)(h->ring_cap - 1);
+  if (P.n_ranks > 1) {
+    const char* env = getenv("HHD_XCHG_CAP");
+    P.xchg_cap = env && atoi(env) > 0 ? atoi(env) : std::min(h->N, 4096 + h->N / 16);
+    rc = dev_alloc(h, &P.xchg_send, (size_t)1 + P.xchg_cap, true);
+    if (!rc) rc = dev_alloc(h, &P.xchg_recv, (size_t)P.n_ranks * (1 + P.xchg_cap), true);
+    if (rc) return rc;
+  }
   {
     /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than tiles */
     int per_sm[6] = {0, 0, 0, 0, 0, 0};
@@ -1519,7 +1585,12 @@ static int finalize_setup(hhd_handle h) {
     if (h->cfg.plan == HHD_PLAN_RESIDENT && !can)
       return fail(h, HHD_E_ARG, "HHD_PLAN_RESIDENT needs independent instances of at most %d neurons (instance_size), no synapse "
                   "between instances, max delay < refractory period and a single rank", RES_MAX_CLUSTER * RES_BLOCK);
-    h->resident = can && (h->cfg.plan == HHD_PLAN_RESIDENT || (h->cfg.plan == HHD_PLAN_AUTO && !getenv("HHD_NO_RESIDENT")));
+    /* AUTO: resident only while every cluster is on the chip at once (it is the latency-bound regime's plan; with many
+     * instances the grid-wide kernels have more parallelism per step — 256 x 1003 neurons: 29 vs 47 us per step) */
+    int cs0 = 1;
+    while (cs0 * RES_BLOCK < inst) cs0 <<= 1;
+    const bool one_wave = (long long)(h->N / inst) * cs0 <= (long long)h->sm_count;
+    h->resident = can && (h->cfg.plan == HHD_PLAN_RESIDENT || (h->cfg.plan == HHD_PLAN_AUTO && one_wave && !getenv("HHD_NO_RESIDENT")));
     if (h->resident) {
       P.inst_size = inst;
       P.n_inst = h->N / inst;
@@ -1579,6 +1650,12 @@ static void launch_neuron(hhd_handle h, int offset) {
 
 static void launch_step(hhd_handle h, int offset) {
   launch_neuron<true>(h, offset);
+#ifdef HHD_WITH_NCCL
+  if (h->cfg.n_ranks > 1) {   /* the one real exchange of the path: this step's spike indices, every rank to every rank */
+    ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
+    k_append<<<1, 256, 0, h->stream>>>(h->P, offset);
+  }
+#endif
   if (h->fused) {
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
@@ -1702,7 +1779,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
     long long s = 0;
     while (seg - s >= STEPS_PER_GRAPH && h->graph_exec && !h->graph_dirty) {
       CU(cudaGraphLaunch(h->graph_exec, h->stream));
-      h->cnt.kernel_launches += h->kernels_per_step * STEPS_PER_GRAPH + 1;
+      h->cnt.kernel_launches += (h->kernels_per_step + (h->cfg.n_ranks > 1 ? 1 : 0)) * STEPS_PER_GRAPH + 1;
       s += STEPS_PER_GRAPH;
     }
     const int rem = (int)(seg - s);
@@ -1724,7 +1801,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   h->cnt.neuron_updates += n_steps * (long long)h->N;
   unsigned long long c[CNT_N];
   CU(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
-  if (c[CNT_OVERFLOW]) return fail(h, HHD_E_CAPACITY, "a monitor buffer overflowed on the device");
+  if (c[CNT_OVERFLOW]) return fail(h, HHD_E_CAPACITY, "a device buffer overflowed (monitor capacity, or more spikes in one step than the exchange buffer holds: HHD_XCHG_CAP)");
   {
     unsigned long long slots[CNT_SLOTS];
     CU(cudaMemcpy(slots, h->P.del_slots, sizeof slots, cudaMemcpyDeviceToHost));
@@ -1769,6 +1846,12 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
   for (int64_t s = 0; s < n_steps; ++s) {
     launch_neuron<true>(h, (int)s);
     CU(cudaEventRecord(ev[3 * s + 1], h->stream));
+#ifdef HHD_WITH_NCCL
+    if (h->cfg.n_ranks > 1) {   /* the exchange is accounted to slot 1 */
+      ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
+      k_append<<<1, 256, 0, h->stream>>>(h->P, (int)s);
+    }
+#endif
     if (!h->fused) k_stp<<<h->nsyn ? h->stp_grid : 1, h->nsyn ? STP_BLOCK : 32, 0, h->stream>>>(h->P, (int)s);
     else k_spike_new<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
     CU(cudaEventRecord(ev[3 * s + 2], h->stream));
@@ -1863,5 +1946,31 @@ extern "C" int hhd_current_step(hhd_handle h, int64_t* step) {
   return HHD_OK;
 }
 
-extern "C" int hhd_comm_unique_id(uint8_t out_id[128]) { memset(out_id, 0, 128); return HHD_E_COMM; }
-extern "C" int hhd_comm_init(hhd_handle h, const uint8_t id[128]) { (void)id; return fail(h, HHD_E_COMM, "NCCL exchange is not built into this library yet"); }
+extern "C" int hhd_comm_unique_id(uint8_t out_id[128]) {
+#ifdef HHD_WITH_NCCL
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return HHD_E_COMM;
+  memcpy(out_id, &id, 128);
+  return HHD_OK;
+#else
+  memset(out_id, 0, 128);
+  return HHD_E_COMM;
+#endif
+}
+
+extern "C" int hhd_comm_init(hhd_handle h, const uint8_t id_bytes[128]) {
+  if (!h || !id_bytes) return fail(h, HHD_E_ARG, "null argument");
+  if (h->started) return fail(h, HHD_E_STATE, "hhd_comm_init after run");
+#ifdef HHD_WITH_NCCL
+  cudaSetDevice(h->cfg.device);
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, 128);
+  ncclResult_t r = ncclCommInitRank(&h->comm, h->cfg.n_ranks, id, h->cfg.rank);
+  if (r != ncclSuccess) return fail(h, HHD_E_COMM, "ncclCommInitRank failed: %s", ncclGetErrorString(r));
+  h->comm_ready = true;
+  return HHD_OK;
+#else
+  return fail(h, HHD_E_COMM, "this libhhd.so was built without NCCL");
+#endif
+}

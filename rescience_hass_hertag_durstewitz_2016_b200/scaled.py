@@ -27,14 +27,14 @@ def tile_columns(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_columns, ji
                 I_DC=idc, n_per_column=n1)
 
 
-def tile_synapses_device(SynPar, source_arr, target_arr, n_columns, n_per_column, device):
+def tile_synapses_device(SynPar, source_arr, target_arr, n_columns, n_per_column, device, id_offset=0):
     """The synapse arrays of `tile_columns`, built as torch CUDA tensors directly in HBM (PyTorch is used for device
     buffers only): -> (src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms) for Engine.set_synapses_dev.
     1000 columns of the 1003-neuron column are 2.9e8 synapses = 17 GB, which should not be staged through host memory."""
     import torch
     S = torch.as_tensor(np.ascontiguousarray(SynPar, dtype=np.float64), device=device)
     k = int(n_columns)
-    offs = (torch.arange(k, device=device, dtype=torch.int64) * int(n_per_column))[:, None]
+    offs = (torch.arange(k, device=device, dtype=torch.int64) * int(n_per_column) + int(id_offset))[:, None]
     src1 = torch.as_tensor(np.asarray(source_arr, dtype=np.int64), device=device)[None, :]
     tgt1 = torch.as_tensor(np.asarray(target_arr, dtype=np.int64), device=device)[None, :]
     src = (src1 + offs).reshape(-1).to(torch.int32).contiguous()
