@@ -1544,7 +1544,8 @@ static int finalize_setup(hhd_handle h) {
   P.cap_mask = (unsigned int)(h->ring_cap - 1);
   if (P.n_ranks > 1) {
     const char* env = getenv("HHD_XCHG_CAP");
-    P.xchg_cap = env && atoi(env) > 0 ? atoi(env) : std::min(h->N, 4096 + h->N / 16);
+    /* must be identical on every rank (all-gather count), so it is derived from global quantities only */
+    P.xchg_cap = env && atoi(env) > 0 ? atoi(env) : std::min(h->NG, 4096 + h->NG / (16 * P.n_ranks));
     rc = dev_alloc(h, &P.xchg_send, (size_t)1 + P.xchg_cap, true);
     if (!rc) rc = dev_alloc(h, &P.xchg_recv, (size_t)P.n_ranks * (1 + P.xchg_cap), true);
     if (rc) return rc;

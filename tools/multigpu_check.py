@@ -33,11 +33,14 @@ def main():
             uid = torch.tensor(list(e.comm_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         e.comm_init(bytes(uid.cpu().tolist()))
+        print('rank', rank, name, 'comm ready', flush=True)
         e.run(steps)
+        print('rank', rank, name, 'ran', flush=True)
         i, s = e.spikes()
         mine = dict(i=i, s=s, V=e.read_state("V"), ev=e.counters()["syn_events"])
         parts = [None] * world
         dist.all_gather_object(parts, mine)
+        print('rank', rank, name, 'gathered', flush=True)
         if rank == 0:
             ref = Engine(g["NeuPar"].shape[1], 0.05, method="rk2", accum="fixed", seed=23, device=lr, plan="graph")
             load_codes_network(ref, gnet["NeuPar"], gnet["V0"], g["STypPar"], gnet["SynPar"], gnet["source_arr"], gnet["target_arr"], gnet["I_DC"])
