@@ -342,10 +342,11 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
       continue;
     }
 
-    /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510) --------------------- */
+    /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510).  State variables are
+     *      written now; derived ones (I_tot ...) after the update, from the subexpressions of the first stage -------- */
     for (int m = 0; m < P.n_mon; ++m) {
       const MonDesc md = P.mon[m];
-      if (!md.active) continue;
+      if (!md.active || hhd_var_is_derived(md.var)) continue;
       const long long sample = k - md.k0;
       if (sample < 0 || sample >= md.capacity) {
         if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
@@ -367,8 +368,30 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     if (live) {
       /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
 #if !(HHD_EXPERIMENT & 2)
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
+      SubExpr s1;
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1);
+#else
+      SubExpr s1;
+      hhd_subexpr(P.cc, p, x, s1);
 #endif
+      for (int m = 0; m < P.n_mon; ++m) {
+        const MonDesc md = P.mon[m];
+        if (!md.active || !hhd_var_is_derived(md.var)) continue;
+        const long long sample = k - md.k0;
+        if (sample < 0 || sample >= md.capacity) {
+          if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+          continue;
+        }
+        const int slot = md.slot ? md.slot[i] : i;
+        if (slot >= 0) {
+          const double v = hhd_var_from_subexpr(s1, md.var);
+          if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
+          else {
+#pragma unroll
+            for (int r = 0; r < MAX_RED; ++r) if (r == md.red_slot) mon_acc[r] += v;
+          }
+        }
+      }
       bad = !(isfinite(x[0]) && isfinite(x[1]));
       /* ---- slot `thresholds` (:304, 306) --------------------------------------------------------------------- */
       const int lastk = meta >> 2;
@@ -721,7 +744,8 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
 
     bool spiked = false, wcross = false;
     if (live) {
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt);
+      SubExpr s1;
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1);
       n_bad += !(isfinite(x[0]) && isfinite(x[1]));
       const int lastk = meta >> 2;
       spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);

@@ -46,9 +46,10 @@ __device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const Neuron
   s.dD0 = p.C * (s.ex - 1.0);
 }
 
+/* Right-hand sides at state x; `s` returns the subexpressions of that state (the first stage's are exactly what a
+ * StateMonitor of I_tot, I_syn ... samples in Brian's `start` slot, so monitors of derived variables cost nothing extra). */
 __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t,
-                                          double ls, double d[8]) {
-  SubExpr s;
+                                          double ls, double d[8], SubExpr& s) {
   hhd_subexpr(cc, p, x, s);
   const double V = x[0], w = x[1];
   const double a = ((s.I_tot >= p.Iref) ? 1.0 : 0.0) * ((t - ls < cc.window_ms) ? 1.0 : 0.0);
@@ -68,9 +69,10 @@ __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPa
 /* Brian 2's ExplicitStateUpdaters: METHOD 0 euler, 1 rk2 (midpoint), 2 rk4. */
 template <int METHOD>
 __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t,
-                                              double ls, double dt) {
+                                              double ls, double dt, SubExpr& s1) {
   double k1[8], y[8];
-  hhd_deriv(cc, p, x, t, ls, k1);
+  SubExpr sk;
+  hhd_deriv(cc, p, x, t, ls, k1, s1);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k1[v] = dt * k1[v];
   if (METHOD == 0) {
@@ -81,7 +83,7 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   double k2[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k1[v] * 0.5;
-  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k2);
+  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k2, sk);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k2[v] = dt * k2[v];
   if (METHOD == 1) {
@@ -92,17 +94,37 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   double k3[8], k4[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k2[v] * 0.5;
-  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k3);
+  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k3, sk);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k3[v] = dt * k3[v];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k3[v];
-  hhd_deriv(cc, p, y, t + dt, ls, k4);
+  hhd_deriv(cc, p, y, t + dt, ls, k4, sk);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
 #pragma unroll
   for (int v = 0; v < 8; ++v) x[v] = x[v] + hhd_div(((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v], 6.0);
 }
+
+/* Derived variable (id >= 8, != last_spike) from subexpressions already evaluated at the sampled state. */
+__device__ __forceinline__ double hhd_var_from_subexpr(const SubExpr& s, int var) {
+  switch (var) {
+    case 8: return s.g[0];
+    case 9: return s.g[1];
+    case 10: return s.g[2];
+    case 11: return s.I_AMPA;
+    case 12: return s.I_GABA;
+    case 13: return s.I_NMDA;
+    case 14: return s.I_syn;
+    case 15: return s.I_inj;
+    case 16: return s.I_tot;
+    case 17: return s.I_AMPA + s.I_NMDA;
+    case 18: return (s.I_AMPA + s.I_NMDA) + s.I_inj;
+    case 19: return s.I_exp;
+  }
+  return 0.0;
+}
+__device__ __forceinline__ bool hhd_var_is_derived(int var) { return var >= 8 && var != 20; }
 
 /* Value of a monitored / derived variable (ids of include/hhd.h) from the state. */
 __device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const NeuronPar& p, const double x[8], int var,
