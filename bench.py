@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--workload", default="columns", choices=["columns", "column"])
     ap.add_argument("--columns", type=int, default=0, help="columns in the scaled network (0 = workload default)")
     ap.add_argument("--template", default="n1000", choices=["n1000", "n200"], help="one-column fixture that is tiled")
-    ap.add_argument("--method", default="euler", choices=["euler", "rk2", "rk4"])
+    ap.add_argument("--method", default="euler", choices=["euler", "rk2", "rk4", "rk23", "gsl_rk2"])
     ap.add_argument("--dt", type=float, default=0.05)
     ap.add_argument("--window", type=int, default=2000, help="time steps per bench step")
     ap.add_argument("--accum", default="fp64", choices=["fp64", "fixed"])

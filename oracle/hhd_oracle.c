@@ -433,43 +433,51 @@ static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], doub
 }
 
 /*
- * gsl_rk2 stand-in (codes/Mainrk2.py:32): GSL's embedded RK2(3) step (gsl_odeiv2_step_rk2) driven by the standard
- * controller with eps_abs = 1e-6 in SI units on every variable (so 1e-3 mV, 1e6 pA, 1e3 nS here: only V controls),
- * eps_rel = 0, sub-stepping inside each dt.  Statistical stand-in only; GSL itself is not available.
+ * gsl_rk2 stand-in (codes/Mainrk2.py:32, codes_revision/Tests.py:126): an embedded RK2(3) pair with per-neuron
+ * sub-stepping inside each dt, in the spirit of GSL's gsl_odeiv2_step_rk2 + standard controller that Brian's GSL
+ * state updater drives (k1 = f(y), k2 = f(y + h/2 k1), k3 = f(y + h(2 k2 - k1)); y+ = y + h(k1 + 4 k2 + k3)/6; error =
+ * y+ minus the second-order solution y + h k2), absolute tolerance 1e-6 in SI units on every variable (1e-3 mV for V;
+ * the pA / nS variables never bind), reject when err > 1.1 tol and shrink by max(0.9 err^-1/2, 0.2), grow by
+ * min(0.9 err^-1/4, 5) when err < 0.5 tol, last sub-step clipped to the end of the step.  GSL itself is not available
+ * here, so this is a STATISTICAL stand-in, written with IEEE sqrt only so that the CUDA engine
+ * reproduces it bit for bit (the growth exponent is -1/4 instead of GSL's -1/3 for that reason).
  */
+#define RK23_MAX_SUBSTEPS 4096
 static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], double t0, double ls) {
   const double dt = h->cfg.dt_ms;
-  static const double tol[8] = {1e-3, 1e6, 1e3, 1e3, 1e3, 1e3, 1e3, 1e3};
+  static const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
   double t = 0.0, hs = dt;
-  int guard = 0;
-  while (t < dt && guard++ < 100000) {
+  for (int it = 0; it < RK23_MAX_SUBSTEPS && t < dt; ++it) {
     if (t + hs > dt) hs = dt - t;
     double k1[8], k2[8], k3[8], y[8], ynew[8];
     deriv(h, p, x, t0 + t, ls, k1);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
-    deriv(h, p, y, t0 + t + 0.5 * hs, ls, k2);
+    deriv(h, p, y, t0 + (t + 0.5 * hs), ls, k2);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    deriv(h, p, y, t0 + t + hs, ls, k3);
+    deriv(h, p, y, t0 + (t + hs), ls, k3);
     double rmax = 0.0;
     for (int v = 0; v < 8; ++v) {
       ynew[v] = x[v] + hs * (((k1[v] + 4.0 * k2[v]) + k3[v]) / 6.0);
-      const double err = hs * (((4.0 * k2[v] - 2.0 * k1[v]) - 2.0 * k3[v]) / 6.0);  /* y3 - y2, y2 = x + h*k2 */
-      const double r = fabs(err) / tol[v];
-      if (r > rmax) rmax = r;
+      const double err = hs * (((k1[v] - 2.0 * k2[v]) + k3[v]) / 6.0);
+      const double r = fabs(err) * inv_tol[v];
+      if (r > rmax) rmax = r;                      /* NaN never wins: a non-finite error accepts the step */
     }
-    if (rmax > 1.1 && hs > dt * 1e-6) {           /* reject, shrink: h *= max(0.9 r^(-1/2), 0.2)   (ord = 2) */
+    if (rmax > 1.1 && hs > dt * 9.5367431640625e-07) {     /* 2^-20 dt floor */
       double f = 0.9 / sqrt(rmax);
       if (f < 0.2) f = 0.2;
-      hs *= f;
+      hs = hs * f;
       continue;
     }
     for (int v = 0; v < 8; ++v) x[v] = ynew[v];
-    t += hs;
-    if (rmax < 0.5) {                             /* grow: h *= min(0.9 r^(-1/3), 5) */
-      double f = rmax > 0 ? 0.9 / cbrt(rmax) : 5.0;
-      if (f > 5.0) f = 5.0;
-      if (f < 1.0) f = 1.0;
-      hs *= f;
+    t = t + hs;
+    if (rmax < 0.5) {
+      double f = 5.0;
+      if (rmax > 0.0) {
+        f = 0.9 / sqrt(sqrt(rmax));
+        if (f > 5.0) f = 5.0;
+        if (f < 1.0) f = 1.0;
+      }
+      hs = hs * f;
     }
   }
 }

@@ -177,6 +177,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may be
+ * scheduled while its predecessor in the stream is still draining; pdl_wait() blocks until that predecessor has
+ * completed and its writes are visible, pdl_trigger() lets the successor start being scheduled.  Both are no-ops for a
+ * normal launch. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #ifndef HHD_EXPERIMENT
 #define HHD_EXPERIMENT 0          /* timing experiments only (bit 0: no w_crossing test, bit 1: no integration) */
 #endif
@@ -199,7 +206,7 @@ struct NeuronStage {
  * 21 doubles + meta word of its NEXT tile into shared memory with cp.async while it integrates the current one, so the
  * HBM stream (240 B per neuron-update) and the fp64 pipe (≈350 instructions per euler update) overlap inside every warp
  * instead of alternating; a thread only ever reads the shared slots it filled itself, so no block barrier is needed.
- * METHOD: 0 euler, 1 rk2, 2 rk4.  STEP = false: only finish the previous step (used once at the end of hhd_run so that
+ * METHOD: 0 euler, 1 rk2, 2 rk4, 3 adaptive rk2(3).  STEP = false: only finish the previous step (used once at the end of hhd_run so that
  * the state read back is the state after `resets`/`after_resets`).
  * meta = lastspike_step * 4 + flags (FLAG_SPIKED | FLAG_WCROSS of the previous step).
  */
@@ -208,6 +215,8 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NeuronStage* st = reinterpret_cast<NeuronStage*>(smem_raw);
   __shared__ double red[MAX_MON][NEURON_BLOCK / 32];
+  pdl_trigger();
+  pdl_wait();
   __shared__ unsigned long long cnt_sh[3];
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
@@ -527,6 +536,8 @@ __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, d
  */
 /* Pathways p0..p6 + the zero-delay deliveries + p5 for the spikes of THIS step, one CTA per new spike (fused mode). */
 __global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
+  pdl_trigger();
+  pdl_wait();
   const long long k = *P.base_step + step_offset;
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
@@ -563,6 +574,8 @@ __global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__
 
 template <bool FUSED>
 __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
+  pdl_trigger();
+  pdl_wait();
   const long long k = *P.base_step + step_offset;
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
@@ -983,6 +996,7 @@ struct hhd_engine {
   bool cross_instance = false; /* some synapse joins two instances: the resident plan is not applicable */
   bool resident = false;       /* HHD_PLAN_RESIDENT chosen */
   int res_smem = 0;
+  bool pdl = false;            /* programmatic dependent launch between the kernels of the main stream */
   bool fused = false;          /* spike-time STP runs inside k_deliver (max_delay < refractory steps) */
   int kernels_per_step = 3;
 };
@@ -1038,7 +1052,6 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (cfg->abi_version != HHD_ABI_VERSION) return fail(h, HHD_E_ARG, "abi_version %d != %d", cfg->abi_version, HHD_ABI_VERSION);
   if (cfg->n_neurons <= 0 || !(cfg->dt_ms > 0)) return fail(h, HHD_E_ARG, "n_neurons and dt_ms must be positive");
   if (cfg->method < HHD_EULER || cfg->method > HHD_RK23_ADAPTIVE) return fail(h, HHD_E_ARG, "unknown method %d", cfg->method);
-  if (cfg->method == HHD_RK23_ADAPTIVE) return fail(h, HHD_E_ARG, "HHD_RK23_ADAPTIVE is not available in the CUDA engine yet");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1576,14 +1589,15 @@ static int finalize_setup(hhd_handle h) {
   }
   {
     /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than tiles */
-    int per_sm[6] = {0, 0, 0, 0, 0, 0};
-    const void* fn[6] = {(const void*)k_neuron<0, true>, (const void*)k_neuron<1, true>, (const void*)k_neuron<2, true>,
-                         (const void*)k_neuron<0, false>, (const void*)k_neuron<1, false>, (const void*)k_neuron<2, false>};
-    for (int q = 0; q < 6; ++q) {
+    int per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const void* fn[8] = {(const void*)k_neuron<0, true>, (const void*)k_neuron<1, true>, (const void*)k_neuron<2, true>,
+                         (const void*)k_neuron<3, true>, (const void*)k_neuron<0, false>, (const void*)k_neuron<1, false>,
+                         (const void*)k_neuron<2, false>, (const void*)k_neuron<3, false>};
+    for (int q = 0; q < 8; ++q) {
       CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[q], fn[q], NEURON_BLOCK, NEURON_SMEM));
     }
-    const int m = h->cfg.method == HHD_EULER ? 0 : h->cfg.method == HHD_RK2 ? 1 : 2;
+    const int m = h->cfg.method;
     const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
     const char* env = getenv("HHD_NEURON_CTAS_PER_SM");
     int cps = std::max(1, per_sm[m]);
@@ -1596,6 +1610,7 @@ static int finalize_setup(hhd_handle h) {
   if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
   h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
   h->kernels_per_step = 3;
+  h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
     rc = dev_alloc(h, &bkt, (size_t)h->NG * DELAY_BUCKETS, true);
@@ -1626,8 +1641,8 @@ static int finalize_setup(hhd_handle h) {
       rc = dev_alloc(h, &P.res_store, (size_t)P.n_inst * (2 + P.W + 2 * (size_t)P.res_cap), true);
       if (rc) return rc;
       h->res_smem = 3 * RES_BLOCK * 8 + MAX_MON * (int)sizeof(MonDesc) + (int)sizeof(ResList) + P.W * 4 + 2 * P.res_cap * 4 + 16;
-      const void* fn[3] = {(const void*)k_resident<0>, (const void*)k_resident<1>, (const void*)k_resident<2>};
-      for (int q = 0; q < 3; ++q) {
+      const void* fn[4] = {(const void*)k_resident<0>, (const void*)k_resident<1>, (const void*)k_resident<2>, (const void*)k_resident<3>};
+      for (int q = 0; q < 4; ++q) {
         CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, h->res_smem));
         if (cs > 8) CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       }
@@ -1655,7 +1670,8 @@ static int launch_resident(hhd_handle h, int n_steps) {
   switch (h->cfg.method) {
     case HHD_EULER: e = cudaLaunchKernelEx(&lc, k_resident<0>, h->P, n_steps); break;
     case HHD_RK2: e = cudaLaunchKernelEx(&lc, k_resident<1>, h->P, n_steps); break;
-    default: e = cudaLaunchKernelEx(&lc, k_resident<2>, h->P, n_steps); break;
+    case HHD_RK4: e = cudaLaunchKernelEx(&lc, k_resident<2>, h->P, n_steps); break;
+    default: e = cudaLaunchKernelEx(&lc, k_resident<3>, h->P, n_steps); break;
   }
   if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "launch of the cluster-resident kernel failed: %s", cudaGetErrorString(e));
   k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, n_steps);
@@ -1663,13 +1679,30 @@ static int launch_resident(hhd_handle h, int n_steps) {
   return 0;
 }
 
+template <typename K>
+static void launch_pdl(hhd_handle h, K kernel, int grid, int block, size_t smem, cudaStream_t stream, int offset) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof lc);
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3((unsigned)block);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = h->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&lc, kernel, h->P, offset);
+}
+
 template <bool STEP>
 static void launch_neuron(hhd_handle h, int offset) {
   const int grid = h->neuron_grid;
   switch (h->cfg.method) {
-    case HHD_EULER: k_neuron<0, STEP><<<grid, NEURON_BLOCK, NEURON_SMEM, h->stream>>>(h->P, offset); break;
-    case HHD_RK2: k_neuron<1, STEP><<<grid, NEURON_BLOCK, NEURON_SMEM, h->stream>>>(h->P, offset); break;
-    default: k_neuron<2, STEP><<<grid, NEURON_BLOCK, NEURON_SMEM, h->stream>>>(h->P, offset); break;
+    case HHD_EULER: launch_pdl(h, k_neuron<0, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
+    case HHD_RK2: launch_pdl(h, k_neuron<1, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
+    case HHD_RK4: launch_pdl(h, k_neuron<2, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
+    default: launch_pdl(h, k_neuron<3, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
   }
 }
 
@@ -1686,7 +1719,7 @@ static void launch_step(hhd_handle h, int offset) {
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
     k_spike_new<<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
     cudaEventRecord(h->ev_join, h->stream2);
-    k_deliver<true><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+    launch_pdl(h, k_deliver<true>, h->deliver_grid, DELIVER_BLOCK, 0, h->stream, offset);
     cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   } else {
     if (h->nsyn) k_stp<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, offset);

@@ -106,6 +106,56 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   for (int v = 0; v < 8; ++v) x[v] = x[v] + hhd_div(((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v], 6.0);
 }
 
+/* METHOD 3: the gsl_rk2 stand-in — embedded RK2(3) with per-neuron sub-stepping inside dt; operation for operation the
+ * function integrate_rk23 of oracle/hhd_oracle.c (IEEE sqrt only), see there for the controller. */
+template <>
+__device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const NeuronPar& p, double x[8], double t0,
+                                                 double ls, double dt, SubExpr& s1) {
+  const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
+  double t = 0.0, hs = dt;
+  bool first = true;
+  for (int it = 0; it < 4096 && t < dt; ++it) {
+    if (t + hs > dt) hs = dt - t;
+    double k1[8], k2[8], k3[8], y[8], ynew[8];
+    SubExpr sk;
+    if (first) hhd_deriv(cc, p, x, t0 + t, ls, k1, s1);
+    else hhd_deriv(cc, p, x, t0 + t, ls, k1, sk);
+    first = false;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
+    hhd_deriv(cc, p, y, t0 + (t + 0.5 * hs), ls, k2, sk);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
+    hhd_deriv(cc, p, y, t0 + (t + hs), ls, k3, sk);
+    double rmax = 0.0;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      ynew[v] = x[v] + hs * hhd_div((k1[v] + 4.0 * k2[v]) + k3[v], 6.0);
+      const double err = hs * hhd_div((k1[v] - 2.0 * k2[v]) + k3[v], 6.0);
+      const double r = fabs(err) * inv_tol[v];
+      if (r > rmax) rmax = r;
+    }
+    if (rmax > 1.1 && hs > dt * 9.5367431640625e-07) {
+      double f = hhd_div(0.9, sqrt(rmax));
+      if (f < 0.2) f = 0.2;
+      hs = hs * f;
+      continue;
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = ynew[v];
+    t = t + hs;
+    if (rmax < 0.5) {
+      double f = 5.0;
+      if (rmax > 0.0) {
+        f = hhd_div(0.9, sqrt(sqrt(rmax)));
+        if (f > 5.0) f = 5.0;
+        if (f < 1.0) f = 1.0;
+      }
+      hs = hs * f;
+    }
+  }
+}
+
 /* Derived variable (id >= 8, != last_spike) from subexpressions already evaluated at the sampled state. */
 __device__ __forceinline__ double hhd_var_from_subexpr(const SubExpr& s, int var) {
   switch (var) {

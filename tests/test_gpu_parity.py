@@ -24,7 +24,7 @@ def gpu_cpu(g, plan, **kw):
 
 
 @pytest.mark.parametrize("plan", PLANS)
-@pytest.mark.parametrize("method", ["euler", "rk2", "rk4"])
+@pytest.mark.parametrize("method", ["euler", "rk2", "rk4", "rk23"])
 def test_uncoupled_neurons_bit_exact(method, plan):
     g = load_golden("net_n200_s0")
     idc = default_idc(g) * 1.5          # enough drive that most cells fire without synaptic input
@@ -43,7 +43,7 @@ def test_uncoupled_neurons_bit_exact(method, plan):
 
 
 @pytest.mark.parametrize("plan", PLANS)
-@pytest.mark.parametrize("method", ["euler", "rk4"])
+@pytest.mark.parametrize("method", ["euler", "rk4", "gsl_rk2"])
 def test_network_fixed_accumulation_bit_exact(method, plan):
     g = load_golden("net_n200_s0")
     gpu, cpu = gpu_cpu(g, plan, method=method, accum="fixed", seed=11)
