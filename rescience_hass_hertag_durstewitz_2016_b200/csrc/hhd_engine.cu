@@ -188,7 +188,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #define HHD_EXPERIMENT 0          /* timing experiments only (bit 0: no w_crossing test, bit 1: no integration) */
 #endif
 #ifndef HHD_NEURON_PREFETCH
-#define HHD_NEURON_PREFETCH 2     /* 2: TMA bulk copies + mbarrier, double-buffered tiles in shared memory; 1: per-thread cp.async; 0: plain loads */
+#define HHD_NEURON_PREFETCH 2     /* 3: TMA bulk copies + one mbarrier per WARP (warps of a CTA never wait for each other);
+                                     2: TMA + one mbarrier per CTA; 1: per-thread cp.async; 0: plain loads */
 #endif
 #ifndef HHD_NEURON_MINBLOCKS_EULER
 #define HHD_NEURON_MINBLOCKS_EULER 5
@@ -215,8 +216,10 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NeuronStage* st = reinterpret_cast<NeuronStage*>(smem_raw);
   __shared__ double red[MAX_MON][NEURON_BLOCK / 32];
+  __shared__ MonDesc mon_sh[MAX_MON];      /* read once per CTA instead of once per tile from global memory */
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x < P.n_mon) mon_sh[threadIdx.x] = P.mon[threadIdx.x];
   __shared__ unsigned long long cnt_sh[3];
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
@@ -224,27 +227,36 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   const double t = (double)k * P.dt;
   const int ntiles = (P.N + NEURON_BLOCK - 1) / NEURON_BLOCK;
   if (tid < 3) cnt_sh[tid] = 0ull;
+#if HHD_NEURON_PREFETCH < 2
+  __syncthreads();
+#endif
 
-#if HHD_NEURON_PREFETCH == 2
-  __shared__ __align__(8) unsigned long long full_bar[NEURON_STAGES];
+#if HHD_NEURON_PREFETCH >= 2
+  /* mode 2: one barrier per stage for the CTA; mode 3: one per stage and warp */
+  constexpr int GROUP = HHD_NEURON_PREFETCH == 3 ? 32 : NEURON_BLOCK;      /* threads that share a barrier */
+  constexpr int NGROUPS = NEURON_BLOCK / GROUP;
+  const int grp = tid / GROUP, gl = tid % GROUP;
+  __shared__ __align__(8) unsigned long long full_bar[NEURON_STAGES * NGROUPS];
   if (tid == 0) {
 #pragma unroll
-    for (int q = 0; q < NEURON_STAGES; ++q) mbar_init(&full_bar[q], 1);
+    for (int q = 0; q < NEURON_STAGES * NGROUPS; ++q) mbar_init(&full_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  /* Producer = thread 0: twenty 1 KB bulk copies (8 state + 12 parameter rows of the tile; the arrays are padded to whole
-   * tiles) complete on the stage's mbarrier; every thread fetches its own last_spike and meta word with cp.async. */
+  /* Producer = first thread of the group: twenty bulk copies (8 state + 12 parameter rows of the group's part of the
+   * tile; the arrays are padded to whole tiles) complete on the group's mbarrier of that stage; every thread fetches its
+   * own last_spike and meta word with cp.async. */
   auto issue = [&](int tile, int s) {
     const int i = tile * NEURON_BLOCK + tid;
     if (tile < ntiles) {
-      if (tid == 0) {
-        const size_t o = (size_t)tile * NEURON_BLOCK;
-        mbar_expect_tx(&full_bar[s], 20u * NEURON_BLOCK * 8u);
+      if (gl == 0) {
+        const size_t o = (size_t)tile * NEURON_BLOCK + (size_t)grp * GROUP;
+        unsigned long long* bar = &full_bar[s * NGROUPS + grp];
+        mbar_expect_tx(bar, 20u * GROUP * 8u);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) tma_load_1d(&st[s].f[v][0], P.x[v] + o, NEURON_BLOCK * 8u, &full_bar[s]);
+        for (int v = 0; v < 8; ++v) tma_load_1d(&st[s].f[v][grp * GROUP], P.x[v] + o, GROUP * 8u, bar);
 #pragma unroll
-        for (int q = 0; q < HHD_N_PARAMS; ++q) tma_load_1d(&st[s].f[8 + q][0], P.par[q] + o, NEURON_BLOCK * 8u, &full_bar[s]);
+        for (int q = 0; q < HHD_N_PARAMS; ++q) tma_load_1d(&st[s].f[8 + q][grp * GROUP], P.par[q] + o, GROUP * 8u, bar);
       }
       if (i < P.N) {
         cp_async8(&st[s].f[20][tid], P.last_spike + P.off + i);
@@ -277,6 +289,9 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
 #if HHD_NEURON_PREFETCH
   issue(tile, 0);
 #endif
+#if HHD_NEURON_PREFETCH >= 2
+  issue(tile + gridDim.x, 1);        /* two tiles in flight from the start */
+#endif
   for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
     const int i = tile * NEURON_BLOCK + tid;
     const bool live = i < P.N;
@@ -294,11 +309,10 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     }
     if (false) {
       const int s = 0;
-#elif HHD_NEURON_PREFETCH == 2
+#elif HHD_NEURON_PREFETCH >= 2
     const int s = it & 1;
-    issue(tile + gridDim.x, s ^ 1);   /* stage s^1 was released by the block barrier of the previous iteration */
     cp_async_wait<1>();
-    mbar_wait(&full_bar[s], (it >> 1) & 1);
+    mbar_wait(&full_bar[s * NGROUPS + grp], (it >> 1) & 1);
     if (live) {
 #else
     const int s = it & 1;
@@ -316,7 +330,11 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
       meta = st[s].meta[tid];
     }
 #if HHD_NEURON_PREFETCH == 2
-    __syncthreads();   /* stage s is free again: thread 0 may aim the next bulk copies at it one iteration from now */
+    __syncthreads();   /* every thread holds its neuron of this tile in registers: stage s is free again */
+    issue(tile + 2 * gridDim.x, s);    /* so the tile after next is requested NOW: two tiles in flight with two stages */
+#elif HHD_NEURON_PREFETCH == 3
+    __syncwarp();      /* the warp's part of stage s is free again */
+    issue(tile + 2 * gridDim.x, s);
 #endif
     if (live) {
       /* ---- finish step k-1 -------------------------------------------------------------------------------- */
@@ -354,7 +372,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510).  State variables are
      *      written now; derived ones (I_tot ...) after the update, from the subexpressions of the first stage -------- */
     for (int m = 0; m < P.n_mon; ++m) {
-      const MonDesc md = P.mon[m];
+      const MonDesc& md = mon_sh[m];
       if (!md.active || hhd_var_is_derived(md.var)) continue;
       const long long sample = k - md.k0;
       if (sample < 0 || sample >= md.capacity) {
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
       hhd_subexpr(P.cc, p, x, s1);
 #endif
       for (int m = 0; m < P.n_mon; ++m) {
-        const MonDesc md = P.mon[m];
+        const MonDesc& md = mon_sh[m];
         if (!md.active || !hhd_var_is_derived(md.var)) continue;
         const long long sample = k - md.k0;
         if (sample < 0 || sample >= md.capacity) {
@@ -447,7 +465,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
 
   /* ---- once per CTA: reduced monitors (LFP) and counters ------------------------------------------------------- */
   for (int m = 0; m < P.n_mon; ++m) {
-    const MonDesc md = P.mon[m];
+    const MonDesc& md = mon_sh[m];
     if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
     const long long sample = k - md.k0;
     if (sample < 0 || sample >= md.capacity) continue;
@@ -472,7 +490,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     if (cnt_sh[1]) atomicAdd(&P.counters[CNT_WCROSS], cnt_sh[1]);
     if (cnt_sh[2]) atomicAdd(&P.counters[CNT_NONFINITE], cnt_sh[2]);
     for (int m = 0; m < P.n_mon; ++m) {
-      const MonDesc md = P.mon[m];
+      const MonDesc& md = mon_sh[m];
       if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
       const long long sample = k - md.k0;
       if (sample < 0 || sample >= md.capacity) continue;
