@@ -61,7 +61,8 @@ typedef enum { HHD_ACCUM_FP64 = 0, HHD_ACCUM_FIXED = 1 } hhd_accum;
 typedef enum {
   HHD_PLAN_AUTO = 0,
   HHD_PLAN_GRAPH = 1,     /* 3 grid-wide kernels per step, captured in CUDA graphs (any N, HBM-bound regime) */
-  HHD_PLAN_RESIDENT = 2   /* persistent thread-block-cluster kernel, state in registers (N small, latency-bound regime) */
+  HHD_PLAN_RESIDENT = 2,  /* persistent thread-block-cluster kernel, state in registers (N small, latency-bound regime) */
+  HHD_PLAN_PERSISTENT = 3 /* one cooperative launch per segment: the graph plan's phases separated by grid barriers */
 } hhd_plan;
 
 typedef struct {

@@ -46,7 +46,9 @@
 #define MAX_MON 16
 #define MAX_RED 4   /* reduced (sum/mean) monitors: their per-thread accumulators live in registers */
 #define NEURON_BLOCK 128
+#ifndef STP_BLOCK
 #define STP_BLOCK 128
+#endif
 #define DELIVER_BLOCK 128
 #define STEPS_PER_GRAPH 50
 #define RES_BLOCK 128          /* threads (= neurons) per CTA of the cluster-resident plan */
@@ -115,6 +117,7 @@ struct Params {
   MonDesc* mon;                /* [MAX_MON] device */
   unsigned long long* counters;
   unsigned long long* del_slots;  /* [CNT_SLOTS] */
+  unsigned long long* grid_bar;   /* arrival counter of the cooperative plan's grid barrier */
   const long long* base_step;
   /* multi-GPU spike exchange (n_ranks > 1): k_neuron appends local spikes to xchg_send = {count, ids...}; after the
    * all-gather k_append copies every rank's list into the ring */
@@ -211,38 +214,47 @@ struct NeuronStage {
  * the state read back is the state after `resets`/`after_resets`).
  * meta = lastspike_step * 4 + flags (FLAG_SPIKED | FLAG_WCROSS of the previous step).
  */
+struct NeuronShared {            /* static shared memory of a CTA that runs neuron_phase */
+  double red[MAX_MON][NEURON_BLOCK / 32];
+  MonDesc mon[MAX_MON];          /* read once per CTA instead of once per tile from global memory */
+  unsigned long long cnt[3];
+  unsigned long long full_bar[NEURON_STAGES * (HHD_NEURON_PREFETCH == 3 ? NEURON_BLOCK / 32 : 1)];
+};
+
+/* Called once per CTA before the first neuron_phase: monitor descriptors, mbarriers. */
+__device__ __forceinline__ void neuron_shared_init(const Params& P, NeuronShared& sh) {
+  if (threadIdx.x < P.n_mon) sh.mon[threadIdx.x] = P.mon[threadIdx.x];
+#if HHD_NEURON_PREFETCH >= 2
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NEURON_STAGES * (HHD_NEURON_PREFETCH == 3 ? NEURON_BLOCK / 32 : 1); ++q) mbar_init(&sh.full_bar[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+#endif
+  __syncthreads();
+}
+
+/* One pass over this CTA's tiles for time step k.  `bar_parity` carries the phase bit of every mbarrier across calls
+ * (the cooperative whole-run kernel calls this once per step on the same barriers). */
 template <int METHOD, bool STEP>
-__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  NeuronStage* st = reinterpret_cast<NeuronStage*>(smem_raw);
-  __shared__ double red[MAX_MON][NEURON_BLOCK / 32];
-  __shared__ MonDesc mon_sh[MAX_MON];      /* read once per CTA instead of once per tile from global memory */
-  pdl_trigger();
-  pdl_wait();
-  if (threadIdx.x < P.n_mon) mon_sh[threadIdx.x] = P.mon[threadIdx.x];
-  __shared__ unsigned long long cnt_sh[3];
+__device__ __forceinline__ void neuron_phase(const Params& P, const long long k, NeuronStage* st, NeuronShared& sh,
+                                             unsigned& bar_parity) {
+  double (*red)[NEURON_BLOCK / 32] = sh.red;
+  MonDesc* mon_sh = sh.mon;
+  unsigned long long* cnt_sh = sh.cnt;
+  unsigned long long* full_bar = sh.full_bar;
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
-  const long long k = *P.base_step + step_offset;
   const double t = (double)k * P.dt;
   const int ntiles = (P.N + NEURON_BLOCK - 1) / NEURON_BLOCK;
   if (tid < 3) cnt_sh[tid] = 0ull;
-#if HHD_NEURON_PREFETCH < 2
   __syncthreads();
-#endif
 
 #if HHD_NEURON_PREFETCH >= 2
   /* mode 2: one barrier per stage for the CTA; mode 3: one per stage and warp */
   constexpr int GROUP = HHD_NEURON_PREFETCH == 3 ? 32 : NEURON_BLOCK;      /* threads that share a barrier */
   constexpr int NGROUPS = NEURON_BLOCK / GROUP;
   const int grp = tid / GROUP, gl = tid % GROUP;
-  __shared__ __align__(8) unsigned long long full_bar[NEURON_STAGES * NGROUPS];
-  if (tid == 0) {
-#pragma unroll
-    for (int q = 0; q < NEURON_STAGES * NGROUPS; ++q) mbar_init(&full_bar[q], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
   /* Producer = first thread of the group: twenty bulk copies (8 state + 12 parameter rows of the group's part of the
    * tile; the arrays are padded to whole tiles) complete on the group's mbarrier of that stage; every thread fetches its
    * own last_spike and meta word with cp.async. */
@@ -312,7 +324,8 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
 #elif HHD_NEURON_PREFETCH >= 2
     const int s = it & 1;
     cp_async_wait<1>();
-    mbar_wait(&full_bar[s * NGROUPS + grp], (it >> 1) & 1);
+    mbar_wait(&full_bar[s * NGROUPS + grp], (bar_parity >> (s * NGROUPS + grp)) & 1u);
+    bar_parity ^= 1u << (s * NGROUPS + grp);
     if (live) {
 #else
     const int s = it & 1;
@@ -502,6 +515,21 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   }
 }
 
+/*
+ * METHOD: 0 euler, 1 rk2, 2 rk4, 3 adaptive rk2(3).  STEP = false: only finish the previous step (used once at the end of
+ * hhd_run so that the state read back is the state after `resets`/`after_resets`).
+ */
+template <int METHOD, bool STEP>
+__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ NeuronShared sh;
+  pdl_trigger();
+  pdl_wait();
+  neuron_shared_init(P, sh);
+  unsigned bar_parity = 0;
+  neuron_phase<METHOD, STEP>(P, *P.base_step + step_offset, reinterpret_cast<NeuronStage*>(smem_raw), sh, bar_parity);
+}
+
 /* Pathways p0..p6 for the synapses of every neuron that spiked in this step. */
 __global__ void __launch_bounds__(STP_BLOCK) k_stp(const __grid_constant__ Params P, const int step_offset) {
   const long long k = *P.base_step + step_offset;
@@ -553,10 +581,7 @@ __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, d
  * another CTA is rewriting.  Otherwise the host launches k_stp, then this kernel with FUSED = false.
  */
 /* Pathways p0..p6 + the zero-delay deliveries + p5 for the spikes of THIS step, one CTA per new spike (fused mode). */
-__global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
-  pdl_trigger();
-  pdl_wait();
-  const long long k = *P.base_step + step_offset;
+__device__ __forceinline__ void spike_new_phase(const Params& P, const long long k) {
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];
@@ -590,11 +615,14 @@ __global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__
   if (lane == 0 && delivered0) atomicAdd(&P.counters[CNT_DELIVERIES], delivered0);
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
+__global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
   pdl_trigger();
   pdl_wait();
-  const long long k = *P.base_step + step_offset;
+  spike_new_phase(P, *P.base_step + step_offset);
+}
+
+template <bool FUSED>
+__device__ __forceinline__ void deliver_phase(const Params& P, const long long k) {
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long lo = P.step_end[(k + 1) % P.W];   /* head at the end of step k - max_delay - 1 */
@@ -645,6 +673,60 @@ __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && e1 > e0) atomicAdd(&P.counters[CNT_EXT], (unsigned long long)(e1 - e0));
   }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
+  pdl_trigger();
+  pdl_wait();
+  deliver_phase<FUSED>(P, *P.base_step + step_offset);
+}
+
+/* ================================================================================================================== *
+ * Whole-run cooperative plan (HHD_PLAN_PERSISTENT): ONE launch runs a whole segment of time steps on the whole chip.
+ * The grid is the persistent state-update grid (every CTA resident, 5 per SM); a step is neuron_phase, grid barrier,
+ * spike_new_phase + deliver_phase by the same CTAs, grid barrier.  It removes the three launches and two dependency
+ * edges per step of the graph plan (~10 us of a 66 us step at 1M neurons).  Same phase functions, same results.
+ * Requires max_delay < refractory steps and a single rank.
+ * ================================================================================================================== */
+/* Grid-wide barrier for a cooperative launch (every CTA resident): one release-add per CTA on a monotone counter, one
+ * thread per CTA spins with acquire loads.  The gpu-scope fences also invalidate the SM's L1 (CCTL.IVALL), so data other
+ * SMs wrote before the barrier is re-read from L2 afterwards.  Measured ~4x cheaper than cooperative_groups' grid.sync()
+ * on 740 CTAs (profiles/r1_notes.md). */
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1ull);
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_grid(const __grid_constant__ Params P, const int n_steps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ NeuronShared sh;
+  NeuronStage* st = reinterpret_cast<NeuronStage*>(smem_raw);
+  neuron_shared_init(P, sh);
+  unsigned bar_parity = 0;
+  const long long k0 = *P.base_step;
+  unsigned long long arrived = *P.grid_bar;      /* a multiple of gridDim.x: every earlier launch completed its barriers */
+  for (int s = 0; s < n_steps; ++s) {
+    const long long k = k0 + s;
+    neuron_phase<METHOD, true>(P, k, st, sh, bar_parity);
+    arrived += gridDim.x;
+    grid_barrier(P.grid_bar, arrived);
+    spike_new_phase(P, k);
+    deliver_phase<true>(P, k);
+    arrived += gridDim.x;
+    grid_barrier(P.grid_bar, arrived);
+  }
+  neuron_phase<METHOD, false>(P, k0 + n_steps, st, sh, bar_parity);
 }
 
 
@@ -1013,6 +1095,7 @@ struct hhd_engine {
   bool comm_ready = false;
   bool cross_instance = false; /* some synapse joins two instances: the resident plan is not applicable */
   bool resident = false;       /* HHD_PLAN_RESIDENT chosen */
+  bool gridplan = false;       /* HHD_PLAN_PERSISTENT chosen: one cooperative launch per segment */
   int res_smem = 0;
   bool pdl = false;            /* programmatic dependent launch between the kernels of the main stream */
   bool fused = false;          /* spike-time STP runs inside k_deliver (max_delay < refractory steps) */
@@ -1117,6 +1200,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (!rc) rc = dev_alloc(h, &h->d_base_step, 1);
   if (!rc) rc = dev_alloc(h, &h->d_counters, CNT_N);
   if (!rc) rc = dev_alloc(h, &P.del_slots, CNT_SLOTS);
+  if (!rc) rc = dev_alloc(h, &P.grid_bar, 1);
   if (!rc) rc = dev_alloc(h, &h->d_mon, MAX_MON);
   if (rc) { std::string m = h->err; hhd_destroy(h); g_create_err = m; return rc; }
   P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
@@ -1649,6 +1733,22 @@ static int finalize_setup(hhd_handle h) {
     while (cs0 * RES_BLOCK < inst) cs0 <<= 1;
     const bool one_wave = (long long)(h->N / inst) * cs0 <= (long long)h->sm_count;
     h->resident = can && (h->cfg.plan == HHD_PLAN_RESIDENT || (h->cfg.plan == HHD_PLAN_AUTO && one_wave && !getenv("HHD_NO_RESIDENT")));
+    {
+      /* whole-run cooperative plan: needs every CTA of the state-update grid resident at once (it is sized that way)
+       * and smem opt-in for k_grid */
+      const void* gfn[4] = {(const void*)k_grid<0>, (const void*)k_grid<1>, (const void*)k_grid<2>, (const void*)k_grid<3>};
+      int per_sm = 0;
+      CU(cudaFuncSetAttribute(gfn[h->cfg.method], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfn[h->cfg.method], NEURON_BLOCK, NEURON_SMEM));
+      const bool gcan = HHD_NEURON_PREFETCH >= 2 && h->cfg.n_ranks == 1 && h->fused && per_sm > 0 && h->NG == h->N;
+      if (h->cfg.plan == HHD_PLAN_PERSISTENT && !gcan)
+        return fail(h, HHD_E_ARG, "HHD_PLAN_PERSISTENT needs max delay < refractory period and a single rank");
+      const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+      const int ggrid = std::max(1, std::min(tiles, h->sm_count * per_sm));
+      h->gridplan = !h->resident && gcan &&
+                    (h->cfg.plan == HHD_PLAN_PERSISTENT || (h->cfg.plan == HHD_PLAN_AUTO && getenv("HHD_GRIDPLAN") && atoi(getenv("HHD_GRIDPLAN"))));
+      if (h->gridplan) h->neuron_grid = std::min(h->neuron_grid, ggrid);
+    }
     if (h->resident) {
       P.inst_size = inst;
       P.n_inst = h->N / inst;
@@ -1667,6 +1767,31 @@ static int finalize_setup(hhd_handle h) {
     }
   }
   h->started = true;
+  return 0;
+}
+
+static int launch_grid(hhd_handle h, int n_steps) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof lc);
+  lc.gridDim = dim3((unsigned)h->neuron_grid);
+  lc.blockDim = dim3(NEURON_BLOCK);
+  lc.dynamicSmemBytes = (size_t)NEURON_SMEM;
+  lc.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  cudaError_t e;
+  switch (h->cfg.method) {
+    case HHD_EULER: e = cudaLaunchKernelEx(&lc, k_grid<0>, h->P, n_steps); break;
+    case HHD_RK2: e = cudaLaunchKernelEx(&lc, k_grid<1>, h->P, n_steps); break;
+    case HHD_RK4: e = cudaLaunchKernelEx(&lc, k_grid<2>, h->P, n_steps); break;
+    default: e = cudaLaunchKernelEx(&lc, k_grid<3>, h->P, n_steps); break;
+  }
+  if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, n_steps);
+  h->cnt.kernel_launches += 2;
   return 0;
 }
 
@@ -1839,14 +1964,14 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   if (prev_n_mon != h->P.n_mon) h->graph_dirty = true;
   for (Monitor& m : h->mons) if (m.active && m.first_step < 0) m.first_step = h->step;
   CU(cudaMemcpyAsync(h->d_base_step, &h->step, 8, cudaMemcpyHostToDevice, h->stream));
-  if (!h->resident && h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
+  if (!h->resident && !h->gridplan && h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
 
   CU(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   while (done < n_steps) {
     const long long seg = std::min<long long>(h->seg_steps, n_steps - done);
-    if (h->resident) {
-      if ((rc = launch_resident(h, (int)seg))) return rc;
+    if (h->resident || h->gridplan) {
+      if ((rc = h->resident ? launch_resident(h, (int)seg) : launch_grid(h, (int)seg))) return rc;
       done += seg;
       CU(cudaGetLastError());
       if ((rc = drain_spikes(h))) return rc;

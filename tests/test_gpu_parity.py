@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 STATE = ["V", "w", "g_AMPA_on", "g_AMPA_off", "g_GABA_on", "g_GABA_off", "g_NMDA_on", "g_NMDA_off"]
 
 
-PLANS = ["graph", "resident"]     # grid-wide kernels in CUDA graphs / one persistent thread-block cluster per instance
+PLANS = ["graph", "resident", "persistent"]   # CUDA graphs of grid-wide kernels / one cluster per instance / one cooperative launch
 
 
 def gpu_cpu(g, plan, **kw):
