@@ -339,6 +339,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_PER_NEURON_UPDATE * n / (prof["k_neuron"] * 1e-6) / 1e9
+    traffic = None
+    try:        # DRAM bytes per launch of the same kernel from the committed ncu capture (same workload only)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.workload == "columns" and n == 1003000 and args.method == "euler":
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     out = dict(
         metric="neuron_updates_per_s", value=value, unit="neuron-updates/s", n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -346,7 +353,7 @@ def main():
         syn_events_per_s=syn_ev / (dev_ms * 1e-3), realtime_factor=bio_s / (dev_ms * 1e-3),
         mean_rate_hz=spikes / n_total / bio_s, us_per_time_step=dev_ms * 1e3 / (S * args.steps),
         roofline=dict(bound="hbm", kernel="k_neuron<%s>" % args.method, achieved=achieved, peak=peak, unit="GB/s",
-                      frac=achieved / peak, traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                      frac=achieved / peak, traffic=traffic, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                       algorithmic_bytes_per_launch=BYTES_PER_NEURON_UPDATE * n,
                       us_per_launch=prof, note="mean of %d launches, CUDA events between kernels on the engine's stream" % min(S, 200)),
         e2e=dict(value=e2e_value, unit="neuron-updates/s", h2d_bytes_per_step=int(n * 8), d2h_bytes_per_step=int(d2h / args.steps),

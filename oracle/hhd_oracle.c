@@ -138,6 +138,7 @@ struct hhd_engine {
   /* scratch of the current step */
   int32_t* cur_spikes; int n_cur_spikes;      /* local ids */
   int32_t* cur_wcross; int n_cur_wcross;
+  uint8_t* flag_scratch;
   int step_open;
   hhd_counters cnt;
 };
@@ -195,7 +196,7 @@ void hhd_destroy(hhd_handle h) {
   if (!h) return;
   for (int i = 0; i < HHD_N_PARAMS; ++i) free(h->par[i]);
   for (int i = 0; i < 8; ++i) free(h->x[i]);
-  free(h->last_spike); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross);
+  free(h->last_spike); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch);
   free(h->src); free(h->tgt); free(h->chan); free(h->gmax); free(h->U); free(h->tau_rec); free(h->tau_fac);
   free(h->pfail); free(h->delay_steps); free(h->u); free(h->R); free(h->a_syn); free(h->failure); free(h->touched);
   free(h->row_ptr); free(h->row_syn);
@@ -562,19 +563,28 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
   /* slot `thresholds`: spike = V > V_up and not_refractory (:304); w_crossing (:306) evaluated on the same state */
   h->n_cur_spikes = 0;
   h->n_cur_wcross = 0;
+  if (!h->flag_scratch) h->flag_scratch = (uint8_t*)malloc((size_t)h->N);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int i = 0; i < h->N; ++i) {
     const int not_refractory = (k - h->lastspike_step[i]) >= h->refr_steps;
-    if (h->x[HHD_V][i] > h->par[HHD_P_VUP][i] && not_refractory) {
-      h->cur_spikes[h->n_cur_spikes++] = i;
-      h->lastspike_step[i] = k;
-    }
+    uint8_t f = (h->x[HHD_V][i] > h->par[HHD_P_VUP][i] && not_refractory) ? 1 : 0;
     npar p = load_par(h, i);
     double x[8];
     for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
     subexpr s;
     subexpressions(h, &p, x, &s);
     const double w = x[HHD_W];
-    if (w > s.w_V - s.D0 / p.tauw && w < s.w_V + s.D0 / p.tauw && x[HHD_V] <= p.VT) h->cur_wcross[h->n_cur_wcross++] = i;
+    if (w > s.w_V - s.D0 / p.tauw && w < s.w_V + s.D0 / p.tauw && x[HHD_V] <= p.VT) f |= 2;
+    h->flag_scratch[i] = f;
+  }
+  for (int i = 0; i < h->N; ++i) {                      /* lists in ascending neuron order, as Brian's spike space */
+    if (h->flag_scratch[i] & 1) {
+      h->cur_spikes[h->n_cur_spikes++] = i;
+      h->lastspike_step[i] = k;
+    }
+    if (h->flag_scratch[i] & 2) h->cur_wcross[h->n_cur_wcross++] = i;
   }
   h->cnt.spikes += h->n_cur_spikes;
   h->cnt.w_crossings += h->n_cur_wcross;
