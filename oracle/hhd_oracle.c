@@ -128,6 +128,7 @@ struct hhd_engine {
   int64_t* row_ptr; int64_t* row_syn;   /* CSR by GLOBAL source, synapse ids ascending within a row */
   int64_t max_delay;
   vec64* queue;                         /* [max_delay+1] slots of synapse ids: Brian's SpikeQueue */
+  double* pendd;                        /* HHD_ACCUM_FP64: [3*N] per-step sums of increments */
   int64_t* pend[2];                     /* HHD_ACCUM_FIXED: [3*N] int64 sums for on/off (identical, kept for clarity) */
   /* inputs */
   ext_source* ext; int n_ext; int64_t ext_syn_total;
@@ -201,7 +202,7 @@ void hhd_destroy(hhd_handle h) {
   free(h->pfail); free(h->delay_steps); free(h->u); free(h->R); free(h->a_syn); free(h->failure); free(h->touched);
   free(h->row_ptr); free(h->row_syn);
   if (h->queue) { for (int64_t s = 0; s <= h->max_delay; ++s) free(h->queue[s].v); free(h->queue); }
-  free(h->pend[0]); free(h->pend[1]);
+  free(h->pend[0]); free(h->pend[1]); free(h->pendd);
   for (int i = 0; i < h->n_ext; ++i) free_ext(&h->ext[i]);
   free(h->ext);
   for (int i = 0; i < h->n_mon; ++i) { free(h->mon[i].idx); free(h->mon[i].samples.v); }
@@ -512,6 +513,7 @@ static double monitor_value(const hhd_handle h, int var, int i) {
 static int check_ready(hhd_handle h) {
   if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
   if (!h->channels_set) return fail(h, HHD_E_STATE, "hhd_set_channels has not been called");
+  if (!h->pendd) h->pendd = (double*)calloc((size_t)3 * h->N, sizeof(double));
   if (h->cfg.accum == HHD_ACCUM_FIXED && !h->pend[0]) {
     h->pend[0] = (int64_t*)calloc((size_t)3 * h->N, 8);
     h->pend[1] = (int64_t*)calloc((size_t)3 * h->N, 8);
@@ -603,8 +605,11 @@ static void add_increment(hhd_handle h, int c, int tgt_local, double inc) {
     const int64_t q = llrint(inc * 1099511627776.0);   /* 2^40 */
     h->pend[0][(size_t)c * h->N + tgt_local] += q;
   } else {
-    h->x[HHD_G_AMPA_ON + 2 * c][tgt_local] += inc;     /* p7a / p8a / p9a */
-    h->x[HHD_G_AMPA_OFF + 2 * c][tgt_local] += inc;    /* p7b / p8b / p9b */
+    /* p7a/p7b ... p9b: `g_X_on_post += inc; g_X_off_post += inc`.  The increments of one step are summed per (target,
+     * channel) first and the sum is added to both conductances at the end of the slot — g + (a + b) instead of
+     * (g + a) + b — because that is the only order a parallel engine can reproduce; identical whenever a target receives
+     * at most two increments per channel in a step, a rounding-level difference otherwise. */
+    h->pendd[(size_t)c * h->N + tgt_local] += inc;
   }
 }
 
@@ -662,6 +667,17 @@ int hhdo_step_end(hhd_handle h, const int32_t* all_spikes, int32_t n_all) {
         h->cnt.ext_events++;
       }
     }
+  }
+  if (h->cfg.accum != HHD_ACCUM_FIXED) {
+    for (int c = 0; c < 3; ++c)
+      for (int i = 0; i < h->N; ++i) {
+        const double inc = h->pendd[(size_t)c * h->N + i];
+        if (inc != 0.0) {
+          h->x[HHD_G_AMPA_ON + 2 * c][i] += inc;
+          h->x[HHD_G_AMPA_OFF + 2 * c][i] += inc;
+          h->pendd[(size_t)c * h->N + i] = 0.0;
+        }
+      }
   }
   if (h->cfg.accum == HHD_ACCUM_FIXED) {
     for (int c = 0; c < 3; ++c)

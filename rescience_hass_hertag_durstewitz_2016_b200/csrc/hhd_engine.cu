@@ -45,7 +45,9 @@
 
 #define MAX_MON 16
 #define MAX_RED 4   /* reduced (sum/mean) monitors: their per-thread accumulators live in registers */
+#ifndef NEURON_BLOCK
 #define NEURON_BLOCK 128
+#endif
 #ifndef STP_BLOCK
 #define STP_BLOCK 128
 #endif
@@ -58,7 +60,8 @@
 enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_N };
 #define CNT_SLOTS 256   /* the delivery counter is spread over 256 addresses: thousands of warps bump it every step, and
                            same-address atomics serialise in one L2 slice */
-enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2 };
+enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2, FLAG_HAS_PREV = 2 };   /* meta bit 1: the stored state is the result of an integrated step whose
+                                                                     w_crossing test is still due (done at the start of the next pass) */
 
 struct MonDesc {
   int var, reduce, active, red_slot;
@@ -93,7 +96,10 @@ struct Params {
   double* last_spike;          /* [NG] */
   int* meta;                   /* [N] lastspike_step * 4 + flags of the previous step */
   const unsigned char* has_out;/* [NG] */
-  long long* pend;             /* [3][N] fixed-point increments (HHD_ACCUM_FIXED) */
+  long long* pend;             /* [3][n_pad] synaptic increments of the step in progress, summed per (channel, target):
+                                  fp64 bits (HHD_ACCUM_FP64) or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED); consumed
+                                  and cleared by the next state-update pass */
+  long long n_pad;             /* neurons rounded up to whole tiles */
   /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
   const long long* row_ptr;    /* [NG+1] */
   SynHot* hot;
@@ -195,9 +201,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
                                      2: TMA + one mbarrier per CTA; 1: per-thread cp.async; 0: plain loads */
 #endif
 #ifndef HHD_NEURON_MINBLOCKS_EULER
-#define HHD_NEURON_MINBLOCKS_EULER 5
+#define HHD_NEURON_MINBLOCKS_EULER 4   /* 128 registers: the single-evaluation kernel spills at the 96 a fifth CTA would allow */
 #endif
-#define NEURON_FIELDS 21   /* 8 state + 12 parameters + last_spike */
+#define NEURON_FIELDS 21   /* 8 state + 12 parameters + last_spike (the 3 pending-increment words are prefetched into
+                              registers one tile ahead: staging them would cost the fifth resident CTA per SM) */
 struct NeuronStage {
   double f[NEURON_FIELDS][NEURON_BLOCK];
   int meta[NEURON_BLOCK];
@@ -298,8 +305,13 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   unsigned n_spk = 0, n_wc = 0, n_bad = 0;
 
   int tile = blockIdx.x;
+  long long pd_next[3] = {0, 0, 0};
 #if HHD_NEURON_PREFETCH
   issue(tile, 0);
+  if (tile * NEURON_BLOCK + tid < P.N) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pd_next[c] = P.pend[(size_t)c * P.n_pad + tile * NEURON_BLOCK + tid];
+  }
 #endif
 #if HHD_NEURON_PREFETCH >= 2
   issue(tile + gridDim.x, 1);        /* two tiles in flight from the start */
@@ -311,6 +323,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     NeuronPar p;
     double ls = 0.0;
     int meta = 0;
+    long long pd[3] = {0, 0, 0};
 #if !HHD_NEURON_PREFETCH
     if (live) {
 #pragma unroll
@@ -318,6 +331,8 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       p = load_par(P, i);
       ls = P.last_spike[P.off + i];
       meta = P.meta[i];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pd[c] = P.pend[(size_t)c * P.n_pad + i];
     }
     if (false) {
       const int s = 0;
@@ -342,6 +357,15 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       ls = st[s].f[20][tid];
       meta = st[s].meta[tid];
     }
+#if HHD_NEURON_PREFETCH
+    {   /* pending increments: this tile's were requested one iteration ago, the next tile's are requested now */
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pd[c] = pd_next[c];
+      const int in = i + (int)gridDim.x * NEURON_BLOCK;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pd_next[c] = in < P.N ? P.pend[(size_t)c * P.n_pad + in] : 0;
+    }
+#endif
 #if HHD_NEURON_PREFETCH == 2
     __syncthreads();   /* every thread holds its neuron of this tile in registers: stage s is free again */
     issue(tile + 2 * gridDim.x, s);    /* so the tile after next is requested NOW: two tiles in flight with two stages */
@@ -349,29 +373,38 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     __syncwarp();      /* the warp's part of stage s is free again */
     issue(tile + 2 * gridDim.x, s);
 #endif
+    SubExpr S;
+    bool wcross = false;
     if (live) {
-      /* ---- finish step k-1 -------------------------------------------------------------------------------- */
-      if (P.accum == HHD_ACCUM_FIXED) {
+      /* ---- the part of step k-1 that had to wait for that step's synaptic deliveries ------------------------------
+       * x is the state right after the integration of step k-1.  Its subexpressions S decide the `w_crossing` event of
+       * step k-1 (slot `thresholds`, codes/CortexNetwork.py:306) and — unless this neuron received input or was reset,
+       * and then only their linear part changes — ARE the subexpressions of the first stage of step k: one evaluation
+       * (two exponentials, three divisions) per neuron-step instead of two. */
+      hhd_subexpr(P.cc, p, x, S);
+      if (meta & FLAG_HAS_PREV) {
+        const double band = hhd_div(S.D0, p.tauw);
+        wcross = (x[1] > S.w_V - band) && (x[1] < S.w_V + band) && (x[0] <= p.VT);
+      }
+      bool new_g = false;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const long long q = P.pend[(size_t)c * P.N + i];
-          if (q) {
-            const double inc = (double)q * (1.0 / 1099511627776.0);
-            x[2 + 2 * c] += inc;
-            x[3 + 2 * c] += inc;
-            P.pend[(size_t)c * P.N + i] = 0;
-          }
+      for (int c = 0; c < 3; ++c) {          /* slot `synapses`: g_X_on_post += ..., g_X_off_post += ... (:367-372) */
+        if (pd[c]) {
+          const double inc = P.accum == HHD_ACCUM_FIXED ? (double)pd[c] * (1.0 / 1099511627776.0) : __longlong_as_double(pd[c]);
+          x[2 + 2 * c] += inc;
+          x[3 + 2 * c] += inc;
+          P.pend[(size_t)c * P.n_pad + i] = 0;
+          new_g = true;
         }
       }
       if (meta & FLAG_SPIKED) {        /* slot `resets`: V = V_r; w += b   (codes/CortexNetwork.py:305) */
         x[0] = p.Vr;
         x[1] += p.b;
+        hhd_subexpr(P.cc, p, x, S);
+      } else if (new_g) {
+        hhd_subexpr_new_g(P.cc, p, x, S);
       }
-      if (meta & FLAG_WCROSS) {        /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
-        SubExpr sx;
-        hhd_subexpr(P.cc, p, x, sx);
-        x[1] = sx.w_V - hhd_div(sx.D0, p.tauw);
-      }
+      if (wcross) x[1] = S.w_V - hhd_div(S.D0, p.tauw);      /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
     }
     if (!STEP) {
       if (live) {
@@ -379,14 +412,14 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
         for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
         P.meta[i] = meta & ~3;
       }
+      n_wc += wcross;
       continue;
     }
 
-    /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510).  State variables are
-     *      written now; derived ones (I_tot ...) after the update, from the subexpressions of the first stage -------- */
+    /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510) ----------------------------- */
     for (int m = 0; m < P.n_mon; ++m) {
       const MonDesc& md = mon_sh[m];
-      if (!md.active || hhd_var_is_derived(md.var)) continue;
+      if (!md.active) continue;
       const long long sample = k - md.k0;
       if (sample < 0 || sample >= md.capacity) {
         if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
@@ -395,7 +428,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       int slot = -1;
       if (live) slot = md.slot ? md.slot[i] : i;
       if (slot >= 0) {
-        const double v = hhd_var_value(P.cc, p, x, md.var, ls);
+        const double v = hhd_var_is_derived(md.var) ? hhd_var_from_subexpr(S, md.var) : hhd_var_value(P.cc, p, x, md.var, ls);
         if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
         else {
 #pragma unroll
@@ -404,47 +437,19 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       }
     }
 
-    bool spiked = false, wcross = false, bad = false;
+    bool spiked = false, bad = false;
     if (live) {
       /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
 #if !(HHD_EXPERIMENT & 2)
-      SubExpr s1;
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1);
-#else
-      SubExpr s1;
-      hhd_subexpr(P.cc, p, x, s1);
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S);
 #endif
-      for (int m = 0; m < P.n_mon; ++m) {
-        const MonDesc& md = mon_sh[m];
-        if (!md.active || !hhd_var_is_derived(md.var)) continue;
-        const long long sample = k - md.k0;
-        if (sample < 0 || sample >= md.capacity) {
-          if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
-          continue;
-        }
-        const int slot = md.slot ? md.slot[i] : i;
-        if (slot >= 0) {
-          const double v = hhd_var_from_subexpr(s1, md.var);
-          if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
-          else {
-#pragma unroll
-            for (int r = 0; r < MAX_RED; ++r) if (r == md.red_slot) mon_acc[r] += v;
-          }
-        }
-      }
       bad = !(isfinite(x[0]) && isfinite(x[1]));
-      /* ---- slot `thresholds` (:304, 306) --------------------------------------------------------------------- */
+      /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
       const int lastk = meta >> 2;
       spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
-#if !(HHD_EXPERIMENT & 1)
-      SubExpr sx;
-      hhd_subexpr(P.cc, p, x, sx);
-      const double band = hhd_div(sx.D0, p.tauw);
-      wcross = (x[1] > sx.w_V - band) && (x[1] < sx.w_V + band) && (x[0] <= p.VT);
-#endif
 #pragma unroll
       for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
-      P.meta[i] = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0);
+      P.meta[i] = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | FLAG_HAS_PREV;
     }
     /* ---- warp-ballot spike compaction: one atomic per warp that has spikes ----------------------------------- */
     const unsigned bal = __ballot_sync(0xffffffffu, spiked);
@@ -474,7 +479,11 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     n_bad += bad;
   }
   cp_async_wait<0>();
-  if (!STEP) return;
+  if (!STEP) {                      /* only the w_crossing events found while finishing the last step are left to count */
+    n_wc = __reduce_add_sync(0xffffffffu, n_wc);
+    if (lane == 0 && n_wc) atomicAdd(&P.counters[CNT_WCROSS], (unsigned long long)n_wc);
+    return;
+  }
 
   /* ---- once per CTA: reduced monitors (LFP) and counters ------------------------------------------------------- */
   for (int m = 0; m < P.n_mon; ++m) {
@@ -558,12 +567,12 @@ __global__ void __launch_bounds__(STP_BLOCK) k_stp(const __grid_constant__ Param
 }
 
 __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc) {
+  /* summed per (channel, target) for this step; the target's next state-update pass adds the sum to g_on and g_off */
   if (P.accum == HHD_ACCUM_FIXED) {
     const long long q = __double2ll_rn(inc * 1099511627776.0);
-    atomicAdd((unsigned long long*)&P.pend[(size_t)c * P.N + tgt], (unsigned long long)q);
+    atomicAdd((unsigned long long*)&P.pend[(size_t)c * P.n_pad + tgt], (unsigned long long)q);
   } else {
-    atomicAdd(&P.x[2 + 2 * c][tgt], inc);   /* g_X_on_post  += ... */
-    atomicAdd(&P.x[3 + 2 * c][tgt], inc);   /* g_X_off_post += ... */
+    atomicAdd(reinterpret_cast<double*>(&P.pend[(size_t)c * P.n_pad + tgt]), inc);
   }
 }
 
@@ -592,7 +601,7 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
     const int j = P.spk_neuron[(unsigned)sp & P.cap_mask];
     const double last = P.last_spike[j];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-    for (long long r = r0 + threadIdx.x; r < r1; r += STP_BLOCK) {
+    for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
       SynStp sy = P.stp[r];
       const SynHot sh = P.hot[r];
       const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t,
@@ -629,8 +638,8 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
   const unsigned long long hi = *P.head;
   /* fused mode: the spikes of this step belong to k_spike_new, which runs concurrently on the second stream */
   const unsigned long long old_hi = FUSED ? P.step_end[(k + P.W - 1) % P.W] : hi;
-  const unsigned warps = (gridDim.x * DELIVER_BLOCK) >> 5;
-  const unsigned wid = (blockIdx.x * DELIVER_BLOCK + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   unsigned long long delivered = 0;
   for (unsigned long long sp = lo + wid; sp < old_hi; sp += warps) {
     const unsigned pos = (unsigned)sp & P.cap_mask;
@@ -663,7 +672,7 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
   /* SpikeGeneratorGroup events of this step: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
   if (P.ext_ptr && k >= P.ext_first && k <= P.ext_last) {
     const int e0 = P.ext_ptr[k - P.ext_first], e1 = P.ext_ptr[k - P.ext_first + 1];
-    for (int e = e0 + blockIdx.x * DELIVER_BLOCK + threadIdx.x; e < e1; e += gridDim.x * DELIVER_BLOCK) {
+    for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
       const double failure = hhd_philox_u01(P.seed, (unsigned long long)P.ext_id[e], (unsigned long long)k, 1) < P.ext_pfail[e] ? 1.0 : 0.0;
       const unsigned char mask = P.ext_mask[e];
       const double g = P.ext_gmax[e] * (1.0 - failure);
@@ -858,6 +867,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
     bool spiked = false, wcross = false;
     if (live) {
       SubExpr s1;
+      hhd_subexpr(P.cc, p, x, s1);
       hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1);
       n_bad += !(isfinite(x[0]) && isfinite(x[1]));
       const int lastk = meta >> 2;
@@ -1192,7 +1202,8 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   unsigned char* ho = nullptr;
   if (!rc) rc = dev_alloc(h, &ho, h->NG);
   P.has_out = ho;
-  if (!rc) rc = dev_alloc(h, &P.pend, (size_t)3 * h->N);
+  P.n_pad = (long long)n_pad;
+  if (!rc) rc = dev_alloc(h, &P.pend, (size_t)3 * n_pad);
   long long* rp = nullptr;
   if (!rc) rc = dev_alloc(h, &rp, (size_t)h->NG + 1);
   P.row_ptr = rp;

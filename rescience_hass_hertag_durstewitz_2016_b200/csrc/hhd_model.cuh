@@ -23,7 +23,7 @@ struct NeuronPar {
 };
 
 struct SubExpr {
-  double I_AMPA, I_GABA, I_NMDA, I_syn, I_inj, I_tot, I_exp, w_V, D0, dD0, ex, g[3];
+  double I_AMPA, I_GABA, I_NMDA, I_syn, I_inj, I_tot, I_exp, w_V, D0, dD0, ex, Mg, g[3];
 };
 
 /* state order: V, w, gA_on, gA_off, gG_on, gG_off, gN_on, gN_off (= HHD_V .. HHD_G_NMDA_OFF) */
@@ -36,6 +36,7 @@ __device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const Neuron
   const double Mg = hhd_div(1.0, 1.0 + cc.mg_fac * hhd_exp(cc.mg_slope * (cc.mg_half - V)));
   s.I_GABA = s.g[1] * (cc.E[1] - V);
   s.I_NMDA = (s.g[2] * (cc.E[2] - V)) * Mg;
+  s.Mg = Mg;
   s.I_syn = (s.I_AMPA + s.I_NMDA) + s.I_GABA;
   s.I_inj = p.IDC + 0.0;
   s.I_tot = s.I_syn + s.I_inj;
@@ -46,11 +47,26 @@ __device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const Neuron
   s.dD0 = p.C * (s.ex - 1.0);
 }
 
-/* Right-hand sides at state x; `s` returns the subexpressions of that state (the first stage's are exactly what a
- * StateMonitor of I_tot, I_syn ... samples in Brian's `start` slot, so monitors of derived variables cost nothing extra). */
-__device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t,
-                                          double ls, double d[8], SubExpr& s) {
-  hhd_subexpr(cc, p, x, s);
+/* The subexpressions again after ONLY the conductances changed (synaptic increments): Mg, exp((V-V_T)/delta_T), I_exp and
+ * dD0 depend on V alone and are kept; everything else is recomputed with the operations and order of hhd_subexpr, so the
+ * result is bit-identical to a full re-evaluation at a third of its cost (no exponential, one division). */
+__device__ __forceinline__ void hhd_subexpr_new_g(const ChannelConst& cc, const NeuronPar& p, const double x[8], SubExpr& s) {
+  const double V = x[0];
+  s.g[0] = x[3] - x[2];
+  s.g[1] = x[5] - x[4];
+  s.g[2] = x[7] - x[6];
+  s.I_AMPA = s.g[0] * (cc.E[0] - V);
+  s.I_GABA = s.g[1] * (cc.E[1] - V);
+  s.I_NMDA = (s.g[2] * (cc.E[2] - V)) * s.Mg;
+  s.I_syn = (s.I_AMPA + s.I_NMDA) + s.I_GABA;
+  s.I_tot = s.I_syn + s.I_inj;
+  s.w_V = (s.I_tot + s.I_exp) - p.gL * (V - p.EL);
+  s.D0 = hhd_div(p.C, p.gL) * s.w_V;
+}
+
+/* Right-hand sides at state x given the subexpressions `s` of that state. */
+__device__ __forceinline__ void hhd_rhs(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t, double ls,
+                                        const SubExpr& s, double d[8]) {
   const double V = x[0], w = x[1];
   const double a = ((s.I_tot >= p.Iref) ? 1.0 : 0.0) * ((t - ls < cc.window_ms) ? 1.0 : 0.0);
   const double dV = (a * hhd_div(-p.gL, p.C)) * (V - p.Vdep) + hhd_div((1.0 - a) * (s.w_V - w), p.C);
@@ -66,13 +82,21 @@ __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPa
   }
 }
 
-/* Brian 2's ExplicitStateUpdaters: METHOD 0 euler, 1 rk2 (midpoint), 2 rk4. */
+/* Subexpressions + right-hand sides (stages after the first). */
+__device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t,
+                                          double ls, double d[8], SubExpr& s) {
+  hhd_subexpr(cc, p, x, s);
+  hhd_rhs(cc, p, x, t, ls, s, d);
+}
+
+/* Brian 2's ExplicitStateUpdaters: METHOD 0 euler, 1 rk2 (midpoint), 2 rk4.  `s1` = subexpressions of the state x on entry
+ * (the caller has them already: they also decide the deferred w_crossing test and feed the monitors). */
 template <int METHOD>
 __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t,
-                                              double ls, double dt, SubExpr& s1) {
+                                              double ls, double dt, const SubExpr& s1) {
   double k1[8], y[8];
   SubExpr sk;
-  hhd_deriv(cc, p, x, t, ls, k1, s1);
+  hhd_rhs(cc, p, x, t, ls, s1, k1);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k1[v] = dt * k1[v];
   if (METHOD == 0) {
@@ -110,7 +134,7 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
  * function integrate_rk23 of oracle/hhd_oracle.c (IEEE sqrt only), see there for the controller. */
 template <>
 __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const NeuronPar& p, double x[8], double t0,
-                                                 double ls, double dt, SubExpr& s1) {
+                                                 double ls, double dt, const SubExpr& s1) {
   const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
   double t = 0.0, hs = dt;
   bool first = true;
@@ -118,7 +142,7 @@ __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const N
     if (t + hs > dt) hs = dt - t;
     double k1[8], k2[8], k3[8], y[8], ynew[8];
     SubExpr sk;
-    if (first) hhd_deriv(cc, p, x, t0 + t, ls, k1, s1);
+    if (first) hhd_rhs(cc, p, x, t0 + t, ls, s1, k1);
     else hhd_deriv(cc, p, x, t0 + t, ls, k1, sk);
     first = false;
 #pragma unroll
