@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="columns", choices=["columns", "column"])
+    ap.add_argument("--workload", default="columns", choices=["columns", "column", "multicolumn"],
+                    help="columns: tiled independent columns; multicolumn: ring of columns with inter-column synapses; column: one column")
     ap.add_argument("--columns", type=int, default=0, help="columns in the scaled network (0 = workload default)")
     ap.add_argument("--template", default="n1000", choices=["n1000", "n200"], help="one-column fixture that is tiled")
     ap.add_argument("--method", default="euler", choices=["euler", "rk2", "rk4", "rk23", "gsl_rk2"])
@@ -58,8 +59,9 @@ def one_column(template):
     if not os.path.exists(os.path.join(ROOT, "tests", "golden", name + ".npz")):
         name = "net_n200_s0"
     g = load_golden(name)
+    from oracle_binding import golden_groups
     return dict(NeuPar=g["NeuPar"], V0=g["V0"], STypPar=g["STypPar"], SynPar=g["SynPar"], source_arr=g["source_arr"],
-                target_arr=g["target_arr"], I_DC=default_idc(g),
+                target_arr=g["target_arr"], I_DC=default_idc(g), groups=[grp[0] for grp in golden_groups(g)],
                 name="%s: %d neurons, %d synapses" % (name, g["NeuPar"].shape[1], g["SynPar"].shape[1]))
 
 
@@ -71,7 +73,7 @@ def build_workload(args, rank, world, device_synapses=False):
         ncol = 1
     else:
         ncol = args.columns or 1000
-    per_rank = ncol // world if args.workload == "columns" else 1
+    per_rank = ncol // world if args.workload != "column" else 1
     if device_synapses:
         # neurons on the host (96 B each), synapses generated straight into HBM by make_engine
         net = tile_columns(col["NeuPar"], col["V0"], np.zeros((7, 0)), [], [], col["I_DC"], per_rank)
@@ -102,9 +104,19 @@ def make_engine(cls, net, args, seed, **kw):
             has_out = np.zeros(net["n_per_column"], dtype=np.uint8)
             has_out[np.unique(col["source_arr"])] = 1
             e.set_has_outgoing(np.tile(has_out, kw["n_global"] // net["n_per_column"]))
-        e.set_synapses_dev(*tile_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], net["columns_rank"],
-                                                 net["n_per_column"], dev, id_offset=off),
-                           syn_id_base=kw.get("rank", 0) * net["nsyn"])
+        if args.workload == "multicolumn":
+            from rescience_hass_hertag_durstewitz_2016_b200.scaled import multicolumn_synapses_device
+            c0 = off // net["n_per_column"]
+            syn = multicolumn_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], col["groups"], net["columns_total"],
+                                              net["n_per_column"], dev, c0, c0 + net["columns_rank"], seed=1)
+            net["nsyn"] = int(syn[0].numel())
+            if kw.get("n_ranks", 1) > 1:                      # every PC / IN_CC_L5 / IN_F_L5 cell projects somewhere
+                e.set_has_outgoing(np.ones(kw["n_global"], dtype=np.uint8))
+            e.set_synapses_dev(*syn, syn_id_base=kw.get("rank", 0) * (1 << 30))
+        else:
+            e.set_synapses_dev(*tile_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], net["columns_rank"],
+                                                     net["n_per_column"], dev, id_offset=off),
+                               syn_id_base=kw.get("rank", 0) * net["nsyn"])
     return e
 
 
@@ -168,7 +180,8 @@ def cpu_sample(args, seconds, threads):
     from oracle_binding import OracleEngine
     import copy
     a2 = copy.copy(args)
-    if args.workload == "columns":
+    if args.workload != "column":
+        a2.workload = "columns"           # the CPU sample is always a block of independent columns
         a2.columns = min(args.columns or 1000, CPU_SAMPLE_COLUMNS)
     net = build_workload(a2, 0, 1)
     e = make_engine(OracleEngine, net, args, seed=1, record_spikes=True)
@@ -214,9 +227,11 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(args, net, world):
     n = net["NeuPar"].shape[1]
-    return dict(workload=("%d-column PFC network (%s tiled, block-diagonal)" % (net["columns_total"], net["template"])
-                          if args.workload == "columns" else "one PFC column (%s)" % net["template"]),
-                neurons=n * (world if args.workload == "columns" else 1), synapses=net["nsyn"] * (world if args.workload == "columns" else 1),
+    name = {"columns": "%d-column PFC network (%s tiled, block-diagonal)" % (net["columns_total"], net["template"]),
+            "multicolumn": "ring of %d PFC columns (%s tiled) with inter-column synapses drawn by the reference's rules" % (net["columns_total"], net["template"]),
+            "column": "one PFC column (%s)" % net["template"]}[args.workload]
+    return dict(workload=name,
+                neurons=n * (world if args.workload != "column" else 1), synapses=net["nsyn"] * (world if args.workload != "column" else 1),
                 method=args.method, dt_ms=args.dt, time_steps_per_step=args.window, accumulate=args.accum,
                 monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
                 l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
@@ -342,7 +357,7 @@ def main():
     traffic = None
     try:        # DRAM bytes per launch of the same kernel from the committed ncu capture (same workload only)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if args.workload == "columns" and n == 1003000 and args.method == "euler":
+        if args.workload == "columns" and n == 1003000 and args.method == "euler" and world == 1:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass

@@ -42,3 +42,90 @@ def tile_synapses_device(SynPar, source_arr, target_arr, n_columns, n_per_column
     chan = (S[0].to(torch.int64) - 1).to(torch.uint8).repeat(k).contiguous()
     rows = [S[r].repeat(k).contiguous() for r in (4, 1, 2, 3, 6, 5)]   # g_max, U, tau_rec, tau_fac, p_fail, delay
     return (src, tgt, chan) + tuple(rows)
+
+
+def _clipped(torch, draw, lo, hi, gen, device):
+    """The reference's `rand_par` rule (codes/NetworkSetup.py:621-643): draws outside [lo, hi] are replaced by uniform ones."""
+    bad = (draw < lo) | (draw > hi)
+    return torch.where(bad, lo + (hi - lo) * torch.rand(draw.shape, generator=gen, device=device, dtype=torch.float64), draw)
+
+
+def inter_column_synapses_device(groups, n_per_column, n_columns, device, col_lo=0, col_hi=None, seed=0):
+    """Inter-column synapses of a ring of `n_columns` identical columns, for the TARGET columns [col_lo, col_hi), drawn on
+    the GPU with the reference's rules (codes/ParamSetup.py:575-587, codes/NetworkSetup.py:267-321): PC_L23 -> PC_L23 at
+    +-2 and +-4 columns, IN_CC_L5 -> PC_L5 and IN_F_L5 -> PC_L5 at +-1, connection probability and peak conductance
+    falling off as exp(-d/0.909), delay mean and spread growing linearly with d (up to ~15 ms, i.e. beyond the refractory
+    period), AMPA synapses with an NMDA twin of the same delay, STP classes mixed as within a column.
+    `groups[g]` = template-local neuron ids of cell group g.  Pairs are drawn WITH replacement (< 1 % duplicates), which
+    the reference's own blocks also contain; this is the synthetic stand-in for SURVEY §8f-1, not a bit-exact port.
+    -> (src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms) as torch CUDA tensors, ids global."""
+    import contextlib
+    import io
+    import torch
+    from .codes.ParamSetup import ParamSetup
+    with contextlib.redirect_stdout(io.StringIO()):
+        ps = ParamSetup(1000, 1, ([1, 1, 1, 1], [1, 1, 1, 1], np.ones((10, 14))))
+    SynTypes, Syngmax, Syndelay, STSP_prob, STSP_types, pCon, S_sig = ps[8], ps[9], ps[10], ps[12], ps[13], ps[14], ps[16]
+    STSP_setup, get_SynType, get_STSP_prob, get_STSP_types = ps[26], ps[27], ps[28], ps[29]
+    rules, coef, offsets = ps[31]
+    col_hi = n_columns if col_hi is None else col_hi
+    ncol = col_hi - col_lo
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed) * 7919 + 17 * col_lo + 1)
+    cols = torch.arange(col_lo, col_hi, device=device, dtype=torch.int64)[:, None]
+    out = [[] for _ in range(9)]
+    f64 = dict(generator=gen, device=device, dtype=torch.float64)
+    for q, (ia, ja) in enumerate(rules):
+        tg = torch.as_tensor(np.asarray(groups[ia], dtype=np.int64), device=device)
+        sr = torch.as_tensor(np.asarray(groups[ja], dtype=np.int64), device=device)
+        if len(tg) == 0 or len(sr) == 0:
+            continue
+        for off in offsets[q]:
+            dist = abs(off)
+            fall = float(np.exp(-dist / coef[q][0]))
+            n = int(round(pCon[ia, ja] * fall * len(tg) * len(sr), 0))
+            if n == 0 or n_columns <= dist:
+                continue
+            t_loc = tg[torch.randint(len(tg), (ncol, n), generator=gen, device=device)]
+            s_loc = sr[torch.randint(len(sr), (ncol, n), generator=gen, device=device)]
+            tgt = (cols * n_per_column + t_loc).reshape(-1)
+            src = (((cols - off) % n_columns) * n_per_column + s_loc).reshape(-1)      # target column = source column + off
+            m = tgt.numel()
+            d_mean, d_sig = float(Syndelay[ia, ja] + coef[q][1] * dist), float(S_sig[ia, ja, 1] + coef[q][1] * dist)
+            delay = _clipped(torch, d_mean + d_sig * torch.randn(m, **f64), 0.0, 2.0 * d_mean, gen, device)
+            g_mean, g_sig = float(Syngmax[ia, ja]) * fall, float(S_sig[ia, ja, 0]) * fall
+            mu, sd = np.log(g_mean ** 2 / np.sqrt(g_sig ** 2 + g_mean ** 2)), np.sqrt(np.log(g_sig ** 2 / g_mean ** 2 + 1))
+            probs = np.asarray(get_STSP_prob[int(STSP_prob[ia, ja])])
+            classes = get_STSP_types[int(STSP_types[ia, ja])]
+            for stype in get_SynType[int(SynTypes[ia, ja])]:             # 1 AMPA (+ 3 NMDA twin) or 2 GABA
+                gmax = _clipped(torch, torch.exp(mu + sd * torch.randn(m, **f64)), 0.0, 100.0 * g_mean, gen, device)
+                cls = torch.multinomial(torch.as_tensor(probs, device=device, dtype=torch.float64), m, replacement=True, generator=gen)
+                U = torch.empty(m, device=device, dtype=torch.float64)
+                trec = torch.empty_like(U)
+                tfac = torch.empty_like(U)
+                for c, name in enumerate(classes):
+                    tab = STSP_setup[name]
+                    sel = cls == c
+                    k = int(sel.sum())
+                    U[sel] = _clipped(torch, tab[0, 0] + tab[1, 0] * torch.randn(k, **f64), 0.0, 1.0, gen, device)
+                    trec[sel] = _clipped(torch, tab[0, 1] + tab[1, 1] * torch.randn(k, **f64), 0.0, 1500.0, gen, device)
+                    tfac[sel] = _clipped(torch, tab[0, 2] + tab[1, 2] * torch.randn(k, **f64), 0.0, 1500.0, gen, device)
+                trec.clamp_(min=1e-3)
+                tfac.clamp_(min=1e-3)
+                for lst, val in zip(out, (src.to(torch.int32), tgt.to(torch.int32), torch.full((m,), stype - 1, device=device, dtype=torch.uint8),
+                                          gmax, U, trec, tfac, torch.full((m,), 0.3, **{k2: v for k2, v in f64.items() if k2 != "generator"}), delay)):
+                    lst.append(val)
+    if not out[0]:
+        return None
+    return tuple(torch.cat(x).contiguous() for x in out)
+
+
+def multicolumn_synapses_device(SynPar, source_arr, target_arr, groups, n_columns, n_per_column, device, col_lo=0, col_hi=None, seed=0):
+    """Tiled intra-column synapses + drawn inter-column synapses for the target columns [col_lo, col_hi) of a ring."""
+    import torch
+    col_hi = n_columns if col_hi is None else col_hi
+    intra = tile_synapses_device(SynPar, source_arr, target_arr, col_hi - col_lo, n_per_column, device, id_offset=col_lo * n_per_column)
+    inter = inter_column_synapses_device(groups, n_per_column, n_columns, device, col_lo, col_hi, seed)
+    if inter is None:
+        return intra
+    return tuple(torch.cat([a, b]).contiguous() for a, b in zip(intra, inter))

@@ -148,3 +148,27 @@ def test_error_behaviour():
         b = small(Engine, 20, np.zeros(20), plan="resident", instance_size=10)
         b.set_synapses(**dict(ok, src=[0], tgt=[15]))
         b.run(1)
+
+
+def test_ring_of_columns_with_inter_column_synapses():
+    """scaled.multicolumn_synapses_device (the bench's `multicolumn` workload) at small scale: 7 columns of the 207-neuron
+    column, inter-column delays up to ~15 ms (3x the refractory period) -> the non-fused path, against the oracle."""
+    from oracle_binding import golden_groups
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import channels_from_STypPar, neuron_rows_from_NeuPar
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import multicolumn_synapses_device, tile_columns
+    g = load_golden("net_n200_s0")
+    K, n1 = 7, 207
+    groups = [grp[0] for grp in golden_groups(g)]
+    syn = [x.numpy() for x in multicolumn_synapses_device(g["SynPar"], g["source_arr"], g["target_arr"], groups, K, n1, "cpu", seed=3)]
+    assert len(syn[0]) > K * g["SynPar"].shape[1] and (syn[8] / 0.05).max() > 200
+    net = tile_columns(g["NeuPar"], g["V0"], np.zeros((7, 0)), [], [], default_idc(g), K)
+    out = {}
+    for name, cls, kw in (("gpu", Engine, dict(plan="graph")), ("cpu", OracleEngine, {})):
+        e = cls(K * n1, 0.05, method="rk2", accum="fixed", seed=6, **kw)
+        e.set_neurons(neuron_rows_from_NeuPar(net["NeuPar"], net["I_DC"]), net["V0"][0], net["V0"][1])
+        e.set_channels(**channels_from_STypPar(g["STypPar"]))
+        e.set_synapses(*syn)
+        e.run(8000)
+        out[name] = e
+    assert same(out["gpu"], out["cpu"]) > 2000
+    assert out["gpu"].counters()["syn_deliveries"] == out["cpu"].counters()["syn_deliveries"]
