@@ -5,6 +5,11 @@ realtime factor) on B200, with the HBM roofline of the state-update kernel and a
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload columns|column]
                     [--columns C] [--method euler|rk2|rk4] [--window S]
 
+Default workload: BASELINE config 5 on one GPU — a ring of 1000 columns (1 003 000 neurons): the reference's default column
+(bit-exact NetworkSetup output, seed 0) tiled 1000 times plus inter-column synapses drawn by the reference's rules
+(3.16e8 synapses, delays up to 15 ms); `--workload columns` leaves the inter-column synapses out, `--workload column` is
+the single 1003-neuron column (configs 0-1, cluster-resident plan).
+
 A bench "step" = one window of S consecutive time steps (default 100 ms of biological time) of the whole network:
 `value` times hhd_run on the device with everything resident in HBM; `e2e` times the user-facing call sequence with
 host buffers — upload this window's background current (H2D), run, read back the window's spikes, the summed-current
@@ -35,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="columns", choices=["columns", "column", "multicolumn"],
+    ap.add_argument("--workload", default="multicolumn", choices=["columns", "column", "multicolumn"],
                     help="columns: tiled independent columns; multicolumn: ring of columns with inter-column synapses; column: one column")
     ap.add_argument("--columns", type=int, default=0, help="columns in the scaled network (0 = workload default)")
     ap.add_argument("--template", default="n1000", choices=["n1000", "n200"], help="one-column fixture that is tiled")
@@ -357,7 +362,7 @@ def main():
     traffic = None
     try:        # DRAM bytes per launch of the same kernel from the committed ncu capture (same workload only)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if args.workload == "columns" and n == 1003000 and args.method == "euler" and world == 1:
+        if args.workload != "column" and n == 1003000 and args.method == "euler" and world == 1:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass

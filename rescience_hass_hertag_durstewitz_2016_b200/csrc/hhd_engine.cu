@@ -1,22 +1,22 @@
 /*
  * hhd_engine.cu — sm_100a engine behind the C ABI of include/hhd.h (plan HHD_PLAN_GRAPH: grid-wide kernels).
  *
- * One time step = three kernels on the handle's stream, captured STEPS_PER_GRAPH at a time into a CUDA graph:
- *   k_neuron   one thread per neuron, SoA fp64: finish the previous step (reset `V=V_r; w+=b`, the `w_crossing`
- *              projection — both need the conductances AFTER that step's deliveries), sample the monitors (Brian's
- *              `start` slot), integrate the 8 ODEs (euler / rk2 / rk4), evaluate threshold + refractoriness +
- *              w_crossing, and append spikes to the spike ring with one atomic per warp (ballot compaction).
- *              Replaces NeuronGroup's stateupdater/thresholder/resetter + StateMonitor + SpikeMonitor
- *              (codes/CortexNetwork.py:304-311, 487, 510).
- *   k_stp      one CTA per NEW spike, threads over that neuron's CSR row: failure draw (Philox keyed by synapse and
- *              step), Tsodyks–Markram update of (u, R), and the amplitude the delayed pathways will add
- *              (pathways p0..p6, codes/CortexNetwork.py:360-366).
- *   k_deliver  one warp per ACTIVE spike (any spike not older than the longest delay): the row is sorted by delay, the
- *              lanes scan its uint16 delay column and the synapses whose delay equals the spike's age add their
- *              CURRENT amplitude to the target conductances (pathways p7a..p9b with `delay = dtax`, :367-372,463-468).
- *              The spike history itself is the delay queue: no per-event queue memory, bounded by one spike per neuron
- *              per refractory period, and values are read at delivery time exactly as Brian's SpikeQueue does
- *              (SURVEY F5).  External SpikeGeneratorGroup events (:570-622) are delivered by the same kernel.
+ * One time step = three kernels, captured STEPS_PER_GRAPH at a time into a CUDA graph:
+ *   k_neuron      persistent CTAs, one thread per neuron and tile, SoA fp64 staged by TMA bulk copies: finish the previous
+ *                 step (w_crossing test on the stored state, pending synaptic increments, reset `V=V_r; w+=b`, w_crossing
+ *                 projection), sample the monitors (Brian's `start` slot), integrate the 8 ODEs (euler / rk2 / rk4 /
+ *                 adaptive rk2(3)), threshold + refractoriness, append spikes to the spike ring with one atomic per
+ *                 warp (ballot compaction).  Replaces NeuronGroup's stateupdater/thresholder/resetter + StateMonitor +
+ *                 SpikeMonitor (codes/CortexNetwork.py:304-311, 487, 510).
+ *   k_spike_new   [second stream] one CTA per NEW spike, threads over that neuron's CSR row: failure draw (Philox keyed by
+ *                 synapse and step), Tsodyks–Markram update of (u, R), the amplitude the delayed pathways will add
+ *                 (pathways p0..p6, codes/CortexNetwork.py:360-366), zero-delay deliveries, `last_spike_pre = t`.
+ *   k_deliver     [concurrently] one warp per ACTIVE older spike (any spike not older than its neuron's longest delay):
+ *                 the row is sorted by delay and carries a 16-entry bucket index; the synapses whose delay equals the
+ *                 spike's age add their CURRENT amplitude to the target's pending increments (pathways p7a..p9b with
+ *                 `delay = dtax`, :367-372,463-468).  The spike history itself is the delay queue: no per-event queue
+ *                 memory, bounded by one spike per neuron per refractory period, and values are read at delivery time
+ *                 exactly as Brian's SpikeQueue does.  SpikeGeneratorGroup events (:570-622) as well.
  *
  * Data layout in HBM: structure of arrays, fp64; per neuron 8 state + 12 parameter doubles + last_spike + int32
  * lastspike step + 1 flag byte (≈ 240 B read+written per neuron-update, the roofline figure of SURVEY §8d);
@@ -104,6 +104,7 @@ struct Params {
   const long long* row_ptr;    /* [NG+1] */
   SynHot* hot;
   SynStp* stp;
+  const unsigned short* row_maxd; /* [NG] largest delay (steps) in the row */
   const unsigned int* row_bkt; /* [NG][DELAY_BUCKETS] offset inside the row of the first synapse with delay >= b*bkt_width */
   int bkt_width;
   long long syn_id_base;
@@ -111,6 +112,9 @@ struct Params {
   int* spk_neuron;             /* global ids */
   int* spk_step;
   unsigned int cap_mask;
+  int* spk_hist;               /* [NG][hist_depth] steps of the latest spikes of every neuron whose rows k_spike_new<true> processed */
+  int hist_depth;
+  int* spk_last;               /* [NG] step of the latest spike of every (global) neuron, written when the spike is appended */
   unsigned long long* head;    /* monotone count of spikes appended */
   unsigned long long* step_end;/* [W] head value at the end of step (k % W) */
   /* external input events, grouped by step */
@@ -471,6 +475,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
           const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
           P.spk_neuron[pos] = P.off + i;
           P.spk_step[pos] = (int)k;
+          P.spk_last[P.off + i] = (int)k;
         }
       }
     }
@@ -539,33 +544,6 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   neuron_phase<METHOD, STEP>(P, *P.base_step + step_offset, reinterpret_cast<NeuronStage*>(smem_raw), sh, bar_parity);
 }
 
-/* Pathways p0..p6 for the synapses of every neuron that spiked in this step. */
-__global__ void __launch_bounds__(STP_BLOCK) k_stp(const __grid_constant__ Params P, const int step_offset) {
-  const long long k = *P.base_step + step_offset;
-  const double t = (double)k * P.dt;
-  const unsigned long long lo = P.step_end[(k + P.W - 1) % P.W];
-  const unsigned long long hi = *P.head;
-  if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[k % P.W] = hi;
-  unsigned long long events = 0;
-  for (unsigned long long sp = lo + blockIdx.x; sp < hi; sp += gridDim.x) {
-    const int j = P.spk_neuron[(unsigned)sp & P.cap_mask];
-    const double last = P.last_spike[j];
-    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-    for (long long r = r0 + threadIdx.x; r < r1; r += STP_BLOCK) {
-      SynStp sy = P.stp[r];
-      const SynHot sh = P.hot[r];
-      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t,
-                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig),
-                                        (unsigned long long)k);
-      P.stp[r].u = sy.u;
-      P.stp[r].R = sy.R;
-      P.hot[r].amp = amp;
-    }
-    if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
-  }
-  if (threadIdx.x == 0 && events) atomicAdd(&P.counters[CNT_SYN_EVENTS], events);
-}
-
 __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc) {
   /* summed per (channel, target) for this step; the target's next state-update pass adds the sum to g_on and g_off */
   if (P.accum == HHD_ACCUM_FIXED) {
@@ -574,6 +552,31 @@ __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, d
   } else {
     atomicAdd(reinterpret_cast<double*>(&P.pend[(size_t)c * P.n_pad + tgt]), inc);
   }
+}
+
+/* All synapses of neuron j whose delay equals `age` (whole warp): bucket index -> segment of the delay-sorted row ->
+ * 16-byte records; returns the number of deliveries this lane made. */
+__device__ __forceinline__ unsigned deliver_row_due(const Params& P, const int j, const int age, const unsigned lane) {
+  unsigned n = 0;
+  const long long r0 = P.row_ptr[j];
+  const int b = age / P.bkt_width;
+  const long long s0 = r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b];
+  const long long s1 = b + 1 < DELAY_BUCKETS ? r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b + 1] : P.row_ptr[j + 1];
+  for (long long rb = s0; rb < s1; rb += 32) {
+    const long long r = rb + lane;
+    int d = 0x7fffffff;
+    SynHot sh;
+    if (r < s1) {
+      sh = P.hot[r];                                           /* one 16-byte load: target, delay, channel, amplitude */
+      d = sh.delay;
+    }
+    if (d == age) {
+      ++n;
+      if (sh.amp != 0.0) add_increment(P, sh.chan, sh.tgt, sh.amp);
+    }
+    if (__all_sync(0xffffffffu, d > age)) break;              /* rows are sorted by delay */
+  }
+  return n;
 }
 
 __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc);
@@ -587,9 +590,13 @@ __device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, d
  * FUSED = true: this kernel handles only spikes of EARLIER steps while k_spike_new (p0..p6 + zero-delay deliveries of
  * this step's spikes) runs concurrently on a second stream; legal only while max_delay < refractory steps, because then
  * no neuron can have a new spike and an undelivered older one at once, so no delivery can read an amplitude that
- * another CTA is rewriting.  Otherwise the host launches k_stp, then this kernel with FUSED = false.
+ * another CTA is rewriting.
  */
 /* Pathways p0..p6 + the zero-delay deliveries + p5 for the spikes of THIS step, one CTA per new spike (fused mode). */
+/* LONG = true (some delay >= refractory steps): the neuron may still have older spikes in flight whose deliveries must
+ * use the amplitudes just rewritten; their steps are in the per-neuron history spk_hist, and warp 0 delivers
+ * what is due from them now, while k_deliver<DELIVER_MAIN> skips every neuron that spiked in this step. */
+template <bool LONG>
 __device__ __forceinline__ void spike_new_phase(const Params& P, const long long k) {
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
@@ -616,55 +623,58 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
       }
     }
     if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
-    __syncthreads();                                           /* every thread has read last_spike[j] */
+    __syncthreads();                                           /* every thread has read last_spike[j]; the row is rewritten */
     if (threadIdx.x == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5 */
+    if (LONG) {
+      if (threadIdx.x < 32) {
+        int* hist = P.spk_hist + (size_t)j * P.hist_depth;
+        const int maxd = P.row_maxd[j];
+        for (int q = 0; q < P.hist_depth; ++q) {
+          const int age = (int)(k - (long long)hist[q]);
+          if (age > 0 && age <= maxd) delivered0 += deliver_row_due(P, j, age, lane);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          for (int q = P.hist_depth - 1; q > 0; --q) hist[q] = hist[q - 1];
+          hist[0] = (int)k;
+        }
+      }
+      __syncthreads();
+    }
   }
   if (threadIdx.x == 0 && events) atomicAdd(&P.counters[CNT_SYN_EVENTS], events);
   delivered0 = (unsigned long long)warp_sum((double)delivered0);
   if (lane == 0 && delivered0) atomicAdd(&P.counters[CNT_DELIVERIES], delivered0);
 }
 
+template <bool LONG>
 __global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
   pdl_trigger();
   pdl_wait();
-  spike_new_phase(P, *P.base_step + step_offset);
+  spike_new_phase<LONG>(P, *P.base_step + step_offset);
 }
 
-template <bool FUSED>
+/* MODE: DELIVER_FUSED (max_delay < refractory steps) or DELIVER_MAIN (longer delays).  Either way this launch delivers
+ * for the spikes of EARLIER steps and runs concurrently with k_spike_new on the second stream; with longer delays a
+ * neuron that spiked again in this step is skipped here — its amplitudes are being rewritten, k_spike_new<true> delivers
+ * for it. */
+enum { DELIVER_FUSED = 1, DELIVER_MAIN = 2 };
+
+template <int MODE>
 __device__ __forceinline__ void deliver_phase(const Params& P, const long long k) {
-  const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
-  const unsigned long long lo = P.step_end[(k + 1) % P.W];   /* head at the end of step k - max_delay - 1 */
-  const unsigned long long hi = *P.head;
-  /* fused mode: the spikes of this step belong to k_spike_new, which runs concurrently on the second stream */
-  const unsigned long long old_hi = FUSED ? P.step_end[(k + P.W - 1) % P.W] : hi;
+  const unsigned long long lo = P.step_end[(k + 1) % P.W];             /* head at the end of step k - max_delay - 1 */
+  const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];   /* first spike of this step */
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
   const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   unsigned long long delivered = 0;
-  for (unsigned long long sp = lo + wid; sp < old_hi; sp += warps) {
+  for (unsigned long long sp = lo + wid; sp < lo_new; sp += warps) {     /* one warp per spike of an earlier step */
     const unsigned pos = (unsigned)sp & P.cap_mask;
     const int j = P.spk_neuron[pos];
     const int age = (int)(k - (long long)P.spk_step[pos]);
-    if (!FUSED && age == 0 && lane == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5; every k_stp read of it is complete */
-    if (age > P.max_delay) continue;
-    const long long r0 = P.row_ptr[j];
-    const int b = age / P.bkt_width;
-    const long long s0 = r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b];
-    const long long s1 = b + 1 < DELAY_BUCKETS ? r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b + 1] : P.row_ptr[j + 1];
-    for (long long rb = s0; rb < s1; rb += 32) {
-      const long long r = rb + lane;
-      int d = 0x7fffffff;
-      SynHot sh;
-      if (r < s1) {
-        sh = P.hot[r];                                         /* one 16-byte load: target, delay, channel, amplitude */
-        d = sh.delay;
-      }
-      if (d == age) {
-        ++delivered;
-        if (sh.amp != 0.0) add_increment(P, sh.chan, sh.tgt, sh.amp);
-      }
-      if (__all_sync(0xffffffffu, d > age)) break;            /* rows are sorted by delay */
-    }
+    if (age > (int)P.row_maxd[j]) continue;                             /* nothing of this neuron can be due any more */
+    if (MODE == DELIVER_MAIN && P.spk_last[j] == (int)k) continue;      /* spiked again now: k_spike_new<true> */
+    delivered += deliver_row_due(P, j, age, lane);
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
   if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
@@ -684,11 +694,11 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
   }
 }
 
-template <bool FUSED>
+template <int MODE>
 __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
   pdl_trigger();
   pdl_wait();
-  deliver_phase<FUSED>(P, *P.base_step + step_offset);
+  deliver_phase<MODE>(P, *P.base_step + step_offset);
 }
 
 /* ================================================================================================================== *
@@ -730,8 +740,8 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     neuron_phase<METHOD, true>(P, k, st, sh, bar_parity);
     arrived += gridDim.x;
     grid_barrier(P.grid_bar, arrived);
-    spike_new_phase(P, k);
-    deliver_phase<true>(P, k);
+    spike_new_phase<false>(P, k);
+    deliver_phase<DELIVER_FUSED>(P, k);
     arrived += gridDim.x;
     grid_barrier(P.grid_bar, arrived);
   }
@@ -1030,6 +1040,7 @@ __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P
       const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
       P.spk_neuron[pos] = src[1 + q];
       P.spk_step[pos] = (int)k;
+      P.spk_last[src[1 + q]] = (int)k;
     }
   }
   __syncthreads();
@@ -1363,7 +1374,7 @@ __global__ void k_syn_rows(long long nsyn, const unsigned long long* keys, int N
 }
 
 /* row_bkt[j][b] = offset inside row j of the first synapse whose delay is >= b * width (rows are sorted by delay) */
-__global__ void k_syn_buckets(int NG, const long long* row_ptr, const SynHot* hot, int width, unsigned int* row_bkt) {
+__global__ void k_syn_buckets(int NG, const long long* row_ptr, const SynHot* hot, int width, unsigned int* row_bkt, unsigned short* row_maxd) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (long long)NG * DELAY_BUCKETS) return;
   const int j = (int)(q / DELAY_BUCKETS), b = (int)(q % DELAY_BUCKETS);
@@ -1375,6 +1386,7 @@ __global__ void k_syn_buckets(int NG, const long long* row_ptr, const SynHot* ho
     if ((int)hot[mid].delay < want) lo = mid + 1; else hi = mid;
   }
   row_bkt[q] = (unsigned int)(lo - r0);
+  if (b == 0) row_maxd[j] = r1 > r0 ? hot[r1 - 1].delay : 0;      /* rows are sorted by delay */
 }
 
 static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
@@ -1429,11 +1441,14 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
   CU(cudaStreamSynchronize(h->stream));
   {
     unsigned int* bkt = nullptr;
+    unsigned short* rmax = nullptr;
     rc = dev_alloc(h, &bkt, (size_t)h->NG * DELAY_BUCKETS, true);
+    if (!rc) rc = dev_alloc(h, &rmax, (size_t)h->NG, true);
     if (rc) return rc;
+    P.row_maxd = rmax;
     P.bkt_width = (maxd + 1 + DELAY_BUCKETS - 1) / DELAY_BUCKETS;
     const long long nq = (long long)h->NG * DELAY_BUCKETS;
-    k_syn_buckets<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, P.bkt_width, bkt);
+    k_syn_buckets<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, P.bkt_width, bkt, rmax);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     P.row_bkt = bkt;
@@ -1688,6 +1703,20 @@ static int finalize_setup(hhd_handle h) {
   const long long per_neuron = (h->seg_steps + P.max_delay + 1 + refr - 1) / refr + 2;
   h->ring_cap = next_pow2((unsigned long long)h->NG * (unsigned long long)per_neuron);
   if (h->ring_cap > (1ull << 31)) return fail(h, HHD_E_NOMEM, "spike ring too large");
+  {
+    std::vector<int> never((size_t)h->NG, -(1 << 30));
+    rc = dev_alloc(h, &P.spk_last, (size_t)h->NG, false);
+    if (!rc) rc = upload(h, P.spk_last, never.data(), never.size());
+    if (rc) return rc;
+  }
+  P.hist_depth = (int)(P.max_delay / refr) + 1;
+  if (P.max_delay >= P.refr_steps) {
+    if (P.hist_depth > 16) return fail(h, HHD_E_ARG, "delays of more than 16 refractory periods are not supported");
+    std::vector<int> never((size_t)h->NG * P.hist_depth, -(1 << 30));
+    rc = dev_alloc(h, &P.spk_hist, never.size(), false);
+    if (!rc) rc = upload(h, P.spk_hist, never.data(), never.size());
+    if (rc) return rc;
+  }
   rc = dev_alloc(h, &P.spk_neuron, (size_t)h->ring_cap, false);
   if (!rc) rc = dev_alloc(h, &P.spk_step, (size_t)h->ring_cap, false);
   if (rc) return rc;
@@ -1726,9 +1755,12 @@ static int finalize_setup(hhd_handle h) {
   h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
+    unsigned short* rmax = nullptr;
     rc = dev_alloc(h, &bkt, (size_t)h->NG * DELAY_BUCKETS, true);
+    if (!rc) rc = dev_alloc(h, &rmax, (size_t)h->NG, true);
     if (rc) return rc;
     P.row_bkt = bkt;
+    P.row_maxd = rmax;
     P.bkt_width = 1;
   }
   {
@@ -1871,14 +1903,19 @@ static void launch_step(hhd_handle h, int offset) {
   if (h->fused) {
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    k_spike_new<<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
+    k_spike_new<false><<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
     cudaEventRecord(h->ev_join, h->stream2);
-    launch_pdl(h, k_deliver<true>, h->deliver_grid, DELIVER_BLOCK, 0, h->stream, offset);
+    launch_pdl(h, k_deliver<DELIVER_FUSED>, h->deliver_grid, DELIVER_BLOCK, 0, h->stream, offset);
     cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   } else {
-    if (h->nsyn) k_stp<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, offset);
-    else k_stp<<<1, 32, 0, h->stream>>>(h->P, offset);          /* still records step_end */
-    k_deliver<false><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+    /* delays beyond the refractory period: same two concurrent kernels; k_spike_new<true> also delivers what is due from
+     * older spikes of the neurons that spiked now, k_deliver<DELIVER_MAIN> skips those neurons */
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    k_spike_new<true><<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
+    cudaEventRecord(h->ev_join, h->stream2);
+    k_deliver<DELIVER_MAIN><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   }
 }
 
@@ -2064,11 +2101,11 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
       k_append<<<1, 256, 0, h->stream>>>(h->P, (int)s);
     }
 #endif
-    if (!h->fused) k_stp<<<h->nsyn ? h->stp_grid : 1, h->nsyn ? STP_BLOCK : 32, 0, h->stream>>>(h->P, (int)s);
-    else k_spike_new<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    if (!h->fused) k_spike_new<true><<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    else k_spike_new<false><<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
     CU(cudaEventRecord(ev[3 * s + 2], h->stream));
-    if (h->fused) k_deliver<true><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
-    else k_deliver<false><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    if (h->fused) k_deliver<DELIVER_FUSED><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    else k_deliver<DELIVER_MAIN><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
     CU(cudaEventRecord(ev[3 * s + 3], h->stream));
   }
   k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, (int)n_steps);
