@@ -147,6 +147,12 @@ int hhd_set_channels(hhd_handle h, const double tau_on[3], const double tau_off[
  * (`group.I_DC[...] = constant_current` codes/CortexNetwork.py:314-318; step-wise stand-in for TimedArray I_AC :137-151). */
 int hhd_set_idc(hhd_handle h, const double* idc);
 
+/* Time-varying injected current I_AC(t): replaces `I_AC = ta(t, i)` with ta = TimedArray(table, dt)
+ * (codes/CortexNetwork.py:133-151, 726-727; revision CortexSetup.py:193-213).  table is [n_steps][n_cols] (pA), row s holds
+ * for step s (row 0 before it, the last row after it, as TimedArray does); col_of_neuron[i] selects the column of LOCAL
+ * neuron i (-1: no timed current).  Runge-Kutta stages evaluated at t + dt read row s + 1.  Call before the first hhd_run. */
+int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const double* table, const int32_t* col_of_neuron);
+
 /* ---- synapses: replaces Synapses(...).connect(i,j) + per-synapse assignments + delays/orders,
  *      codes/CortexNetwork.py:343-482 (revision: CortexSetup.py:62-91,239-308) ---------------------------------- */
 /* src, tgt are GLOBAL neuron ids; every tgt must be local to this handle.  chan in {0,1,2}.  delay_ms -> steps as

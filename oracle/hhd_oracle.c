@@ -49,6 +49,7 @@
 #define hhd_read_monitor_dev hhdo_read_monitor_dev
 #define hhd_clear_monitor hhdo_clear_monitor
 #define hhd_run hhdo_run
+#define hhd_set_timed_current hhdo_set_timed_current
 #define hhd_set_idc hhdo_set_idc
 #define hhd_profile_kernels hhdo_profile_kernels
 #define hhd_spike_count hhdo_spike_count
@@ -140,6 +141,7 @@ struct hhd_engine {
   int32_t* cur_spikes; int n_cur_spikes;      /* local ids */
   int32_t* cur_wcross; int n_cur_wcross;
   uint8_t* flag_scratch;
+  double* iac_table; int32_t* iac_col; int64_t iac_steps; int iac_cols;
   int step_open;
   hhd_counters cnt;
 };
@@ -197,7 +199,7 @@ void hhd_destroy(hhd_handle h) {
   if (!h) return;
   for (int i = 0; i < HHD_N_PARAMS; ++i) free(h->par[i]);
   for (int i = 0; i < 8; ++i) free(h->x[i]);
-  free(h->last_spike); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch);
+  free(h->last_spike); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch); free(h->iac_table); free(h->iac_col);
   free(h->src); free(h->tgt); free(h->chan); free(h->gmax); free(h->U); free(h->tau_rec); free(h->tau_fac);
   free(h->pfail); free(h->delay_steps); free(h->u); free(h->R); free(h->a_syn); free(h->failure); free(h->touched);
   free(h->row_ptr); free(h->row_syn);
@@ -231,6 +233,19 @@ int hhd_set_neurons(hhd_handle h, const double* const* params, const double* V0,
 int hhd_set_idc(hhd_handle h, const double* idc) {
   if (!h || !idc) return fail(h, HHD_E_ARG, "null argument");
   memcpy(h->par[HHD_P_IDC], idc, (size_t)h->N * sizeof(double));
+  return HHD_OK;
+}
+
+int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const double* table, const int32_t* col_of_neuron) {
+  if (!h || n_steps <= 0 || n_cols <= 0 || !table || !col_of_neuron) return fail(h, HHD_E_ARG, "bad argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_timed_current after run");
+  for (int i = 0; i < h->N; ++i) if (col_of_neuron[i] >= n_cols) return fail(h, HHD_E_ARG, "column index out of range");
+  free(h->iac_table); free(h->iac_col);
+  h->iac_table = (double*)malloc((size_t)n_steps * n_cols * 8);
+  h->iac_col = (int32_t*)malloc((size_t)h->N * 4);
+  memcpy(h->iac_table, table, (size_t)n_steps * n_cols * 8);
+  memcpy(h->iac_col, col_of_neuron, (size_t)h->N * 4);
+  h->iac_steps = n_steps; h->iac_cols = n_cols;
   return HHD_OK;
 }
 
@@ -372,7 +387,7 @@ static npar load_par(const hhd_handle h, int i) {
 }
 
 /* Subexpressions of codes/CortexNetwork.py:235-248,265-272 at state x. */
-static void subexpressions(const hhd_handle h, const npar* p, const double x[8], subexpr* s) {
+static void subexpressions(const hhd_handle h, const npar* p, const double x[8], double iac, subexpr* s) {
   const double V = x[HHD_V];
   s->g[0] = x[HHD_G_AMPA_OFF] - x[HHD_G_AMPA_ON];                               /* g_AMPA = g_AMPA_off - g_AMPA_on   :265 */
   s->g[1] = x[HHD_G_GABA_OFF] - x[HHD_G_GABA_ON];                               /* :266 */
@@ -382,7 +397,7 @@ static void subexpressions(const hhd_handle h, const npar* p, const double x[8],
   s->I_GABA = s->g[1] * (h->E[1] - V);                                          /* :271 */
   s->I_NMDA = (s->g[2] * (h->E[2] - V)) * Mg;                                   /* :272 */
   s->I_syn = (s->I_AMPA + s->I_NMDA) + s->I_GABA;                               /* :238 */
-  s->I_inj = p->IDC + 0.0;                                                      /* :236-237, I_AC = 0 */
+  s->I_inj = p->IDC + iac;                                                      /* :236-237 */
   s->I_tot = s->I_syn + s->I_inj;                                               /* :239 */
   s->ex = hhd_exp((V - p->VT) / p->dT);
   s->I_exp = (p->gL * p->dT) * s->ex;                                           /* :245 */
@@ -392,9 +407,9 @@ static void subexpressions(const hhd_handle h, const npar* p, const double x[8],
 }
 
 /* Right-hand sides, codes/CortexNetwork.py:251-263.  t = stage time, ls = this neuron's last_spike. */
-static void deriv(const hhd_handle h, const npar* p, const double x[8], double t, double ls, double d[8]) {
+static void deriv(const hhd_handle h, const npar* p, const double x[8], double t, double ls, double iac, double d[8]) {
   subexpr s;
-  subexpressions(h, p, x, &s);
+  subexpressions(h, p, x, iac, &s);
   const double V = x[HHD_V], w = x[HHD_W];
   const double a = ((s.I_tot >= p->Iref) ? 1.0 : 0.0) * ((t - ls < h->cfg.block_window_ms) ? 1.0 : 0.0);
   const double dV = (a * (-p->gL / p->C)) * (V - p->Vdep) + ((1.0 - a) * (s.w_V - w)) / p->C;      /* :251 */
@@ -409,27 +424,27 @@ static void deriv(const hhd_handle h, const npar* p, const double x[8], double t
 }
 
 /* Brian 2 ExplicitStateUpdater definitions: euler, rk2 (midpoint), rk4. */
-static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], double t, double ls) {
+static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], double t, double ls, double iac0, double iac1) {
   const double dt = h->cfg.dt_ms;
   double k1[8], k2[8], k3[8], k4[8], y[8];
-  deriv(h, p, x, t, ls, k1);
+  deriv(h, p, x, t, ls, iac0, k1);
   for (int v = 0; v < 8; ++v) k1[v] = dt * k1[v];
   if (h->cfg.method == HHD_EULER) {
     for (int v = 0; v < 8; ++v) x[v] = x[v] + k1[v];
     return;
   }
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k1[v] * 0.5;
-  deriv(h, p, y, t + dt * 0.5, ls, k2);
+  deriv(h, p, y, t + dt * 0.5, ls, iac0, k2);
   for (int v = 0; v < 8; ++v) k2[v] = dt * k2[v];
   if (h->cfg.method == HHD_RK2) {
     for (int v = 0; v < 8; ++v) x[v] = x[v] + k2[v];
     return;
   }
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k2[v] * 0.5;
-  deriv(h, p, y, t + dt * 0.5, ls, k3);
+  deriv(h, p, y, t + dt * 0.5, ls, iac0, k3);
   for (int v = 0; v < 8; ++v) k3[v] = dt * k3[v];
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k3[v];
-  deriv(h, p, y, t + dt, ls, k4);
+  deriv(h, p, y, t + dt, ls, iac1, k4);      /* TimedArray read at t + dt: the next row */
   for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
   for (int v = 0; v < 8; ++v) x[v] = x[v] + (((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v]) / 6.0;
 }
@@ -445,18 +460,18 @@ static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], doub
  * reproduces it bit for bit (the growth exponent is -1/4 instead of GSL's -1/3 for that reason).
  */
 #define RK23_MAX_SUBSTEPS 4096
-static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], double t0, double ls) {
+static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], double t0, double ls, double iac0, double iac1) {
   const double dt = h->cfg.dt_ms;
   static const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
   double t = 0.0, hs = dt;
   for (int it = 0; it < RK23_MAX_SUBSTEPS && t < dt; ++it) {
     if (t + hs > dt) hs = dt - t;
     double k1[8], k2[8], k3[8], y[8], ynew[8];
-    deriv(h, p, x, t0 + t, ls, k1);
+    deriv(h, p, x, t0 + t, ls, iac0, k1);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
-    deriv(h, p, y, t0 + (t + 0.5 * hs), ls, k2);
+    deriv(h, p, y, t0 + (t + 0.5 * hs), ls, iac0, k2);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    deriv(h, p, y, t0 + (t + hs), ls, k3);
+    deriv(h, p, y, t0 + (t + hs), ls, (t + hs) >= dt ? iac1 : iac0, k3);
     double rmax = 0.0;
     for (int v = 0; v < 8; ++v) {
       ynew[v] = x[v] + hs * (((k1[v] + 4.0 * k2[v]) + k3[v]) / 6.0);
@@ -484,6 +499,14 @@ static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], doubl
   }
 }
 
+/* I_AC of local neuron i at step s: TimedArray semantics (first row before the table, last row after it). */
+static double iac_at(const hhd_handle h, int i, int64_t s) {
+  if (!h->iac_table || h->iac_col[i] < 0) return 0.0;
+  if (s < 0) s = 0;
+  if (s >= h->iac_steps) s = h->iac_steps - 1;
+  return h->iac_table[(size_t)s * h->iac_cols + h->iac_col[i]];
+}
+
 static double monitor_value(const hhd_handle h, int var, int i) {
   double x[8];
   for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
@@ -491,7 +514,7 @@ static double monitor_value(const hhd_handle h, int var, int i) {
   if (var == HHD_LAST_SPIKE) return h->last_spike[h->cfg.global_offset + i];
   npar p = load_par(h, i);
   subexpr s;
-  subexpressions(h, &p, x, &s);
+  subexpressions(h, &p, x, iac_at(h, i, h->step), &s);
   switch (var) {
     case HHD_G_AMPA: return s.g[0];
     case HHD_G_GABA: return s.g[1];
@@ -555,8 +578,9 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
     npar p = load_par(h, i);
     double x[8];
     for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
-    if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i]);
-    else integrate_fixed(h, &p, x, t, h->last_spike[off + i]);
+    const double iac0 = iac_at(h, i, k), iac1 = iac_at(h, i, k + 1);
+    if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i], iac0, iac1);
+    else integrate_fixed(h, &p, x, t, h->last_spike[off + i], iac0, iac1);
     for (int v = 0; v < 8; ++v) h->x[v][i] = x[v];
     if (!isfinite(x[HHD_V]) || !isfinite(x[HHD_W])) bad++;
   }
@@ -576,7 +600,7 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
     double x[8];
     for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
     subexpr s;
-    subexpressions(h, &p, x, &s);
+    subexpressions(h, &p, x, iac_at(h, i, k), &s);      /* slot `thresholds`: the clock still reads t_k */
     const double w = x[HHD_W];
     if (w > s.w_V - s.D0 / p.tauw && w < s.w_V + s.D0 / p.tauw && x[HHD_V] <= p.VT) f |= 2;
     h->flag_scratch[i] = f;
@@ -704,7 +728,7 @@ int hhdo_step_end(hhd_handle h, const int32_t* all_spikes, int32_t n_all) {
     double x[8];
     for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
     subexpr s;
-    subexpressions(h, &p, x, &s);
+    subexpressions(h, &p, x, iac_at(h, i, k), &s);
     h->x[HHD_W][i] = s.w_V - s.D0 / p.tauw;
   }
   h->step++;

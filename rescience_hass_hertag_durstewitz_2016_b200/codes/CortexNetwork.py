@@ -94,8 +94,6 @@ class CortexNetwork:
                  _engine_cls=None):
         if isinstance(noise, (int, float)) and not isinstance(noise, bool):
             raise NotImplementedError("the conductance-noise variant (codes/CortexNetwork.py:157-230) is not built yet (SURVEY §8f-4)")
-        if len(fluctuating_current):
-            raise NotImplementedError("fluctuating_current / TimedArray I_AC (codes/CortexNetwork.py:133-155) is not built yet (SURVEY §8f-4)")
         seed(simseed)
         self.time_step = float(time_step)
         self.group_distr = group_distr
@@ -145,13 +143,32 @@ class CortexNetwork:
             chan = (self.SynPar[0].astype(np.int64) - 1).astype(np.uint8)
             self.engine.set_synapses(self.source_arr, self.target_arr, chan, self.SynPar[4], self.SynPar[1],
                                      self.SynPar[2], self.SynPar[3], self.SynPar[6], self.SynPar[5])
+        # fluctuating_current = [start_ms, stop_ms, AC[stripe][group] expression strings in t (ms)] -> TimedArray `ta`
+        # (codes/CortexNetwork.py:133-151): zeros before `start`, one sample per time step, last value held afterwards
+        self.ta = []
+        if len(fluctuating_current):
+            start_f, stop_f, AC = fluctuating_current
+            nsteps = int(round(stop_f / self.time_step, 0))
+            nstart = int(round(start_f / self.time_step, 0))
+            ns = {k: getattr(np, k) for k in dir(np) if not k.startswith("_")}
+            cols, col_of = [], np.full(n, -1, dtype=np.int32)
+            for stripe in range(len(group_distr[0])):
+                for grp in range(len(group_distr)):
+                    expr = AC[stripe][grp]
+                    if expr != "":
+                        tt = np.linspace(start_f, stop_f, nsteps - nstart, endpoint=False)
+                        vals = np.asarray([eval(expr, dict(ns), {"t": t}) for t in tt], dtype=np.float64)
+                        col_of[np.asarray(group_distr[grp][stripe]).astype(int)] = len(cols)
+                        cols.append(np.concatenate([np.zeros(nstart), vals]))
+            if cols:
+                self.ta = np.stack(cols, axis=1)
+                self.engine.set_timed_current(self.ta, col_of)
         self.group = _Group(self)
         self.I_SN = self.NeuPar[1] * units.nS * (self.NeuPar[9] - self.NeuPar[2] - self.NeuPar[3]) * units.mV   # :339
         self.spikemonitor = SpikeMonitorView(self.engine, n)
         self.neuronmonitors = {}
         self.synapsesmonitors = {}
         self._n_ext_sources = 0
-        self.ta = []
 
     # ---- monitors ---------------------------------------------------------------------------------------------------
     def neuron_monitors(self, MonitorsSetup):

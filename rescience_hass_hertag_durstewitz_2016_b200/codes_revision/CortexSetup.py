@@ -66,8 +66,9 @@ class Cortex:
                  last_spike0_ms=-1000.0, mg_fac=None, accum="fp64", device=0, _engine_cls=None):
         """last_spike0_ms = -1000 and (optionally) mg_fac = 1 are the revision's values (CortexSetup.py:254,
         BasicsSetup.py:591); mg_fac=None keeps the network's own STypPar entry (0.33 in codes/)."""
-        if fluctuant_stimuli is not None:
-            raise NotImplementedError("fluctuant_stimuli / TimedArray (CortexSetup.py:193-213) is not built yet (SURVEY §8f-4)")
+        if fluctuant_stimuli is not None and isinstance(fluctuant_stimuli[-1], (int, float)):
+            fluctuant_stimuli = [fluctuant_stimuli]
+        self.fluctuant_stimuli = fluctuant_stimuli
         np.random.seed(seed)
         self.network = network
         self.method = method
@@ -103,6 +104,19 @@ class Cortex:
             self.engine.set_synapses(network.syn_pairs[1], network.syn_pairs[0], sp["channel"].values[0].astype(np.uint8),
                                      sp["spiking"].values[0], sp["STSP_params"].values[0], sp["STSP_params"].values[1],
                                      sp["STSP_params"].values[2], sp["spiking"].values[1], sp["delay"].values[0])
+        # fluctuant_stimuli = [[target, function(t_ms) -> pA, start_ms, stop_ms], ...] -> TimedArray (CortexSetup.py:193-213).
+        # As in the reference every entry re-creates the array, so only the LAST entry takes effect.
+        self.fluctuant_array = None
+        if fluctuant_stimuli is not None:
+            for target, function, start, stop in fluctuant_stimuli:
+                idcs = self.neuron_idcs(target)
+                n_total = round(stop / self.dt_ms)
+                n_start = round(start / self.dt_ms)
+                arr = np.asarray([0] * n_start + [function(t) for t in np.linspace(start, stop, n_total - n_start, endpoint=False)], dtype=np.float64)
+                col_of = np.full(n, -1, dtype=np.int32)
+                col_of[idcs] = 0
+                self.fluctuant_array = (arr[:, None], col_of)
+            self.engine.set_timed_current(*self.fluctuant_array)
         self.neurons = _Neurons(self)
         self.spikemonitor = SpikeMonitorView(self.engine, n)
         self._spikes_on = not (transient > 0)

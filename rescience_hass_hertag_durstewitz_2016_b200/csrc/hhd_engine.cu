@@ -129,6 +129,11 @@ struct Params {
   unsigned long long* del_slots;  /* [CNT_SLOTS] */
   unsigned long long* grid_bar;   /* arrival counter of the cooperative plan's grid barrier */
   const long long* base_step;
+  /* TimedArray current I_AC: table[iac_steps][iac_cols], column of local neuron i = iac_col[i] (-1: none); NULL = unused */
+  const double* iac_table;
+  const int* iac_col;
+  long long iac_steps;
+  int iac_cols;
   /* multi-GPU spike exchange (n_ranks > 1): k_neuron appends local spikes to xchg_send = {count, ids...}; after the
    * all-gather k_append copies every rank's list into the ring */
   int n_ranks, xchg_cap;
@@ -147,6 +152,13 @@ __device__ __forceinline__ NeuronPar load_par(const Params& P, int i) {
   p.b = __ldg(P.par[HHD_P_B] + i); p.Vr = __ldg(P.par[HHD_P_VR] + i); p.VT = __ldg(P.par[HHD_P_VT] + i);
   p.Iref = __ldg(P.par[HHD_P_IREF] + i); p.Vdep = __ldg(P.par[HHD_P_VDEP] + i); p.IDC = __ldg(P.par[HHD_P_IDC] + i);
   return p;
+}
+
+/* I_AC of a neuron whose column is `col` at step s: TimedArray semantics (first row before the table, last row after). */
+__device__ __forceinline__ double iac_at(const Params& P, int col, long long s) {
+  if (col < 0) return 0.0;
+  s = s < 0 ? 0 : (s >= P.iac_steps ? P.iac_steps - 1 : s);
+  return __ldg(P.iac_table + (size_t)s * P.iac_cols + col);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -310,11 +322,13 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
 
   int tile = blockIdx.x;
   long long pd_next[3] = {0, 0, 0};
+  int col_next = -1;                 /* TimedArray column of the neuron (only read when a timed current is set) */
 #if HHD_NEURON_PREFETCH
   issue(tile, 0);
   if (tile * NEURON_BLOCK + tid < P.N) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) pd_next[c] = P.pend[(size_t)c * P.n_pad + tile * NEURON_BLOCK + tid];
+    if (P.iac_table) col_next = P.iac_col[tile * NEURON_BLOCK + tid];
   }
 #endif
 #if HHD_NEURON_PREFETCH >= 2
@@ -328,6 +342,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     double ls = 0.0;
     int meta = 0;
     long long pd[3] = {0, 0, 0};
+    int col = -1;
 #if !HHD_NEURON_PREFETCH
     if (live) {
 #pragma unroll
@@ -368,7 +383,11 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       const int in = i + (int)gridDim.x * NEURON_BLOCK;
 #pragma unroll
       for (int c = 0; c < 3; ++c) pd_next[c] = in < P.N ? P.pend[(size_t)c * P.n_pad + in] : 0;
+      col = col_next;
+      col_next = (P.iac_table && in < P.N) ? P.iac_col[in] : -1;
     }
+#else
+    if (P.iac_table && live) col = P.iac_col[i];
 #endif
 #if HHD_NEURON_PREFETCH == 2
     __syncthreads();   /* every thread holds its neuron of this tile in registers: stage s is free again */
@@ -379,13 +398,20 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
 #endif
     SubExpr S;
     bool wcross = false;
+    double iac0 = 0.0, iac1 = 0.0;
     if (live) {
       /* ---- the part of step k-1 that had to wait for that step's synaptic deliveries ------------------------------
        * x is the state right after the integration of step k-1.  Its subexpressions S decide the `w_crossing` event of
        * step k-1 (slot `thresholds`, codes/CortexNetwork.py:306) and — unless this neuron received input or was reset,
        * and then only their linear part changes — ARE the subexpressions of the first stage of step k: one evaluation
        * (two exponentials, three divisions) per neuron-step instead of two. */
-      hhd_subexpr(P.cc, p, x, S);
+      double iac_prev = 0.0, iac_now = 0.0, iac_nxt = 0.0;      /* I_AC at steps k-1, k, k+1 */
+      if (P.iac_table) {
+        iac_prev = iac_at(P, col, k - 1);
+        iac_now = iac_at(P, col, k);
+        iac_nxt = iac_at(P, col, k + 1);
+      }
+      hhd_subexpr(P.cc, p, x, S, iac_prev);
       if (meta & FLAG_HAS_PREV) {
         const double band = hhd_div(S.D0, p.tauw);
         wcross = (x[1] > S.w_V - band) && (x[1] < S.w_V + band) && (x[0] <= p.VT);
@@ -404,11 +430,17 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       if (meta & FLAG_SPIKED) {        /* slot `resets`: V = V_r; w += b   (codes/CortexNetwork.py:305) */
         x[0] = p.Vr;
         x[1] += p.b;
-        hhd_subexpr(P.cc, p, x, S);
+        hhd_subexpr(P.cc, p, x, S, iac_prev);
       } else if (new_g) {
         hhd_subexpr_new_g(P.cc, p, x, S);
       }
       if (wcross) x[1] = S.w_V - hhd_div(S.D0, p.tauw);      /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
+      if (iac_now != iac_prev) {          /* the clock moves on: I_inj of step k; again only the linear part changes */
+        S.I_inj = p.IDC + iac_now;
+        hhd_subexpr_new_g(P.cc, p, x, S);
+      }
+      iac0 = iac_now;
+      iac1 = iac_nxt;
     }
     if (!STEP) {
       if (live) {
@@ -445,7 +477,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     if (live) {
       /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
 #if !(HHD_EXPERIMENT & 2)
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S);
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S, iac0, iac1);
 #endif
       bad = !(isfinite(x[0]) && isfinite(x[1]));
       /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
@@ -1059,7 +1091,7 @@ __global__ void k_read_var(const __grid_constant__ Params P, int var, double* ou
 #pragma unroll
   for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
   const NeuronPar p = load_par(P, i);
-  out[i] = hhd_var_value(P.cc, p, x, var, P.last_spike[P.off + i]);
+  out[i] = hhd_var_value(P.cc, p, x, var, P.last_spike[P.off + i], P.iac_table ? iac_at(P, P.iac_col[i], *P.base_step) : 0.0);
 }
 
 /* ================================================== host side =================================================== */
@@ -1277,6 +1309,23 @@ extern "C" int hhd_set_idc(hhd_handle h, const double* idc) {
   if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
   cudaSetDevice(h->cfg.device);
   return upload(h, h->P.par[HHD_P_IDC], idc, (size_t)h->N);
+}
+
+extern "C" int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const double* table, const int32_t* col_of_neuron) {
+  if (!h || n_steps <= 0 || n_cols <= 0 || !table || !col_of_neuron) return fail(h, HHD_E_ARG, "bad argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_timed_current after run");
+  for (int i = 0; i < h->N; ++i) if (col_of_neuron[i] >= n_cols) return fail(h, HHD_E_ARG, "column index out of range");
+  cudaSetDevice(h->cfg.device);
+  double* dt = nullptr;
+  int* dc = nullptr;
+  int rc = dev_alloc(h, &dt, (size_t)n_steps * n_cols, false);
+  if (!rc) rc = dev_alloc(h, &dc, (size_t)h->N, false);
+  if (!rc) rc = upload(h, dt, table, (size_t)n_steps * n_cols);
+  if (!rc) rc = upload(h, dc, col_of_neuron, (size_t)h->N);
+  if (rc) return rc;
+  h->P.iac_table = dt; h->P.iac_col = dc; h->P.iac_steps = n_steps; h->P.iac_cols = n_cols;
+  h->graph_dirty = true;
+  return HHD_OK;
 }
 
 extern "C" int hhd_set_has_outgoing(hhd_handle h, const uint8_t* has_out_global) {
@@ -1766,7 +1815,7 @@ static int finalize_setup(hhd_handle h) {
   {
     const int inst = h->cfg.instance_size > 0 ? h->cfg.instance_size : h->N;
     const bool can = h->cfg.n_ranks == 1 && P.max_delay < P.refr_steps && inst <= RES_MAX_CLUSTER * RES_BLOCK && h->N % inst == 0 &&
-                     !h->cross_instance && h->NG == h->N;
+                     !h->cross_instance && h->NG == h->N && !P.iac_table;
     if (h->cfg.plan == HHD_PLAN_RESIDENT && !can)
       return fail(h, HHD_E_ARG, "HHD_PLAN_RESIDENT needs independent instances of at most %d neurons (instance_size), no synapse "
                   "between instances, max delay < refractory period and a single rank", RES_MAX_CLUSTER * RES_BLOCK);

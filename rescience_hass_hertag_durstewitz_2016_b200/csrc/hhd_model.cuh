@@ -27,7 +27,8 @@ struct SubExpr {
 };
 
 /* state order: V, w, gA_on, gA_off, gG_on, gG_off, gN_on, gN_off (= HHD_V .. HHD_G_NMDA_OFF) */
-__device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const NeuronPar& p, const double x[8], SubExpr& s) {
+__device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const NeuronPar& p, const double x[8], SubExpr& s,
+                                            const double iac = 0.0) {
   const double V = x[0];
   s.g[0] = x[3] - x[2];
   s.g[1] = x[5] - x[4];
@@ -38,7 +39,7 @@ __device__ __forceinline__ void hhd_subexpr(const ChannelConst& cc, const Neuron
   s.I_NMDA = (s.g[2] * (cc.E[2] - V)) * Mg;
   s.Mg = Mg;
   s.I_syn = (s.I_AMPA + s.I_NMDA) + s.I_GABA;
-  s.I_inj = p.IDC + 0.0;
+  s.I_inj = p.IDC + iac;                                  /* I_inj = I_DC + I_AC   (codes/CortexNetwork.py:236-237) */
   s.I_tot = s.I_syn + s.I_inj;
   s.ex = hhd_exp(hhd_div(V - p.VT, p.dT));
   s.I_exp = (p.gL * p.dT) * s.ex;
@@ -84,8 +85,8 @@ __device__ __forceinline__ void hhd_rhs(const ChannelConst& cc, const NeuronPar&
 
 /* Subexpressions + right-hand sides (stages after the first). */
 __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t,
-                                          double ls, double d[8], SubExpr& s) {
-  hhd_subexpr(cc, p, x, s);
+                                          double ls, double d[8], SubExpr& s, const double iac = 0.0) {
+  hhd_subexpr(cc, p, x, s, iac);
   hhd_rhs(cc, p, x, t, ls, s, d);
 }
 
@@ -93,7 +94,8 @@ __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPa
  * (the caller has them already: they also decide the deferred w_crossing test and feed the monitors). */
 template <int METHOD>
 __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t,
-                                              double ls, double dt, const SubExpr& s1) {
+                                              double ls, double dt, const SubExpr& s1, const double iac0 = 0.0,
+                                              const double iac1 = 0.0) {   /* I_AC of this step / of the next (stage at t+dt) */
   double k1[8], y[8];
   SubExpr sk;
   hhd_rhs(cc, p, x, t, ls, s1, k1);
@@ -107,7 +109,7 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   double k2[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k1[v] * 0.5;
-  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k2, sk);
+  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k2, sk, iac0);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k2[v] = dt * k2[v];
   if (METHOD == 1) {
@@ -118,12 +120,12 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   double k3[8], k4[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k2[v] * 0.5;
-  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k3, sk);
+  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k3, sk, iac0);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k3[v] = dt * k3[v];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k3[v];
-  hhd_deriv(cc, p, y, t + dt, ls, k4, sk);
+  hhd_deriv(cc, p, y, t + dt, ls, k4, sk, iac1);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
 #pragma unroll
@@ -134,7 +136,8 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
  * function integrate_rk23 of oracle/hhd_oracle.c (IEEE sqrt only), see there for the controller. */
 template <>
 __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const NeuronPar& p, double x[8], double t0,
-                                                 double ls, double dt, const SubExpr& s1) {
+                                                 double ls, double dt, const SubExpr& s1, const double iac0,
+                                                 const double iac1) {
   const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
   double t = 0.0, hs = dt;
   bool first = true;
@@ -143,14 +146,14 @@ __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const N
     double k1[8], k2[8], k3[8], y[8], ynew[8];
     SubExpr sk;
     if (first) hhd_rhs(cc, p, x, t0 + t, ls, s1, k1);
-    else hhd_deriv(cc, p, x, t0 + t, ls, k1, sk);
+    else hhd_deriv(cc, p, x, t0 + t, ls, k1, sk, iac0);
     first = false;
 #pragma unroll
     for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
-    hhd_deriv(cc, p, y, t0 + (t + 0.5 * hs), ls, k2, sk);
+    hhd_deriv(cc, p, y, t0 + (t + 0.5 * hs), ls, k2, sk, iac0);
 #pragma unroll
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    hhd_deriv(cc, p, y, t0 + (t + hs), ls, k3, sk);
+    hhd_deriv(cc, p, y, t0 + (t + hs), ls, k3, sk, (t + hs) >= dt ? iac1 : iac0);
     double rmax = 0.0;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -202,7 +205,7 @@ __device__ __forceinline__ bool hhd_var_is_derived(int var) { return var >= 8 &&
 
 /* Value of a monitored / derived variable (ids of include/hhd.h) from the state. */
 __device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const NeuronPar& p, const double x[8], int var,
-                                                double last_spike) {
+                                                double last_spike, const double iac = 0.0) {
   switch (var) {   /* constant indices keep x[] in registers */
     case 0: return x[0];
     case 1: return x[1];
@@ -215,7 +218,7 @@ __device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const Ne
     case 20: return last_spike;
   }
   SubExpr s;
-  hhd_subexpr(cc, p, x, s);
+  hhd_subexpr(cc, p, x, s, iac);
   switch (var) {
     case 8: return s.g[0];
     case 9: return s.g[1];

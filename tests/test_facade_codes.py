@@ -132,3 +132,21 @@ def test_unsupported_variants_fail_loudly():
                       NOSCALE, 0.5, "rk4", 0.05, 0, "", _engine_cls=OracleEngine)
     with pytest.raises(ValueError):
         build(g, method="heun")
+
+
+def test_fluctuating_current():
+    g = load_golden("net_n200_s0")
+    groups = [[list(map(int, s)) for s in grp] for grp in golden_groups(g)]
+    AC = [["" for _ in range(14)]]
+    AC[0][0] = "50*sin(2*pi*t/20)"
+    AC[0][7] = "30"
+    c = CortexNetwork(g["NeuPar"], g["V0"], g["STypPar"], g["SynPar"], (g["target_arr"], g["source_arr"]), groups,
+                      [[0] * 14], [5, 25, AC], NOSCALE, False, "rk4", 0.05, 1, "", _engine_cls=OracleEngine)
+    assert c.ta.shape == (500, 2)
+    c.neuron_monitors([["I", ["I_inj"], [["all", "all"]]]])
+    c.run(40 * ms)
+    I = c.neuronmonitors["I"].I_inj / pA
+    pc23, pc5, other = groups[0][0][0], groups[7][0][0], groups[1][0][0]
+    assert np.all(I[pc23, :100] == 0) and I[pc23, 100:500].max() == pytest.approx(50.0, rel=1e-3)
+    assert np.all(I[pc5, 100:] == 30.0) and np.all(I[other] == 0)
+    assert np.all(I[pc23, 500:] == I[pc23, 499])                      # TimedArray holds its last value

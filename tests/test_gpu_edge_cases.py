@@ -172,3 +172,25 @@ def test_ring_of_columns_with_inter_column_synapses():
         out[name] = e
     assert same(out["gpu"], out["cpu"]) > 2000
     assert out["gpu"].counters()["syn_deliveries"] == out["cpu"].counters()["syn_deliveries"]
+
+
+@pytest.mark.parametrize("plan", ["graph", "persistent", "auto"])
+@pytest.mark.parametrize("method", ["euler", "rk4", "rk23"])
+def test_timed_current(method, plan):
+    """TimedArray I_AC: stages at t + dt read the next row; bit-identical to the oracle (the resident plan steps aside)."""
+    g = load_golden("net_n200_s0")
+    steps = 3000
+    tt = np.arange(steps) * 0.05
+    table = np.stack([150.0 * np.sin(2 * np.pi * tt / 37.0) + 100.0, np.where((tt > 20) & (tt < 60), 400.0, 0.0)], axis=1)
+    col = np.full(207, -1, dtype=np.int32)
+    col[:94] = 0
+    col[150:] = 1
+    res = {}
+    for kind in ("gpu", "cpu"):
+        e = make_engine(kind, g, method=method, accum="fixed", seed=12, **({"plan": plan} if kind == "gpu" else {}))
+        e.set_timed_current(table, col)
+        m = e.add_state_monitor("I_tot", np.arange(0, 207, 11, dtype=np.int32))
+        e.run(steps + 500)
+        res[kind] = (e, e.read_monitor(m))
+    assert same(res["gpu"][0], res["cpu"][0]) > 200
+    assert np.array_equal(res["gpu"][1], res["cpu"][1])

@@ -186,3 +186,24 @@ def test_golden_fixture_digests():
         for key, arr in (("sha_NeuPar", g["NeuPar"]), ("sha_V0", g["V0"]), ("sha_SynPar", g["SynPar"]),
                          ("sha_target", g["target_arr"].astype(np.int64)), ("sha_source", g["source_arr"].astype(np.int64))):
             assert hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest() == str(g[key]), (name, key)
+
+
+def test_timed_current_follows_timedarray_semantics():
+    """I_AC = ta(t, i) (codes/CortexNetwork.py:133-151): row s during step s, the last row held afterwards, neurons
+    without a column get 0; a sinusoidal current makes a passive cell oscillate with the analytic gain."""
+    n, dt, steps = 3, 0.05, 4000
+    e = engine(n, [0.0, 0.0, 100.0], dt=dt, method="rk4")
+    tt = np.arange(steps) * dt
+    table = np.stack([20.0 * np.sin(2 * np.pi * tt / 50.0), np.where(tt < 10.0, 0.0, 30.0)], axis=1)
+    e.set_timed_current(table, [0, 1, -1])
+    mi = e.add_state_monitor("I_inj", None)
+    mv = e.add_state_monitor("V", [0])
+    e.run(steps + 200)
+    I = e.read_monitor(mi)
+    assert np.array_equal(I[:steps, 0], table[:, 0]) and np.array_equal(I[:steps, 1], table[:, 1])
+    assert np.all(I[steps:, 0] == table[-1, 0]) and np.all(I[steps:, 1] == 30.0)      # last row held
+    assert np.all(I[:, 2] == 100.0)                                                    # I_DC only
+    V = e.read_monitor(mv)[2000:steps, 0]                   # steady oscillation of a leaky integrator
+    tau = BASE["C"] / BASE["g_L"]
+    gain = 1.0 / (BASE["g_L"] * math.sqrt(1.0 + (2 * math.pi * tau / 50.0) ** 2))
+    assert (V.max() - V.min()) / 2 == pytest.approx(20.0 * gain, rel=0.02)
