@@ -31,6 +31,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -96,9 +97,10 @@ struct Params {
   double* last_spike;          /* [NG] */
   int* meta;                   /* [N] lastspike_step * 4 + flags of the previous step */
   const unsigned char* has_out;/* [NG] */
-  long long* pend;             /* [3][n_pad] synaptic increments of the step in progress, summed per (channel, target):
-                                  fp64 bits (HHD_ACCUM_FP64) or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED); consumed
-                                  and cleared by the next state-update pass */
+  long long* pend;             /* [2][3][n_pad] synaptic increments summed per (channel, target): fp64 bits (HHD_ACCUM_FP64)
+                                  or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED).  The deliveries of slot k go to buffer
+                                  (k+1)&1; the state-update pass of step k+1 consumes and clears it.  Two buffers, so that
+                                  the pipelined schedule can fill one while the state update drains the other. */
   long long n_pad;             /* neurons rounded up to whole tiles */
   /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
   const long long* row_ptr;    /* [NG+1] */
@@ -107,6 +109,10 @@ struct Params {
   const unsigned short* row_maxd; /* [NG] largest delay (steps) in the row */
   const unsigned int* row_bkt; /* [NG][DELAY_BUCKETS] offset inside the row of the first synapse with delay >= b*bkt_width */
   int bkt_width;
+  const unsigned short* row_doff; /* [NG][max_delay + 2] offset inside the row of the first synapse with delay >= d (pipelined
+                                     schedule: one thread per active spike reads exactly its due synapses); NULL = not built */
+  unsigned long long* dbg_times;   /* HHD_DEBUG_TIMES: [grid][4] globaltimer at start / after ahead_phase / end of the tiles / end */
+  int doff_stride, stp_chunks, ahead_ctas;    /* max_delay + 2; ceil(longest row / NEURON_BLOCK) */
   long long syn_id_base;
   /* spike ring */
   int* spk_neuron;             /* global ids */
@@ -117,6 +123,13 @@ struct Params {
   int* spk_last;               /* [NG] step of the latest spike of every (global) neuron, written when the spike is appended */
   unsigned long long* head;    /* monotone count of spikes appended */
   unsigned long long* step_end;/* [W] head value at the end of step (k % W) */
+  /* pipelined schedule (see k_neuron<.., PIPE>): */
+  double* prev_spike;          /* [NG] last_spike of a neuron before its latest spike (the STP update runs one pass later) */
+  unsigned long long* stp_mark;/* ring position below which pathways p0..p6 have been applied */
+  unsigned int* pass_done;     /* CTAs that finished the current pass */
+  unsigned int* tile_ctr;      /* tiles handed out in the current pass beyond the first two of every CTA */
+  unsigned int* zcount;        /* spikes of the current step whose row starts with zero-delay synapses ... */
+  int* zlist;                  /* [N] ... and their neurons; the last CTA of the pass serves them (spike_local) */
   /* external input events, grouped by step */
   const int* ext_ptr;          /* [ext_last - ext_first + 2] */
   long long ext_first, ext_last;
@@ -241,6 +254,9 @@ struct NeuronShared {            /* static shared memory of a CTA that runs neur
   double red[MAX_MON][NEURON_BLOCK / 32];
   MonDesc mon[MAX_MON];          /* read once per CTA instead of once per tile from global memory */
   unsigned long long cnt[3];
+  int is_last;                   /* pipelined schedule: this CTA is the last one of the pass to finish */
+  int zl_n, zl_j[16];            /* pipelined schedule: this CTA's spikes of the step whose rows start with zero-delay synapses */
+  int tile_fetch[2];             /* pipelined schedule: tile index the producer thread drew for the stage freed in iteration it (slot it & 1) */
   unsigned long long full_bar[NEURON_STAGES * (HHD_NEURON_PREFETCH == 3 ? NEURON_BLOCK / 32 : 1)];
 };
 
@@ -257,9 +273,19 @@ __device__ __forceinline__ void neuron_shared_init(const Params& P, NeuronShared
   __syncthreads();
 }
 
+__device__ __forceinline__ void spike_local(const Params& P, int j, long long k, double t);
+__device__ __forceinline__ void ahead_phase(const Params& P, long long k, unsigned part, unsigned nparts);
+
 /* One pass over this CTA's tiles for time step k.  `bar_parity` carries the phase bit of every mbarrier across calls
- * (the cooperative whole-run kernel calls this once per step on the same barriers). */
-template <int METHOD, bool STEP>
+ * (the cooperative whole-run kernel calls this once per step on the same barriers).
+ * PIPE = true is the pipelined schedule: the pass is the ONLY launch of the step.  Besides the state update it
+ *  - delivers, somewhere between two of its tiles, this CTA's share of slot k's synaptic events whose spikes are at
+ *    least one step old, and applies p0..p6 to the spikes of step k-1 (ahead_phase) — into the pending buffer the NEXT
+ *    pass consumes, so nothing here waits for it;
+ *  - lets the thread that detects a spike do what must be visible to pass k+1: last_spike (p5) and the row's zero-delay
+ *    synapses (spike_local);
+ *  - has its last CTA publish the head of the spike ring as the end of step k. */
+template <int METHOD, bool STEP, bool TIMED, bool PIPE>
 __device__ __forceinline__ void neuron_phase(const Params& P, const long long k, NeuronStage* st, NeuronShared& sh,
                                              unsigned& bar_parity) {
   double (*red)[NEURON_BLOCK / 32] = sh.red;
@@ -271,6 +297,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   const double t = (double)k * P.dt;
   const int ntiles = (P.N + NEURON_BLOCK - 1) / NEURON_BLOCK;
   if (tid < 3) cnt_sh[tid] = 0ull;
+  if (tid == 0) sh.zl_n = 0;
   __syncthreads();
 
 #if HHD_NEURON_PREFETCH >= 2
@@ -320,21 +347,58 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   for (int r = 0; r < MAX_RED; ++r) mon_acc[r] = 0.0;
   unsigned n_spk = 0, n_wc = 0, n_bad = 0;
 
-  int tile = blockIdx.x;
+  auto stamp = [&](int q) {
+    if (STEP && P.dbg_times && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.dbg_times[((size_t)(k & 1) * 4096 + blockIdx.x) * 4 + q] = g;
+      if (blockIdx.x == 0 && q == 0) P.dbg_times[8 * 4096 + (k & 4095) * 2] = g; }
+  };
+  constexpr bool DYN = PIPE && STEP && HHD_NEURON_PREFETCH == 2;
+  stamp(0);
+  /* First two tiles.  Static (b, b + grid) — except in the pipelined schedule: there the first ahead_ctas CTAs of the grid
+   * (one per SM by default) first do the synaptic work of slot k (its latency hides behind the arithmetic of the SM's
+   * other CTAs) and then draw ALL their tiles from the counter, like everybody draws every further tile: whoever is done
+   * earlier integrates more. */
+  int tile = blockIdx.x, tile_nxt = tile + (int)gridDim.x, dyn_base = 2 * (int)gridDim.x;
+  if (DYN) {
+    const int A = P.ahead_ctas, rest = (int)gridDim.x - A;
+    dyn_base = 2 * rest;
+    if ((int)blockIdx.x < A) {
+      ahead_phase(P, k, blockIdx.x, (unsigned)A);
+      if (tid < 2) sh.tile_fetch[tid] = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
+      __syncthreads();
+      tile = min(sh.tile_fetch[0], sh.tile_fetch[1]);
+      tile_nxt = max(sh.tile_fetch[0], sh.tile_fetch[1]);
+      __syncthreads();
+    } else {
+      tile = (int)blockIdx.x - A;
+      tile_nxt = tile + rest;
+    }
+  }
+  stamp(1);
+  long long* const pin = P.pend + (size_t)(k & 1) * 3 * (size_t)P.n_pad;     /* filled during slot k-1 */
   long long pd_next[3] = {0, 0, 0};
   int col_next = -1;                 /* TimedArray column of the neuron (only read when a timed current is set) */
 #if HHD_NEURON_PREFETCH
   issue(tile, 0);
-  if (tile * NEURON_BLOCK + tid < P.N) {
+  if (tile < ntiles && tile * NEURON_BLOCK + tid < P.N) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) pd_next[c] = P.pend[(size_t)c * P.n_pad + tile * NEURON_BLOCK + tid];
-    if (P.iac_table) col_next = P.iac_col[tile * NEURON_BLOCK + tid];
+    for (int c = 0; c < 3; ++c) pd_next[c] = pin[(size_t)c * P.n_pad + tile * NEURON_BLOCK + tid];
+    if ((TIMED && P.iac_table)) col_next = P.iac_col[tile * NEURON_BLOCK + tid];
   }
 #endif
 #if HHD_NEURON_PREFETCH >= 2
-  issue(tile + gridDim.x, 1);        /* two tiles in flight from the start */
+  issue(tile_nxt, 1);                /* two tiles in flight from the start */
 #endif
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+  /* PIPE: after its first two tiles a CTA draws its tiles from a counter (the synaptic share above takes a different
+   * time in every CTA; whoever is done earlier integrates more) — otherwise tile, tile + grid, tile + 2 grid, ... */
+  /* The producer thread draws a tile index a whole iteration before it publishes it: the atomic's round trip must not
+   * stall warp 0 at the top of every iteration. */
+  int fetched = 0;
+  if (DYN && tid == 0) fetched = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
+  for (int it = 0; tile < ntiles; ++it) {
+    if (DYN && tid == 0) {
+      sh.tile_fetch[it & 1] = fetched;
+      fetched = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
+    }
     const int i = tile * NEURON_BLOCK + tid;
     const bool live = i < P.N;
     double x[8];
@@ -351,7 +415,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       ls = P.last_spike[P.off + i];
       meta = P.meta[i];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) pd[c] = P.pend[(size_t)c * P.n_pad + i];
+      for (int c = 0; c < 3; ++c) pd[c] = pin[(size_t)c * P.n_pad + i];
     }
     if (false) {
       const int s = 0;
@@ -380,22 +444,29 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     {   /* pending increments: this tile's were requested one iteration ago, the next tile's are requested now */
 #pragma unroll
       for (int c = 0; c < 3; ++c) pd[c] = pd_next[c];
-      const int in = i + (int)gridDim.x * NEURON_BLOCK;
+      const int in = tile_nxt * NEURON_BLOCK + tid;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) pd_next[c] = in < P.N ? P.pend[(size_t)c * P.n_pad + in] : 0;
+      for (int c = 0; c < 3; ++c) pd_next[c] = in < P.N ? pin[(size_t)c * P.n_pad + in] : 0;
       col = col_next;
-      col_next = (P.iac_table && in < P.N) ? P.iac_col[in] : -1;
+      col_next = ((TIMED && P.iac_table) && in < P.N) ? P.iac_col[in] : -1;
     }
 #else
-    if (P.iac_table && live) col = P.iac_col[i];
+    if ((TIMED && P.iac_table) && live) col = P.iac_col[i];
 #endif
 #if HHD_NEURON_PREFETCH == 2
     __syncthreads();   /* every thread holds its neuron of this tile in registers: stage s is free again */
-    issue(tile + 2 * gridDim.x, s);    /* so the tile after next is requested NOW: two tiles in flight with two stages */
+    const int tile_nn = DYN ? sh.tile_fetch[it & 1] : tile + 2 * (int)gridDim.x;
+    issue(tile_nn, s);                 /* so the tile after next is requested NOW: two tiles in flight with two stages */
+
 #elif HHD_NEURON_PREFETCH == 3
     __syncwarp();      /* the warp's part of stage s is free again */
-    issue(tile + 2 * gridDim.x, s);
+    const int tile_nn = tile + 2 * (int)gridDim.x;
+    issue(tile_nn, s);
+#else
+    const int tile_nn = tile + 2 * (int)gridDim.x;
 #endif
+    tile = tile_nxt;
+    tile_nxt = tile_nn;
     SubExpr S;
     bool wcross = false;
     double iac0 = 0.0, iac1 = 0.0;
@@ -406,7 +477,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
        * and then only their linear part changes — ARE the subexpressions of the first stage of step k: one evaluation
        * (two exponentials, three divisions) per neuron-step instead of two. */
       double iac_prev = 0.0, iac_now = 0.0, iac_nxt = 0.0;      /* I_AC at steps k-1, k, k+1 */
-      if (P.iac_table) {
+      if ((TIMED && P.iac_table)) {
         iac_prev = iac_at(P, col, k - 1);
         iac_now = iac_at(P, col, k);
         iac_nxt = iac_at(P, col, k + 1);
@@ -423,7 +494,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
           const double inc = P.accum == HHD_ACCUM_FIXED ? (double)pd[c] * (1.0 / 1099511627776.0) : __longlong_as_double(pd[c]);
           x[2 + 2 * c] += inc;
           x[3 + 2 * c] += inc;
-          P.pend[(size_t)c * P.n_pad + i] = 0;
+          pin[(size_t)c * P.n_pad + i] = 0;
           new_g = true;
         }
       }
@@ -510,12 +581,27 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
           P.spk_last[P.off + i] = (int)k;
         }
       }
+      if (PIPE && spiked) {      /* what pass k+1 must see of this spike: p5 now, its zero-delay synapses before the pass ends */
+        const int j = P.off + i;
+        const unsigned char ho = P.has_out[j];
+        P.prev_spike[j] = ls;
+        if (ho & 1) P.last_spike[j] = t;
+        if (ho & 2) {            /* served by this CTA after its last tile; beyond 16, by the CTA that closes the pass */
+          const int q = atomicAdd(&sh.zl_n, 1);
+          if (q < 16) sh.zl_j[q] = j; else P.zlist[atomicAdd(P.zcount, 1u)] = j;
+        }
+      }
     }
     n_spk += spiked;
     n_wc += wcross;
     n_bad += bad;
   }
   cp_async_wait<0>();
+  stamp(2);
+  if (PIPE && STEP) {
+    __syncthreads();
+    if (tid < min(sh.zl_n, 16)) spike_local(P, sh.zl_j[tid], k, t);
+  }
   if (!STEP) {                      /* only the w_crossing events found while finishing the last step are left to count */
     n_wc = __reduce_add_sync(0xffffffffu, n_wc);
     if (lane == 0 && n_wc) atomicAdd(&P.counters[CNT_WCROSS], (unsigned long long)n_wc);
@@ -558,6 +644,28 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       for (int q = 0; q < NEURON_BLOCK / 32; ++q) bsum += red[m][q];
       atomicAdd(&md.buf[sample], bsum);
     }
+    if (PIPE) {
+      __threadfence();
+      sh.is_last = atomicAdd(P.pass_done, 1u) == gridDim.x - 1;
+    }
+  }
+  stamp(3);
+  if (PIPE) {          /* the last CTA to finish closes the step: every spike of step k is in the ring below *head */
+    __syncthreads();
+    if (sh.is_last) {
+      __threadfence();
+      const unsigned nz = *(volatile unsigned*)P.zcount;           /* spikes of this step whose row has zero-delay synapses (rare) */
+      for (unsigned q = tid; q < nz; q += NEURON_BLOCK) spike_local(P, ((volatile int*)P.zlist)[q], k, t);
+      __syncthreads();
+      if (tid == 0) {
+        if (P.dbg_times) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.dbg_times[8 * 4096 + (k & 4095) * 2 + 1] = g; }
+        *P.zcount = 0u;
+        *P.pass_done = 0u;
+        *P.tile_ctr = 0u;
+        *P.stp_mark = P.step_end[((int)k + P.W - 1) % P.W];     /* ahead_phase of this pass applied p0..p6 up to here */
+        P.step_end[(int)k % P.W] = *(volatile unsigned long long*)P.head;
+      }
+    }
   }
 }
 
@@ -565,7 +673,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
  * METHOD: 0 euler, 1 rk2, 2 rk4, 3 adaptive rk2(3).  STEP = false: only finish the previous step (used once at the end of
  * hhd_run so that the state read back is the state after `resets`/`after_resets`).
  */
-template <int METHOD, bool STEP>
+template <int METHOD, bool STEP, bool TIMED = false, bool PIPE = false>
 __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ NeuronShared sh;
@@ -573,22 +681,26 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   pdl_wait();
   neuron_shared_init(P, sh);
   unsigned bar_parity = 0;
-  neuron_phase<METHOD, STEP>(P, *P.base_step + step_offset, reinterpret_cast<NeuronStage*>(smem_raw), sh, bar_parity);
+  neuron_phase<METHOD, STEP, TIMED, PIPE>(P, *P.base_step + step_offset, reinterpret_cast<NeuronStage*>(smem_raw), sh, bar_parity);
 }
 
-__device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc) {
+/* buffer that collects the deliveries of slot k */
+__device__ __forceinline__ long long* pend_of_slot(const Params& P, long long k) {
+  return P.pend + (size_t)((k + 1) & 1) * 3 * (size_t)P.n_pad;
+}
+__device__ __forceinline__ void add_increment(const Params& P, long long* pout, int c, int tgt, double inc) {
   /* summed per (channel, target) for this step; the target's next state-update pass adds the sum to g_on and g_off */
   if (P.accum == HHD_ACCUM_FIXED) {
     const long long q = __double2ll_rn(inc * 1099511627776.0);
-    atomicAdd((unsigned long long*)&P.pend[(size_t)c * P.n_pad + tgt], (unsigned long long)q);
+    atomicAdd((unsigned long long*)&pout[(size_t)c * P.n_pad + tgt], (unsigned long long)q);
   } else {
-    atomicAdd(reinterpret_cast<double*>(&P.pend[(size_t)c * P.n_pad + tgt]), inc);
+    atomicAdd(reinterpret_cast<double*>(&pout[(size_t)c * P.n_pad + tgt]), inc);
   }
 }
 
 /* All synapses of neuron j whose delay equals `age` (whole warp): bucket index -> segment of the delay-sorted row ->
  * 16-byte records; returns the number of deliveries this lane made. */
-__device__ __forceinline__ unsigned deliver_row_due(const Params& P, const int j, const int age, const unsigned lane) {
+__device__ __forceinline__ unsigned deliver_row_due(const Params& P, long long* pout, const int j, const int age, const unsigned lane) {
   unsigned n = 0;
   const long long r0 = P.row_ptr[j];
   const int b = age / P.bkt_width;
@@ -604,14 +716,155 @@ __device__ __forceinline__ unsigned deliver_row_due(const Params& P, const int j
     }
     if (d == age) {
       ++n;
-      if (sh.amp != 0.0) add_increment(P, sh.chan, sh.tgt, sh.amp);
+      if (sh.amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, sh.amp);
     }
     if (__all_sync(0xffffffffu, d > age)) break;              /* rows are sorted by delay */
   }
   return n;
 }
 
-__device__ __forceinline__ void add_increment(const Params& P, int c, int tgt, double inc);
+
+/* ---- pipelined schedule -------------------------------------------------------------------------------------------
+ * Legal while max_delay < refractory steps (a neuron never has a new spike and an undelivered older one) on a
+ * single rank.  What pass k+1 must see of the spikes of step k is only last_spike (p5) and the zero-delay deliveries —
+ * spike_local, by the detecting thread.  Everything else of slot k+1 depends on spikes of steps <= k only, so pass k+1
+ * computes it itself while it integrates (ahead_phase) and pass k+2 consumes it. */
+/* zero-delay synapses of neuron j, which spiked in step k (time t): p0..p6 and delivery for those synapses only */
+__device__ __forceinline__ void spike_local(const Params& P, int j, long long k, double t) {
+  const double last = ((volatile double*)P.prev_spike)[j];
+  const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+  long long* const pout = pend_of_slot(P, k);
+  unsigned long long n = 0;
+  for (long long r = r0; r < r1; ++r) {
+    const SynHot sh = P.hot[r];
+    if (sh.delay != 0) break;
+    SynStp sy = P.stp[r];
+    const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t, last,
+                                      P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)k);
+    P.stp[r].u = sy.u;
+    P.stp[r].R = sy.R;
+    P.hot[r].amp = amp;
+    ++n;
+    if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
+  }
+  atomicAdd(&P.del_slots[j & (CNT_SLOTS - 1)], n);
+}
+
+/* p0..p6 for the ring entries [lo, hi) (spikes whose rows were not processed yet).  A task is NEURON_BLOCK consecutive
+ * synapses of one spike's row (stp_chunks tasks per spike); CTA `part` of `nparts` takes every nparts-th task.
+ * slot >= 0: also deliver the synapses of those rows that are due in that slot.  Zero-delay synapses were handled by
+ * spike_local at the spike's own step. */
+__device__ __forceinline__ void stp_range(const Params& P, const long long slot, const unsigned long long lo,
+                                          const unsigned long long hi, const unsigned part, const unsigned nparts) {
+  long long* const pout = pend_of_slot(P, slot);
+  unsigned long long delivered = 0;
+  const unsigned chunks = (unsigned)P.stp_chunks;
+  const unsigned ntasks = (unsigned)(hi - lo) * chunks;                 /* far below 2^32: one spike per neuron and step at most */
+  for (unsigned task = part; task < ntasks; task += nparts) {
+    const unsigned long long sp = lo + task / chunks;
+    const unsigned chunk = task % chunks;
+    const unsigned pos = (unsigned)sp & P.cap_mask;
+    const int j = P.spk_neuron[pos];
+    const long long ks = (long long)P.spk_step[pos];
+    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+    if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
+    const double ts = (double)ks * P.dt;
+    const double last = P.prev_spike[j];
+    /* rows longer than stp_chunks blocks (rare: the chunk count follows the mean row) wrap around */
+    for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x) {
+      const SynHot sh = P.hot[r];
+      if (sh.delay == 0) continue;
+      SynStp sy = P.stp[r];
+      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, ts, last,
+                                        P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)ks);
+      P.stp[r].u = sy.u;
+      P.stp[r].R = sy.R;
+      P.hot[r].amp = amp;
+      if (slot >= 0 && (long long)sh.delay == slot - ks) {
+        ++delivered;
+        if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
+      }
+    }
+  }
+  delivered = (unsigned long long)warp_sum((double)delivered);
+  if ((threadIdx.x & 31) == 0 && delivered) atomicAdd(&P.del_slots[(part * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], delivered);
+}
+
+__device__ __forceinline__ void ext_events(const Params& P, const long long k, long long* const pout, const unsigned gtid, const unsigned gthreads);
+
+/* This CTA's share of slot k in the pipelined schedule: p0..p6 of the spikes of step k-1 (and their delay-1 synapses),
+ * the due synapses of every older active spike — ONE THREAD per active spike: the per-delay offsets of the row give it
+ * exactly its due synapses, so the whole chain is three dependent loads — and the SpikeGeneratorGroup events of step k. */
+__device__ __forceinline__ void ahead_phase(const Params& P, const long long k, const unsigned part, const unsigned nparts) {
+  const unsigned lane = threadIdx.x & 31;
+  long long* const pout = pend_of_slot(P, k);
+  const unsigned long long lo = P.step_end[((int)k + 1) % P.W];        /* head at the end of step k - max_delay - 1 */
+  const unsigned long long hi = P.step_end[((int)k + P.W - 1) % P.W];  /* head at the end of step k - 1 */
+  const unsigned long long mark = *P.stp_mark;
+  const unsigned gthreads = nparts * blockDim.x;
+  /* Deliveries.  The active spikes are spread evenly over every warp of the grid (spw per warp, from the far end of the
+   * grid so that the CTAs with an STP task come last); each lane looks up the due segment of ITS spike, then the warp
+   * walks the concatenation of its lanes' segments 32 synapses at a time — the segments are very uneven (0..~100). */
+  {
+    const unsigned nact = (unsigned)(mark - lo);
+    const unsigned warps = gthreads >> 5;
+    const unsigned spw = min(32u, (nact + warps - 1) / warps);
+    const unsigned wid = (nparts - 1 - part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned long long delivered = 0;
+    for (unsigned long long first = lo + (unsigned long long)wid * spw; first < mark && spw; first += (unsigned long long)warps * spw) {
+      long long ra = 0;
+      unsigned cnt = 0;
+      if (lane < spw && first + lane < mark) {
+        const unsigned pos = (unsigned)(first + lane) & P.cap_mask;
+        const int j = P.spk_neuron[pos];
+        const int age = (int)(k - (long long)P.spk_step[pos]);
+        if (age <= P.max_delay) {
+          const unsigned short* o = P.row_doff + (size_t)j * P.doff_stride + age;
+          const unsigned a0 = o[0], a1 = o[1];
+          ra = P.row_ptr[j] + a0;
+          cnt = a1 - a0;
+        }
+      }
+      unsigned incl = cnt;                                   /* inclusive prefix sum of the segment lengths */
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      const unsigned excl = incl - cnt;
+      for (unsigned base = 0; base < total; base += 32) {
+        const unsigned idx = base + lane;
+        /* owner = the last lane whose exclusive prefix is <= idx (binary search over the warp) */
+        unsigned owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const unsigned probe = owner + step;
+          const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
+          if (probe < 32 && e <= idx) owner = probe;
+        }
+        const long long ra_o = __shfl_sync(0xffffffffu, ra, owner);
+        const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
+        if (idx < total) {
+          const SynHot q = P.hot[ra_o + (idx - ex_o)];
+          ++delivered;
+          if (q.amp != 0.0) add_increment(P, pout, q.chan, q.tgt, q.amp);
+        }
+      }
+    }
+    delivered = (unsigned long long)warp_sum((double)delivered);
+    if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
+  }
+  stp_range(P, k, mark, hi, part, nparts);
+  ext_events(P, k, pout, part * blockDim.x + threadIdx.x, gthreads);
+}
+
+/* End of a run in the pipelined schedule: p0..p6 of the spikes of the last step, so that the synaptic state read back
+ * (and the amplitudes the next run delivers) are complete; the next pass finds nothing below the mark left to do. */
+__global__ void __launch_bounds__(STP_BLOCK) k_stp_flush(const __grid_constant__ Params P) {
+  stp_range(P, -1, *P.stp_mark, *P.head, blockIdx.x, gridDim.x);
+}
+__global__ void k_set_mark(const __grid_constant__ Params P) { *P.stp_mark = *P.head; }
 
 /*
  * Spike delivery.  Order-7 pathways (`g_X_post += ...` after `delay = dtax`, codes/CortexNetwork.py:367-372,463-468) for
@@ -632,6 +885,7 @@ template <bool LONG>
 __device__ __forceinline__ void spike_new_phase(const Params& P, const long long k) {
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
+  long long* const pout = pend_of_slot(P, k);
   const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];
   const unsigned long long hi = *P.head;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[k % P.W] = hi;
@@ -651,19 +905,19 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
       P.hot[r].amp = amp;
       if (sh.delay == 0) {
         ++delivered0;
-        if (amp != 0.0) add_increment(P, sh.chan, sh.tgt, amp);
+        if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
       }
     }
     if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
     __syncthreads();                                           /* every thread has read last_spike[j]; the row is rewritten */
-    if (threadIdx.x == 0 && P.has_out[j]) P.last_spike[j] = t;   /* p5 */
+    if (threadIdx.x == 0 && (P.has_out[j] & 1)) P.last_spike[j] = t;   /* p5 */
     if (LONG) {
       if (threadIdx.x < 32) {
         int* hist = P.spk_hist + (size_t)j * P.hist_depth;
         const int maxd = P.row_maxd[j];
         for (int q = 0; q < P.hist_depth; ++q) {
           const int age = (int)(k - (long long)hist[q]);
-          if (age > 0 && age <= maxd) delivered0 += deliver_row_due(P, j, age, lane);
+          if (age > 0 && age <= maxd) delivered0 += deliver_row_due(P, pout, j, age, lane);
         }
         __syncwarp();
         if (lane == 0) {
@@ -695,6 +949,7 @@ enum { DELIVER_FUSED = 1, DELIVER_MAIN = 2 };
 template <int MODE>
 __device__ __forceinline__ void deliver_phase(const Params& P, const long long k) {
   const unsigned lane = threadIdx.x & 31;
+  long long* const pout = pend_of_slot(P, k);
   const unsigned long long lo = P.step_end[(k + 1) % P.W];             /* head at the end of step k - max_delay - 1 */
   const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];   /* first spike of this step */
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
@@ -706,23 +961,27 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
     const int age = (int)(k - (long long)P.spk_step[pos]);
     if (age > (int)P.row_maxd[j]) continue;                             /* nothing of this neuron can be due any more */
     if (MODE == DELIVER_MAIN && P.spk_last[j] == (int)k) continue;      /* spiked again now: k_spike_new<true> */
-    delivered += deliver_row_due(P, j, age, lane);
+    delivered += deliver_row_due(P, pout, j, age, lane);
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
   if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
 
-  /* SpikeGeneratorGroup events of this step: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
+  ext_events(P, k, pout, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+/* SpikeGeneratorGroup events of step k: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
+__device__ __forceinline__ void ext_events(const Params& P, const long long k, long long* const pout, const unsigned gtid, const unsigned gthreads) {
   if (P.ext_ptr && k >= P.ext_first && k <= P.ext_last) {
     const int e0 = P.ext_ptr[k - P.ext_first], e1 = P.ext_ptr[k - P.ext_first + 1];
-    for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+    for (int e = e0 + (int)gtid; e < e1; e += (int)gthreads) {
       const double failure = hhd_philox_u01(P.seed, (unsigned long long)P.ext_id[e], (unsigned long long)k, 1) < P.ext_pfail[e] ? 1.0 : 0.0;
       const unsigned char mask = P.ext_mask[e];
       const double g = P.ext_gmax[e] * (1.0 - failure);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        if (mask & (1 << c)) add_increment(P, c, P.ext_tgt[e], g * P.cc.gsyn[c]);
+        if (mask & (1 << c)) add_increment(P, pout, c, P.ext_tgt[e], g * P.cc.gsyn[c]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && e1 > e0) atomicAdd(&P.counters[CNT_EXT], (unsigned long long)(e1 - e0));
+    if (gtid == 0 && e1 > e0) atomicAdd(&P.counters[CNT_EXT], (unsigned long long)(e1 - e0));
   }
 }
 
@@ -758,7 +1017,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
   __syncthreads();
 }
 
-template <int METHOD>
+template <int METHOD, bool TIMED = false>
 __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_grid(const __grid_constant__ Params P, const int n_steps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ NeuronShared sh;
@@ -769,7 +1028,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
   unsigned long long arrived = *P.grid_bar;      /* a multiple of gridDim.x: every earlier launch completed its barriers */
   for (int s = 0; s < n_steps; ++s) {
     const long long k = k0 + s;
-    neuron_phase<METHOD, true>(P, k, st, sh, bar_parity);
+    neuron_phase<METHOD, true, TIMED, false>(P, k, st, sh, bar_parity);
     arrived += gridDim.x;
     grid_barrier(P.grid_bar, arrived);
     spike_new_phase<false>(P, k);
@@ -777,7 +1036,7 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     arrived += gridDim.x;
     grid_barrier(P.grid_bar, arrived);
   }
-  neuron_phase<METHOD, false>(P, k0 + n_steps, st, sh, bar_parity);
+  neuron_phase<METHOD, false, TIMED, false>(P, k0 + n_steps, st, sh, bar_parity);
 }
 
 
@@ -848,7 +1107,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
     p = load_par(P, i);
     ls = P.last_spike[P.off + i];
     meta = P.meta[i];
-    has_out = P.has_out[P.off + i] != 0;
+    has_out = (P.has_out[P.off + i] & 1) != 0;
   }
   unsigned long long n_events = 0, n_deliv = 0, n_ext = 0;
   unsigned n_spk = 0, n_wc = 0, n_bad = 0;
@@ -1139,9 +1398,17 @@ struct hhd_engine {
   bool record_spikes = true;
   std::vector<int> rec_neuron;
   std::vector<long long> rec_step;
+  size_t rec_sorted = 0;            /* rec_*[0, rec_sorted) are in (step, neuron) order */
+  cudaStream_t stream_copy = nullptr;
+  cudaEvent_t ev_seg[2] = {nullptr, nullptr};
+  unsigned long long* pin_head = nullptr;   /* [2] pinned */
+  int *pin_nb = nullptr, *pin_sb = nullptr; /* pinned staging of one segment's ring entries */
+  size_t pin_cap = 0;
+  unsigned long long drained_prev = 0;
   cudaGraphExec_t graph_exec = nullptr;
   hhd_counters cnt;
   int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
+  bool pipelined = false;
 #ifdef HHD_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -1228,6 +1495,10 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   h->record_spikes = cfg->record_spikes != 0;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, HHD_E_CUDA, "cudaStreamCreate failed"); }
   cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_seg[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_seg[1], cudaEventDisableTiming);
+  cudaMallocHost(&h->pin_head, 16);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -1246,7 +1517,13 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (!rc) rc = dev_alloc(h, &ho, h->NG);
   P.has_out = ho;
   P.n_pad = (long long)n_pad;
-  if (!rc) rc = dev_alloc(h, &P.pend, (size_t)3 * n_pad);
+  if (!rc) rc = dev_alloc(h, &P.pend, (size_t)6 * n_pad);
+  if (!rc) rc = dev_alloc(h, &P.prev_spike, h->NG);
+  if (!rc) rc = dev_alloc(h, &P.stp_mark, 1);
+  if (!rc) rc = dev_alloc(h, &P.pass_done, 1);
+  if (!rc) rc = dev_alloc(h, &P.tile_ctr, 1);
+  if (!rc) rc = dev_alloc(h, &P.zcount, 1);
+  if (!rc) rc = dev_alloc(h, &P.zlist, h->N);
   long long* rp = nullptr;
   if (!rc) rc = dev_alloc(h, &rp, (size_t)h->NG + 1);
   P.row_ptr = rp;
@@ -1280,6 +1557,11 @@ extern "C" void hhd_destroy(hhd_handle h) {
 #endif
   for (void* p : h->allocs) cudaFree(p);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
+  for (int q = 0; q < 2; ++q) if (h->ev_seg[q]) cudaEventDestroy(h->ev_seg[q]);
+  if (h->pin_head) cudaFreeHost(h->pin_head);
+  if (h->pin_nb) cudaFreeHost(h->pin_nb);
+  if (h->pin_sb) cudaFreeHost(h->pin_sb);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1438,6 +1720,30 @@ __global__ void k_syn_buckets(int NG, const long long* row_ptr, const SynHot* ho
   if (b == 0) row_maxd[j] = r1 > r0 ? hot[r1 - 1].delay : 0;      /* rows are sorted by delay */
 }
 
+/* has_out bit 1: the row starts with zero-delay synapses (rows are sorted by delay) */
+__global__ void k_mark_zero_delay(int NG, const long long* row_ptr, const SynHot* hot, unsigned char* has_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= NG) return;
+  const long long r0 = row_ptr[j], r1 = row_ptr[j + 1];
+  const unsigned char z = (r1 > r0 && hot[r0].delay == 0) ? 2 : 0;
+  has_out[j] = (unsigned char)((has_out[j] & 1) | z);
+}
+
+/* row_doff[j][d] = offset inside row j of the first synapse whose delay is >= d, d = 0 .. max_delay + 1; also the longest row */
+__global__ void k_syn_doff(int NG, const long long* row_ptr, const SynHot* hot, int stride, unsigned short* row_doff, int* max_row) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)NG * stride) return;
+  const int j = (int)(q / stride), want = (int)(q % stride);
+  const long long r0 = row_ptr[j], r1 = row_ptr[j + 1];
+  long long lo = r0, hi = r1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((int)hot[mid].delay < want) lo = mid + 1; else hi = mid;
+  }
+  row_doff[q] = (unsigned short)min(lo - r0, 65535ll);
+  if (want == 0) atomicMax(max_row, (int)min(r1 - r0, (long long)INT_MAX));
+}
+
 static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
                                const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
                                const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
@@ -1501,6 +1807,30 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     P.row_bkt = bkt;
+  }
+  P.row_doff = nullptr;
+  if (maxd < P.refr_steps && HHD_NEURON_PREFETCH == 2) {     /* what the pipelined schedule needs (finalize_setup decides) */
+    unsigned short* doff = nullptr;
+    int* dmax_row = nullptr;
+    const int stride = maxd + 2;
+    rc = dev_alloc(h, &doff, (size_t)h->NG * stride, false);
+    if (!rc) rc = dev_alloc(h, &dmax_row, 1, true);
+    if (rc) return rc;
+    const long long nq = (long long)h->NG * stride;
+    k_syn_doff<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, stride, doff, dmax_row);
+    int max_row = 0;
+    CU(cudaMemcpyAsync(&max_row, dmax_row, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    dev_free(h, dmax_row);
+    if (max_row < 65536) {
+      P.row_doff = doff;
+      P.doff_stride = stride;
+      /* an STP task is one block of a spiking neuron's row: as many tasks per spike as 1.25 mean rows need */
+      const double mean_row = (double)nsyn / std::max(1, h->NG);
+      P.stp_chunks = std::max(1, (int)std::ceil(1.25 * mean_row / NEURON_BLOCK));
+    } else {
+      dev_free(h, doff);
+    }
   }
   dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, vals2); dev_free(h, derr); dev_free(h, dmaxd); dev_free(h, tmp);
   P.max_delay = maxd;
@@ -1721,7 +2051,7 @@ extern "C" int hhd_read_monitor_dev(hhd_handle h, int32_t mon_id, const double**
 extern "C" int hhd_clear_monitor(hhd_handle h, int32_t mon_id) {
   if (!h || mon_id < -1 || mon_id >= (int)h->mons.size()) return fail(h, HHD_E_ARG, "bad monitor id");
   cudaSetDevice(h->cfg.device);
-  if (mon_id == -1) { h->rec_neuron.clear(); h->rec_step.clear(); return HHD_OK; }
+  if (mon_id == -1) { h->rec_neuron.clear(); h->rec_step.clear(); h->rec_sorted = 0; return HHD_OK; }
   Monitor& m = h->mons[mon_id];
   if (m.d_buf && m.n_samples) CU(cudaMemsetAsync(m.d_buf, 0, (size_t)(m.n_samples * m.width) * 8, h->stream));
   m.n_samples = 0;
@@ -1730,6 +2060,22 @@ extern "C" int hhd_clear_monitor(hhd_handle h, int32_t mon_id) {
 }
 
 /* ---- run --------------------------------------------------------------------------------------------------------- */
+/* The TimedArray and pipelined variants are separate instantiations: no cost when unused. */
+template <int M, bool STEP>
+static const void* neuron_fn(bool timed, bool pipe) {
+  if (timed) return pipe ? (const void*)k_neuron<M, STEP, true, STEP> : (const void*)k_neuron<M, STEP, true, false>;
+  return pipe ? (const void*)k_neuron<M, STEP, false, STEP> : (const void*)k_neuron<M, STEP, false, false>;
+}
+template <bool STEP>
+static const void* neuron_fn_of(int method, bool timed, bool pipe) {
+  switch (method) {
+    case HHD_EULER: return neuron_fn<0, STEP>(timed, pipe);
+    case HHD_RK2: return neuron_fn<1, STEP>(timed, pipe);
+    case HHD_RK4: return neuron_fn<2, STEP>(timed, pipe);
+    default: return neuron_fn<3, STEP>(timed, pipe);
+  }
+}
+
 static unsigned long long next_pow2(unsigned long long v) { unsigned long long p = 1; while (p < v) p <<= 1; return p; }
 
 static int finalize_setup(hhd_handle h) {
@@ -1749,7 +2095,7 @@ static int finalize_setup(hhd_handle h) {
    * the delivery window (max_delay) at most NG * per_neuron entries are live. */
   h->seg_steps = 2000;
   const long long refr = std::max(P.refr_steps, 1);
-  const long long per_neuron = (h->seg_steps + P.max_delay + 1 + refr - 1) / refr + 2;
+  const long long per_neuron = (2 * h->seg_steps + P.max_delay + 1 + refr - 1) / refr + 2;   /* two segments: see segment_collect */
   h->ring_cap = next_pow2((unsigned long long)h->NG * (unsigned long long)per_neuron);
   if (h->ring_cap > (1ull << 31)) return fail(h, HHD_E_NOMEM, "spike ring too large");
   {
@@ -1780,18 +2126,18 @@ static int finalize_setup(hhd_handle h) {
   }
   {
     /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than tiles */
-    int per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const void* fn[8] = {(const void*)k_neuron<0, true>, (const void*)k_neuron<1, true>, (const void*)k_neuron<2, true>,
-                         (const void*)k_neuron<3, true>, (const void*)k_neuron<0, false>, (const void*)k_neuron<1, false>,
-                         (const void*)k_neuron<2, false>, (const void*)k_neuron<3, false>};
-    for (int q = 0; q < 8; ++q) {
-      CU(cudaFuncSetAttribute(fn[q], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[q], fn[q], NEURON_BLOCK, NEURON_SMEM));
+    int occ = 1 << 30;
+    for (int v = 0; v < 8; ++v) {           /* every variant of this method may be launched: opt in to the shared memory */
+      const bool timed = v & 1, pipe = v & 2, step = v & 4;
+      const void* fn = step ? neuron_fn_of<true>(h->cfg.method, timed, pipe) : neuron_fn_of<false>(h->cfg.method, timed, pipe);
+      CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
+      int q = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, NEURON_BLOCK, NEURON_SMEM));
+      if (timed == (P.iac_table != nullptr)) occ = std::min(occ, q);
     }
-    const int m = h->cfg.method;
     const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
     const char* env = getenv("HHD_NEURON_CTAS_PER_SM");
-    int cps = std::max(1, per_sm[m]);
+    int cps = std::max(1, occ);
     if (env && atoi(env) > 0) cps = std::min(cps, atoi(env));
     h->neuron_grid = std::max(1, std::min(tiles, h->sm_count * cps));
     if (!HHD_NEURON_PREFETCH && !getenv("HHD_NEURON_PERSISTENT")) h->neuron_grid = tiles;
@@ -1801,6 +2147,8 @@ static int finalize_setup(hhd_handle h) {
   if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
   h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
   h->kernels_per_step = 3;
+  /* pipelined schedule: graph plan, single rank, no neuron with a new spike and an undelivered older one */
+  h->pipelined = h->fused && h->cfg.n_ranks == 1 && P.row_doff && !getenv("HHD_NO_PIPELINE");
   h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
@@ -1828,10 +2176,12 @@ static int finalize_setup(hhd_handle h) {
     {
       /* whole-run cooperative plan: needs every CTA of the state-update grid resident at once (it is sized that way)
        * and smem opt-in for k_grid */
-      const void* gfn[4] = {(const void*)k_grid<0>, (const void*)k_grid<1>, (const void*)k_grid<2>, (const void*)k_grid<3>};
+      const void* gfn[8] = {(const void*)k_grid<0>, (const void*)k_grid<1>, (const void*)k_grid<2>, (const void*)k_grid<3>,
+                            (const void*)k_grid<0, true>, (const void*)k_grid<1, true>, (const void*)k_grid<2, true>, (const void*)k_grid<3, true>};
+      const int gm = h->cfg.method + (P.iac_table ? 4 : 0);
       int per_sm = 0;
-      CU(cudaFuncSetAttribute(gfn[h->cfg.method], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfn[h->cfg.method], NEURON_BLOCK, NEURON_SMEM));
+      CU(cudaFuncSetAttribute(gfn[gm], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfn[gm], NEURON_BLOCK, NEURON_SMEM));
       const bool gcan = HHD_NEURON_PREFETCH >= 2 && h->cfg.n_ranks == 1 && h->fused && per_sm > 0 && h->NG == h->N;
       if (h->cfg.plan == HHD_PLAN_PERSISTENT && !gcan)
         return fail(h, HHD_E_ARG, "HHD_PLAN_PERSISTENT needs max delay < refractory period and a single rank");
@@ -1858,6 +2208,17 @@ static int finalize_setup(hhd_handle h) {
       }
     }
   }
+  if (getenv("HHD_DEBUG_TIMES")) { rc = dev_alloc(h, &P.dbg_times, (size_t)16 * 4096, true); if (rc) return rc; }
+  if (h->resident || h->gridplan) h->pipelined = false;
+  if (h->pipelined) {
+    k_mark_zero_delay<<<(h->NG + 255) / 256, 256, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, const_cast<unsigned char*>(P.has_out));
+    CU(cudaGetLastError());
+  }
+  if (h->pipelined) {
+    h->kernels_per_step = 1;
+    const char* env = getenv("HHD_AHEAD_CTAS");
+    P.ahead_ctas = std::max(1, std::min(h->neuron_grid, env && atoi(env) > 0 ? atoi(env) : h->sm_count));
+  }
   h->started = true;
   return 0;
 }
@@ -1874,12 +2235,13 @@ static int launch_grid(hhd_handle h, int n_steps) {
   at[0].val.cooperative = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
+  const bool timed = h->P.iac_table != nullptr;
   cudaError_t e;
   switch (h->cfg.method) {
-    case HHD_EULER: e = cudaLaunchKernelEx(&lc, k_grid<0>, h->P, n_steps); break;
-    case HHD_RK2: e = cudaLaunchKernelEx(&lc, k_grid<1>, h->P, n_steps); break;
-    case HHD_RK4: e = cudaLaunchKernelEx(&lc, k_grid<2>, h->P, n_steps); break;
-    default: e = cudaLaunchKernelEx(&lc, k_grid<3>, h->P, n_steps); break;
+    case HHD_EULER: e = timed ? cudaLaunchKernelEx(&lc, k_grid<0, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<0, false>, h->P, n_steps); break;
+    case HHD_RK2: e = timed ? cudaLaunchKernelEx(&lc, k_grid<1, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<1, false>, h->P, n_steps); break;
+    case HHD_RK4: e = timed ? cudaLaunchKernelEx(&lc, k_grid<2, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<2, false>, h->P, n_steps); break;
+    default: e = timed ? cudaLaunchKernelEx(&lc, k_grid<3, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<3, false>, h->P, n_steps); break;
   }
   if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
   k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, n_steps);
@@ -1932,16 +2294,16 @@ static void launch_pdl(hhd_handle h, K kernel, int grid, int block, size_t smem,
 
 template <bool STEP>
 static void launch_neuron(hhd_handle h, int offset) {
-  const int grid = h->neuron_grid;
-  switch (h->cfg.method) {
-    case HHD_EULER: launch_pdl(h, k_neuron<0, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
-    case HHD_RK2: launch_pdl(h, k_neuron<1, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
-    case HHD_RK4: launch_pdl(h, k_neuron<2, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
-    default: launch_pdl(h, k_neuron<3, STEP>, grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset); break;
-  }
+  typedef void (*kern_t)(const Params, const int);
+  const kern_t fn = (kern_t)neuron_fn_of<STEP>(h->cfg.method, h->P.iac_table != nullptr, STEP && h->pipelined);
+  launch_pdl(h, fn, h->neuron_grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset);
 }
 
 static void launch_step(hhd_handle h, int offset) {
+  if (h->pipelined) {            /* one launch per step: state update + the synaptic work that is one step ahead */
+    launch_neuron<true>(h, offset);
+    return;
+  }
   launch_neuron<true>(h, offset);
 #ifdef HHD_WITH_NCCL
   if (h->cfg.n_ranks > 1) {   /* the one real exchange of the path: this step's spike indices, every rank to every rank */
@@ -1982,34 +2344,86 @@ static int build_graph(hhd_handle h) {
   return 0;
 }
 
-/* Copy the spikes appended since the last drain out of the ring (local neurons only when partitioned). */
-static int drain_spikes(hhd_handle h) {
-  unsigned long long head = 0;
-  CU(cudaMemcpyAsync(&head, h->P.head, 8, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+/*
+ * Spike recording.  A run is cut into segments of seg_steps; at the end of a segment the ring head is copied to pinned
+ * memory behind an event (segment_mark) and the NEXT segment is enqueued before the host looks at the previous one
+ * (segment_collect): the host copies that segment's ring entries on a second stream and files them while the device
+ * computes, so the device never waits for the host (it used to: ~13 ms of copying and sorting per 2000 steps, 10 % of a
+ * 1M-neuron run).  The ring therefore holds two segments plus the delivery window.  Entries are filed in ring order
+ * (step, arrival); SpikeMonitor order (step, neuron) is established when the spikes are read (finish_spike_order).
+ */
+static int segment_mark(hhd_handle h, int slot) {
+  CU(cudaMemcpyAsync(&h->pin_head[slot], h->P.head, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->ev_seg[slot], h->stream));
+  return 0;
+}
+
+static int segment_collect(hhd_handle h, int slot) {
+  CU(cudaEventSynchronize(h->ev_seg[slot]));
+  const unsigned long long head = h->pin_head[slot];
   const unsigned long long n = head - h->drained;
-  if (n > h->ring_cap) return fail(h, HHD_E_CAPACITY, "spike ring overflow (%llu spikes in one segment, capacity %llu)", n, h->ring_cap);
+  /* while the host read [drained_prev, drained) the device appended up to head */
+  if (head - h->drained_prev > h->ring_cap)
+    return fail(h, HHD_E_CAPACITY, "spike ring overflow (%llu spikes in two segments, capacity %llu)", head - h->drained_prev, h->ring_cap);
   if (h->record_spikes && n) {
-    std::vector<int> nb((size_t)n), sb((size_t)n);
+    if (h->pin_cap < n) {
+      if (h->pin_nb) cudaFreeHost(h->pin_nb);
+      if (h->pin_sb) cudaFreeHost(h->pin_sb);
+      h->pin_nb = h->pin_sb = nullptr;
+      h->pin_cap = (size_t)n + (size_t)n / 2 + 1024;
+      CU(cudaMallocHost(&h->pin_nb, h->pin_cap * 4));
+      CU(cudaMallocHost(&h->pin_sb, h->pin_cap * 4));
+    }
     const unsigned long long p0 = h->drained & (h->ring_cap - 1);
     const unsigned long long first = std::min(n, h->ring_cap - p0);
-    CU(cudaMemcpyAsync(nb.data(), h->P.spk_neuron + p0, (size_t)first * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(sb.data(), h->P.spk_step + p0, (size_t)first * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->pin_nb, h->P.spk_neuron + p0, (size_t)first * 4, cudaMemcpyDeviceToHost, h->stream_copy));
+    CU(cudaMemcpyAsync(h->pin_sb, h->P.spk_step + p0, (size_t)first * 4, cudaMemcpyDeviceToHost, h->stream_copy));
     if (first < n) {
-      CU(cudaMemcpyAsync(nb.data() + first, h->P.spk_neuron, (size_t)(n - first) * 4, cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaMemcpyAsync(sb.data() + first, h->P.spk_step, (size_t)(n - first) * 4, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(h->pin_nb + first, h->P.spk_neuron, (size_t)(n - first) * 4, cudaMemcpyDeviceToHost, h->stream_copy));
+      CU(cudaMemcpyAsync(h->pin_sb + first, h->P.spk_step, (size_t)(n - first) * 4, cudaMemcpyDeviceToHost, h->stream_copy));
     }
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->stream_copy));
     const int lo = h->cfg.global_offset, hi = lo + h->N;
-    /* ring order is (step, arrival); SpikeMonitor order is (step, neuron): sort each step's run */
-    std::vector<std::pair<long long, int>> tmp;
-    tmp.reserve((size_t)n);
-    for (size_t q = 0; q < (size_t)n; ++q) if (nb[q] >= lo && nb[q] < hi) tmp.emplace_back((long long)sb[q], nb[q]);
-    std::sort(tmp.begin(), tmp.end());
-    for (auto& pr : tmp) { h->rec_step.push_back(pr.first); h->rec_neuron.push_back(pr.second); }
+    const int* nb = h->pin_nb;
+    const int* sb = h->pin_sb;
+    for (size_t q = 0; q < (size_t)n; ++q)
+      if (nb[q] >= lo && nb[q] < hi) { h->rec_step.push_back((long long)sb[q]); h->rec_neuron.push_back(nb[q]); }
   }
+  h->drained_prev = h->drained;
   h->drained = head;
   return 0;
+}
+
+/* End of a piece of work whose spikes are wanted now. */
+static int drain_spikes(hhd_handle h) {
+  int rc = segment_mark(h, 0);
+  if (!rc) rc = segment_collect(h, 0);
+  return rc;
+}
+
+/* (step, neuron) order for everything filed since the last call.  Segments are filed in time order, and inside one the
+ * ring is ordered by step unless a plan appends per instance: sort each step's run, or the whole tail if it is not. */
+static void finish_spike_order(hhd_handle h) {
+  const size_t n = h->rec_neuron.size();
+  size_t a = h->rec_sorted;
+  if (a >= n) { h->rec_sorted = n; return; }
+  bool monotone = true;
+  for (size_t q = a + 1; q < n && monotone; ++q) monotone = h->rec_step[q] >= h->rec_step[q - 1];
+  if (monotone) {
+    while (a < n) {
+      size_t b = a + 1;
+      while (b < n && h->rec_step[b] == h->rec_step[a]) ++b;
+      std::sort(h->rec_neuron.begin() + a, h->rec_neuron.begin() + b);
+      a = b;
+    }
+  } else {
+    std::vector<std::pair<long long, int>> tmp;
+    tmp.reserve(n - a);
+    for (size_t q = a; q < n; ++q) tmp.emplace_back(h->rec_step[q], h->rec_neuron[q]);
+    std::sort(tmp.begin(), tmp.end());
+    for (size_t q = a; q < n; ++q) { h->rec_step[q] = tmp[q - a].first; h->rec_neuron[q] = tmp[q - a].second; }
+  }
+  h->rec_sorted = n;
 }
 
 static int grow_monitors(hhd_handle h, long long n_steps) {
@@ -2065,13 +2479,21 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
 
   CU(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
+  int pending = -1, slot = 0;          /* segment whose spikes the host has not filed yet */
+  auto segment_done = [&]() -> int {   /* mark this segment, then file the previous one while this one runs */
+    int r = segment_mark(h, slot);
+    if (!r && pending >= 0) r = segment_collect(h, pending);
+    pending = slot;
+    slot ^= 1;
+    return r;
+  };
   while (done < n_steps) {
     const long long seg = std::min<long long>(h->seg_steps, n_steps - done);
     if (h->resident || h->gridplan) {
       if ((rc = h->resident ? launch_resident(h, (int)seg) : launch_grid(h, (int)seg))) return rc;
       done += seg;
       CU(cudaGetLastError());
-      if ((rc = drain_spikes(h))) return rc;
+      if ((rc = segment_done())) return rc;
       continue;
     }
     long long s = 0;
@@ -2084,12 +2506,37 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
     for (int q = 0; q < rem; ++q) launch_step(h, q);
     if (rem) { k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, rem); h->cnt.kernel_launches += h->kernels_per_step * rem + 1; }
     done += seg;
-    if (done == n_steps) { launch_neuron<false>(h, 0); h->cnt.kernel_launches += 1; }
+    if (done == n_steps) {
+      if (h->pipelined) {          /* p0..p6 of the last step's spikes */
+        k_stp_flush<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P);
+        k_set_mark<<<1, 1, 0, h->stream>>>(h->P);
+        h->cnt.kernel_launches += 2;
+      }
+      launch_neuron<false>(h, 0);
+      h->cnt.kernel_launches += 1;
+    }
     CU(cudaGetLastError());
-    if ((rc = drain_spikes(h))) return rc;
+    if ((rc = segment_done())) return rc;
   }
   CU(cudaEventRecord(h->ev1, h->stream));
+  if (pending >= 0 && (rc = segment_collect(h, pending))) return rc;
   CU(cudaStreamSynchronize(h->stream));
+  if (h->P.dbg_times) {
+    std::vector<unsigned long long> tt((size_t)16 * 4096);
+    CU(cudaMemcpy(tt.data(), h->P.dbg_times, tt.size() * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("HHD_DEBUG_TIMES"), "w")) {
+      for (int half = 0; half < 2; ++half)
+        for (int b = 0; b < h->neuron_grid && b < 4096; ++b) {
+          const size_t o = ((size_t)half * 4096 + b) * 4;
+          fprintf(f, "%d %llu %llu %llu %llu\n", b, tt[o], tt[o + 1], tt[o + 2], tt[o + 3]);
+        }
+      fclose(f);
+    }
+    if (FILE* f = fopen((std::string(getenv("HHD_DEBUG_TIMES")) + ".passes").c_str(), "w")) {
+      for (int q = 0; q < 4096; ++q) fprintf(f, "%d %llu %llu\n", q, tt[8 * 4096 + 2 * q], tt[8 * 4096 + 2 * q + 1]);
+      fclose(f);
+    }
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->cnt.run_ms_device += ms;
@@ -2144,6 +2591,11 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
   for (int64_t s = 0; s < n_steps; ++s) {
     launch_neuron<true>(h, (int)s);
     CU(cudaEventRecord(ev[3 * s + 1], h->stream));
+    if (h->pipelined) {            /* the step is that one launch */
+      CU(cudaEventRecord(ev[3 * s + 2], h->stream));
+      CU(cudaEventRecord(ev[3 * s + 3], h->stream));
+      continue;
+    }
 #ifdef HHD_WITH_NCCL
     if (h->cfg.n_ranks > 1) {   /* the exchange is accounted to slot 1 */
       ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
@@ -2158,6 +2610,10 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
     CU(cudaEventRecord(ev[3 * s + 3], h->stream));
   }
   k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, (int)n_steps);
+  if (h->pipelined) {
+    k_stp_flush<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P);
+    k_set_mark<<<1, 1, 0, h->stream>>>(h->P);
+  }
   launch_neuron<false>(h, 0);
   h->cnt.kernel_launches += h->kernels_per_step * n_steps + 2;
   CU(cudaGetLastError());
@@ -2187,6 +2643,7 @@ extern "C" int hhd_spike_count(hhd_handle h, int64_t* n) {
 
 extern "C" int hhd_read_spikes(hhd_handle h, int32_t* neuron, int64_t* step, int64_t cap, int64_t* n_out) {
   if (!h) return HHD_E_ARG;
+  finish_spike_order(h);
   const int64_t n = (int64_t)h->rec_neuron.size();
   if (n > cap) return fail(h, HHD_E_CAPACITY, "output buffer too small: need %lld", (long long)n);
   if (n) { memcpy(neuron, h->rec_neuron.data(), (size_t)n * 4); memcpy(step, h->rec_step.data(), (size_t)n * 8); }
