@@ -112,7 +112,7 @@ struct Params {
   const unsigned short* row_doff; /* [NG][max_delay + 2] offset inside the row of the first synapse with delay >= d (pipelined
                                      schedule: one thread per active spike reads exactly its due synapses); NULL = not built */
   unsigned long long* dbg_times;   /* HHD_DEBUG_TIMES: [grid][4] globaltimer at start / after ahead_phase / end of the tiles / end */
-  int doff_stride, stp_chunks, ahead_ctas;    /* max_delay + 2; ceil(longest row / NEURON_BLOCK) */
+  int doff_stride, stp_chunks, ahead_ctas, dyn_tiles;    /* max_delay + 2; ceil(longest row / NEURON_BLOCK) */
   long long syn_id_base;
   /* spike ring */
   int* spk_neuron;             /* global ids */
@@ -351,26 +351,28 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     if (STEP && P.dbg_times && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.dbg_times[((size_t)(k & 1) * 4096 + blockIdx.x) * 4 + q] = g;
       if (blockIdx.x == 0 && q == 0) P.dbg_times[8 * 4096 + (k & 4095) * 2] = g; }
   };
-  constexpr bool DYN = PIPE && STEP && HHD_NEURON_PREFETCH == 2;
+  const bool DYN = PIPE && STEP && HHD_NEURON_PREFETCH == 2 && P.dyn_tiles > 0;
   stamp(0);
-  /* First two tiles.  Static (b, b + grid) — except in the pipelined schedule: there the first ahead_ctas CTAs of the grid
-   * (one per SM by default) first do the synaptic work of slot k (its latency hides behind the arithmetic of the SM's
-   * other CTAs) and then draw ALL their tiles from the counter, like everybody draws every further tile: whoever is done
-   * earlier integrates more. */
-  int tile = blockIdx.x, tile_nxt = tile + (int)gridDim.x, dyn_base = 2 * (int)gridDim.x;
-  if (DYN) {
-    const int A = P.ahead_ctas, rest = (int)gridDim.x - A;
-    dyn_base = 2 * rest;
-    if ((int)blockIdx.x < A) {
-      ahead_phase(P, k, blockIdx.x, (unsigned)A);
-      if (tid < 2) sh.tile_fetch[tid] = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
-      __syncthreads();
-      tile = min(sh.tile_fetch[0], sh.tile_fetch[1]);
-      tile_nxt = max(sh.tile_fetch[0], sh.tile_fetch[1]);
-      __syncthreads();
-    } else {
-      tile = (int)blockIdx.x - A;
-      tile_nxt = tile + rest;
+  /* Tiles.  Static (b, b + grid, b + 2 grid, ...) — except in the pipelined schedule, where every CTA first does its share
+   * of the synaptic work of slot k (ahead_phase; it takes a different time in every CTA) and the LAST tiles of the pass
+   * (two per CTA on average) come from a counter instead: whoever is done earlier integrates more.  Only the last ones,
+   * because a drawn index costs the producer warp the round trip of the atomic (the compiler cannot keep its result in a
+   * register across the integration, so the warp waits for it at once): ~1 us per draw, three draws instead of thirteen. */
+  int tile = blockIdx.x, tile_nxt = tile + (int)gridDim.x, dyn_base = 0;
+  int n_static = 1 << 30;            /* iterations whose tile is b + it * grid */
+  if (PIPE && STEP) {
+    if ((int)blockIdx.x < P.ahead_ctas) ahead_phase(P, k, blockIdx.x, (unsigned)P.ahead_ctas);
+    if (DYN) {
+      n_static = max(0, ntiles / (int)gridDim.x - P.dyn_tiles);
+      if (n_static < 2) n_static = 0;
+      dyn_base = n_static * (int)gridDim.x;
+      if (n_static == 0) {           /* small network: every tile is drawn */
+        if (tid < 2) sh.tile_fetch[tid] = (int)atomicAdd(P.tile_ctr, 1u);
+        __syncthreads();
+        tile = min(sh.tile_fetch[0], sh.tile_fetch[1]);
+        tile_nxt = max(sh.tile_fetch[0], sh.tile_fetch[1]);
+        __syncthreads();
+      }
     }
   }
   stamp(1);
@@ -390,15 +392,8 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
 #endif
   /* PIPE: after its first two tiles a CTA draws its tiles from a counter (the synaptic share above takes a different
    * time in every CTA; whoever is done earlier integrates more) — otherwise tile, tile + grid, tile + 2 grid, ... */
-  /* The producer thread draws a tile index a whole iteration before it publishes it: the atomic's round trip must not
-   * stall warp 0 at the top of every iteration. */
-  int fetched = 0;
-  if (DYN && tid == 0) fetched = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
   for (int it = 0; tile < ntiles; ++it) {
-    if (DYN && tid == 0) {
-      sh.tile_fetch[it & 1] = fetched;
-      fetched = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
-    }
+    if (DYN && tid == 0 && it + 2 >= n_static) sh.tile_fetch[it & 1] = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
     const int i = tile * NEURON_BLOCK + tid;
     const bool live = i < P.N;
     double x[8];
@@ -455,7 +450,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
 #endif
 #if HHD_NEURON_PREFETCH == 2
     __syncthreads();   /* every thread holds its neuron of this tile in registers: stage s is free again */
-    const int tile_nn = DYN ? sh.tile_fetch[it & 1] : tile + 2 * (int)gridDim.x;
+    const int tile_nn = (DYN && it + 2 >= n_static) ? sh.tile_fetch[it & 1] : tile + 2 * (int)gridDim.x;
     issue(tile_nn, s);                 /* so the tile after next is requested NOW: two tiles in flight with two stages */
 
 #elif HHD_NEURON_PREFETCH == 3
@@ -750,51 +745,57 @@ __device__ __forceinline__ void spike_local(const Params& P, int j, long long k,
   atomicAdd(&P.del_slots[j & (CNT_SLOTS - 1)], n);
 }
 
-/* p0..p6 for the ring entries [lo, hi) (spikes whose rows were not processed yet).  A task is NEURON_BLOCK consecutive
- * synapses of one spike's row (stp_chunks tasks per spike); CTA `part` of `nparts` takes every nparts-th task.
- * slot >= 0: also deliver the synapses of those rows that are due in that slot.  Zero-delay synapses were handled by
- * spike_local at the spike's own step. */
+/* p0..p6 for ONE synapse of a spike of step ks (spike time ts, previous spike of the neuron `last`); slot >= 0: deliver
+ * it too if it is due in that slot.  Zero-delay synapses were handled by spike_local at the spike's own step. */
+__device__ __forceinline__ void stp_apply(const Params& P, const long long slot, long long* const pout, const long long r,
+                                          const SynHot& sh, SynStp sy, const long long ks, const double ts, const double last,
+                                          unsigned long long& delivered) {
+  if (sh.delay == 0) return;
+  const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, ts, last,
+                                    P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)ks);
+  P.stp[r].u = sy.u;
+  P.stp[r].R = sy.R;
+  P.hot[r].amp = amp;
+  if (slot >= 0 && (long long)sh.delay == slot - ks) {
+    ++delivered;
+    if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
+  }
+}
+
+/* p0..p6 for the ring entries [lo, hi) (spikes whose rows were not processed yet).  A task is one block of NEURON_BLOCK
+ * consecutive synapses of one spike's row, stp_chunks tasks per spike (rows longer than that wrap around; the chunk count
+ * follows the mean row); CTA `part` of `nparts` takes the tasks first_task, first_task + nparts, ... */
 __device__ __forceinline__ void stp_range(const Params& P, const long long slot, const unsigned long long lo,
-                                          const unsigned long long hi, const unsigned part, const unsigned nparts) {
+                                          const unsigned long long hi, const unsigned first_task, const unsigned nparts,
+                                          unsigned long long& delivered) {
   long long* const pout = pend_of_slot(P, slot);
-  unsigned long long delivered = 0;
   const unsigned chunks = (unsigned)P.stp_chunks;
   const unsigned ntasks = (unsigned)(hi - lo) * chunks;                 /* far below 2^32: one spike per neuron and step at most */
-  for (unsigned task = part; task < ntasks; task += nparts) {
-    const unsigned long long sp = lo + task / chunks;
+  for (unsigned task = first_task; task < ntasks; task += nparts) {
     const unsigned chunk = task % chunks;
-    const unsigned pos = (unsigned)sp & P.cap_mask;
+    const unsigned pos = (unsigned)(lo + task / chunks) & P.cap_mask;
     const int j = P.spk_neuron[pos];
     const long long ks = (long long)P.spk_step[pos];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
     if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
     const double ts = (double)ks * P.dt;
     const double last = P.prev_spike[j];
-    /* rows longer than stp_chunks blocks (rare: the chunk count follows the mean row) wrap around */
-    for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x) {
-      const SynHot sh = P.hot[r];
-      if (sh.delay == 0) continue;
-      SynStp sy = P.stp[r];
-      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, ts, last,
-                                        P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)ks);
-      P.stp[r].u = sy.u;
-      P.stp[r].R = sy.R;
-      P.hot[r].amp = amp;
-      if (slot >= 0 && (long long)sh.delay == slot - ks) {
-        ++delivered;
-        if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
-      }
-    }
+    for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x)
+      stp_apply(P, slot, pout, r, P.hot[r], P.stp[r], ks, ts, last, delivered);
   }
-  delivered = (unsigned long long)warp_sum((double)delivered);
-  if ((threadIdx.x & 31) == 0 && delivered) atomicAdd(&P.del_slots[(part * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], delivered);
 }
 
 __device__ __forceinline__ void ext_events(const Params& P, const long long k, long long* const pout, const unsigned gtid, const unsigned gthreads);
 
-/* This CTA's share of slot k in the pipelined schedule: p0..p6 of the spikes of step k-1 (and their delay-1 synapses),
- * the due synapses of every older active spike — ONE THREAD per active spike: the per-delay offsets of the row give it
- * exactly its due synapses, so the whole chain is three dependent loads — and the SpikeGeneratorGroup events of step k. */
+/* This CTA's share of slot k in the pipelined schedule:
+ *  - p0..p6 of the spikes of step k-1 (and the delivery of their delay-1 synapses): one task per CTA, usually;
+ *  - the due synapses of every older active spike: the active spikes are spread evenly over every warp of the share
+ *    (spw per warp); each lane looks up the due segment of ITS spike in the row's per-delay offsets, then the warp walks
+ *    the concatenation of its lanes' segments 32 synapses at a time (the segments are very uneven, 0..~100);
+ *  - the SpikeGeneratorGroup events of step k.
+ * Both chains are three dependent loads deep into 23 GB of synapse data (TLB misses included), and that latency is all
+ * this costs: the loads of the CTA's first STP task and of each warp's first group are issued level by level together,
+ * before anything is stored. */
 __device__ __forceinline__ void ahead_phase(const Params& P, const long long k, const unsigned part, const unsigned nparts) {
   const unsigned lane = threadIdx.x & 31;
   long long* const pout = pend_of_slot(P, k);
@@ -802,18 +803,57 @@ __device__ __forceinline__ void ahead_phase(const Params& P, const long long k, 
   const unsigned long long hi = P.step_end[((int)k + P.W - 1) % P.W];  /* head at the end of step k - 1 */
   const unsigned long long mark = *P.stp_mark;
   const unsigned gthreads = nparts * blockDim.x;
-  /* Deliveries.  The active spikes are spread evenly over every warp of the grid (spw per warp, from the far end of the
-   * grid so that the CTAs with an STP task come last); each lane looks up the due segment of ITS spike, then the warp
-   * walks the concatenation of its lanes' segments 32 synapses at a time — the segments are very uneven (0..~100). */
-  {
-    const unsigned nact = (unsigned)(mark - lo);
-    const unsigned warps = gthreads >> 5;
-    const unsigned spw = min(32u, (nact + warps - 1) / warps);
-    const unsigned wid = (nparts - 1 - part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    unsigned long long delivered = 0;
-    for (unsigned long long first = lo + (unsigned long long)wid * spw; first < mark && spw; first += (unsigned long long)warps * spw) {
-      long long ra = 0;
-      unsigned cnt = 0;
+  const unsigned chunks = (unsigned)P.stp_chunks;
+  const unsigned ntasks = (unsigned)(hi - mark) * chunks;
+  const unsigned nact = (unsigned)(mark - lo);
+  const unsigned warps = gthreads >> 5;
+  const unsigned spw = min(32u, (nact + warps - 1) / warps);
+  /* the warps are walked from the far end of the share for the deliveries and the CTAs from the near end for the STP
+   * tasks: nobody gets both unless there is more work than CTAs */
+  const unsigned wid = (nparts - 1 - part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned long long first0 = lo + (unsigned long long)wid * spw;
+
+  /* ---- level 1: ring entries ---- */
+  const bool stp0 = part < ntasks;
+  int sj = 0, dj = -1;
+  long long sks = 0;
+  int dage = 0;
+  if (stp0) {
+    const unsigned pos = (unsigned)(mark + part / chunks) & P.cap_mask;
+    sj = P.spk_neuron[pos];
+    sks = (long long)P.spk_step[pos];
+  }
+  if (spw && lane < spw && first0 + lane < mark) {
+    const unsigned pos = (unsigned)(first0 + lane) & P.cap_mask;
+    dj = P.spk_neuron[pos];
+    dage = (int)(k - (long long)P.spk_step[pos]);
+  }
+  /* ---- level 2: rows ---- */
+  long long sr0 = 0, sr1 = 0, dra = 0;
+  double slast = 0.0;
+  unsigned dcnt = 0;
+  if (stp0) { sr0 = P.row_ptr[sj]; sr1 = P.row_ptr[sj + 1]; slast = P.prev_spike[sj]; }
+  if (dj >= 0 && dage <= P.max_delay) {
+    const unsigned short* o = P.row_doff + (size_t)dj * P.doff_stride + dage;
+    const unsigned a0 = o[0], a1 = o[1];
+    dra = P.row_ptr[dj] + a0;
+    dcnt = a1 - a0;
+  }
+  /* ---- level 3: synapse records ---- */
+  const unsigned schunk = part % chunks;
+  const long long sr = sr0 + (long long)schunk * blockDim.x + threadIdx.x;
+  const bool sval = stp0 && sr < sr1;
+  SynHot ssh;
+  SynStp ssy;
+  if (sval) { ssh = P.hot[sr]; ssy = P.stp[sr]; }
+
+  unsigned long long delivered = 0;
+  for (unsigned long long first = first0; first < mark && spw; first += (unsigned long long)warps * spw) {
+    long long ra = dra;
+    unsigned cnt = dcnt;
+    if (first != first0) {               /* further groups of this warp (only when there are more than 32 spikes per warp) */
+      ra = 0;
+      cnt = 0;
       if (lane < spw && first + lane < mark) {
         const unsigned pos = (unsigned)(first + lane) & P.cap_mask;
         const int j = P.spk_neuron[pos];
@@ -825,16 +865,21 @@ __device__ __forceinline__ void ahead_phase(const Params& P, const long long k, 
           cnt = a1 - a0;
         }
       }
-      unsigned incl = cnt;                                   /* inclusive prefix sum of the segment lengths */
+    }
+    unsigned incl = cnt;                                   /* inclusive prefix sum of the segment lengths */
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += v;
-      }
-      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-      const unsigned excl = incl - cnt;
-      for (unsigned base = 0; base < total; base += 32) {
-        const unsigned idx = base + lane;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((int)lane >= d) incl += v;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned excl = incl - cnt;
+    for (unsigned base = 0; base < total; base += 64) {    /* two rounds of loads in flight */
+      SynHot q[2];
+      bool ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned idx = base + 32 * u + lane;
         /* owner = the last lane whose exclusive prefix is <= idx (binary search over the warp) */
         unsigned owner = 0;
 #pragma unroll
@@ -845,24 +890,40 @@ __device__ __forceinline__ void ahead_phase(const Params& P, const long long k, 
         }
         const long long ra_o = __shfl_sync(0xffffffffu, ra, owner);
         const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
-        if (idx < total) {
-          const SynHot q = P.hot[ra_o + (idx - ex_o)];
-          ++delivered;
-          if (q.amp != 0.0) add_increment(P, pout, q.chan, q.tgt, q.amp);
-        }
+        ok[u] = idx < total;
+        if (ok[u]) q[u] = P.hot[ra_o + (idx - ex_o)];
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (ok[u]) {
+          ++delivered;
+          if (q[u].amp != 0.0) add_increment(P, pout, q[u].chan, q[u].tgt, q[u].amp);
+        }
     }
-    delivered = (unsigned long long)warp_sum((double)delivered);
-    if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
   }
-  stp_range(P, k, mark, hi, part, nparts);
+  delivered = (unsigned long long)warp_sum((double)delivered);
+  if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
+
+  /* ---- p0..p6: the prefetched task, the rest of its row if it is longer than stp_chunks blocks, further tasks ---- */
+  unsigned long long sdel = 0;
+  if (stp0) {
+    const double ts = (double)sks * P.dt;
+    if (schunk == 0 && threadIdx.x == 0 && sr1 > sr0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(sr1 - sr0));
+    if (sval) stp_apply(P, k, pout, sr, ssh, ssy, sks, ts, slast, sdel);
+    for (long long r = sr + (long long)chunks * blockDim.x; r < sr1; r += (long long)chunks * blockDim.x)
+      stp_apply(P, k, pout, r, P.hot[r], P.stp[r], sks, ts, slast, sdel);
+    stp_range(P, k, mark, hi, part + nparts, nparts, sdel);
+  }
+  sdel = (unsigned long long)warp_sum((double)sdel);
+  if (lane == 0 && sdel) atomicAdd(&P.del_slots[(part * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], sdel);
   ext_events(P, k, pout, part * blockDim.x + threadIdx.x, gthreads);
 }
 
 /* End of a run in the pipelined schedule: p0..p6 of the spikes of the last step, so that the synaptic state read back
  * (and the amplitudes the next run delivers) are complete; the next pass finds nothing below the mark left to do. */
 __global__ void __launch_bounds__(STP_BLOCK) k_stp_flush(const __grid_constant__ Params P) {
-  stp_range(P, -1, *P.stp_mark, *P.head, blockIdx.x, gridDim.x);
+  unsigned long long none = 0;
+  stp_range(P, -1, *P.stp_mark, *P.head, blockIdx.x, gridDim.x, none);
 }
 __global__ void k_set_mark(const __grid_constant__ Params P) { *P.stp_mark = *P.head; }
 
@@ -2217,7 +2278,9 @@ static int finalize_setup(hhd_handle h) {
   if (h->pipelined) {
     h->kernels_per_step = 1;
     const char* env = getenv("HHD_AHEAD_CTAS");
-    P.ahead_ctas = std::max(1, std::min(h->neuron_grid, env && atoi(env) > 0 ? atoi(env) : h->sm_count));
+    /* dyn_tiles: static iterations given up for the drawn tail (0 = all static) */
+    P.dyn_tiles = getenv("HHD_DYN_TILES") ? atoi(getenv("HHD_DYN_TILES")) : 2;
+    P.ahead_ctas = std::max(1, std::min(h->neuron_grid, env && atoi(env) > 0 ? atoi(env) : h->neuron_grid));
   }
   h->started = true;
   return 0;
