@@ -62,7 +62,9 @@ typedef enum {
   HHD_PLAN_AUTO = 0,
   HHD_PLAN_GRAPH = 1,     /* 3 grid-wide kernels per step, captured in CUDA graphs (any N, HBM-bound regime) */
   HHD_PLAN_RESIDENT = 2,  /* persistent thread-block-cluster kernel, state in registers (N small, latency-bound regime) */
-  HHD_PLAN_PERSISTENT = 3 /* one cooperative launch per segment: the graph plan's phases separated by grid barriers */
+  HHD_PLAN_PERSISTENT = 3,/* one cooperative launch per segment: the graph plan's phases separated by grid barriers */
+  HHD_PLAN_PIPELINED = 4  /* one launch per step: the state update also does the synaptic work that is one step ahead (needs
+                             max delay < refractory period, a single rank); opt-in, AUTO never picks it */
 } hhd_plan;
 
 typedef struct {

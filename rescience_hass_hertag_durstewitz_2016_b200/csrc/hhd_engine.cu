@@ -61,8 +61,11 @@
 enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_N };
 #define CNT_SLOTS 256   /* the delivery counter is spread over 256 addresses: thousands of warps bump it every step, and
                            same-address atomics serialise in one L2 slice */
-enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2, FLAG_HAS_PREV = 2 };   /* meta bit 1: the stored state is the result of an integrated step whose
-                                                                     w_crossing test is still due (done at the start of the next pass) */
+enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2, FLAG_HAS_PREV = 2, FLAG_OUT = 4, FLAG_ZERO = 8, META_SHIFT = 4 };   /* FLAG_OUT / FLAG_ZERO: copies of the
+   has_out bits (outgoing synapses: p5 exists; the row starts with zero-delay synapses), so that the thread that detects a
+   spike needs no load — a dependent load there stalls its warp, and with it the CTA, for a microsecond.  */
+/* FLAG_HAS_PREV (meta bit 1): the stored state is the result of an integrated step whose w_crossing test is still due (done
+ * at the start of the next pass) */
 
 struct MonDesc {
   int var, reduce, active, red_slot;
@@ -95,7 +98,7 @@ struct Params {
   double* par[HHD_N_PARAMS];
   double* x[8];
   double* last_spike;          /* [NG] */
-  int* meta;                   /* [N] lastspike_step * 4 + flags of the previous step */
+  int* meta;                   /* [N] lastspike_step << META_SHIFT | flags (of the previous step; FLAG_OUT, FLAG_ZERO static) */
   const unsigned char* has_out;/* [NG] */
   long long* pend;             /* [2][3][n_pad] synaptic increments summed per (channel, target): fp64 bits (HHD_ACCUM_FP64)
                                   or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED).  The deliveries of slot k go to buffer
@@ -118,7 +121,8 @@ struct Params {
   int* spk_neuron;             /* global ids */
   int* spk_step;
   unsigned int cap_mask;
-  int* spk_hist;               /* [NG][hist_depth] steps of the latest spikes of every neuron whose rows k_spike_new<true> processed */
+  int* spk_hist;               /* [NG][hist_depth] steps of the latest spikes of every neuron, newest first (note_spike); NULL while
+                                  max_delay < refractory steps */
   int hist_depth;
   int* spk_last;               /* [NG] step of the latest spike of every (global) neuron, written when the spike is appended */
   unsigned long long* head;    /* monotone count of spikes appended */
@@ -274,6 +278,23 @@ __device__ __forceinline__ void neuron_shared_init(const Params& P, NeuronShared
 }
 
 __device__ __forceinline__ void spike_local(const Params& P, int j, long long k, double t);
+
+/* What the appender of a spike (k_neuron on a single rank, k_append after the exchange) records besides the ring entry:
+ * the neuron's previous spike time for the STP update that follows (p0..p6 read it, possibly from many CTAs), the new one
+ * (p5: last_spike_pre = t, only neurons with outgoing synapses have that pathway), the step of its latest spike, and — when
+ * delays can outlast the refractory period — its spike history.  Returns the has_out flags. */
+/* Two spikes of a neuron are at least refr_steps apart, and hist_depth = max_delay / refr_steps + 2: spikes that can both
+ * be in flight never share a slot, and a reader just skips entries whose age is not in (0, max_delay]. */
+__device__ __forceinline__ int hist_slot(const Params& P, const int k) { return (k / max(P.refr_steps, 1)) % P.hist_depth; }
+
+__device__ __forceinline__ unsigned char note_spike(const Params& P, const int j, const int k, const double t) {
+  const unsigned char ho = P.has_out[j];
+  P.spk_last[j] = k;
+  P.prev_spike[j] = P.last_spike[j];
+  if (ho & 1) P.last_spike[j] = t;
+  if (P.spk_hist) P.spk_hist[(size_t)j * P.hist_depth + hist_slot(P, k)] = k;
+  return ho;
+}
 __device__ __forceinline__ void ahead_phase(const Params& P, long long k, unsigned part, unsigned nparts);
 
 /* One pass over this CTA's tiles for time step k.  `bar_parity` carries the phase bit of every mbarrier across calls
@@ -547,11 +568,11 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
 #endif
       bad = !(isfinite(x[0]) && isfinite(x[1]));
       /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
-      const int lastk = meta >> 2;
+      const int lastk = meta >> META_SHIFT;
       spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
 #pragma unroll
       for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
-      P.meta[i] = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | FLAG_HAS_PREV;
+      P.meta[i] = ((spiked ? (int)k : lastk) << META_SHIFT) | (meta & (FLAG_OUT | FLAG_ZERO)) | (spiked ? FLAG_SPIKED : 0) | FLAG_HAS_PREV;
     }
     /* ---- warp-ballot spike compaction: one atomic per warp that has spikes ----------------------------------- */
     const unsigned bal = __ballot_sync(0xffffffffu, spiked);
@@ -571,19 +592,18 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
         base = __shfl_sync(0xffffffffu, base, 0);
         if (spiked) {
           const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
-          P.spk_neuron[pos] = P.off + i;
+          /* the ring entry and what note_spike records, from registers only */
+          const int j = P.off + i;
+          P.spk_neuron[pos] = j;
           P.spk_step[pos] = (int)k;
-          P.spk_last[P.off + i] = (int)k;
-        }
-      }
-      if (PIPE && spiked) {      /* what pass k+1 must see of this spike: p5 now, its zero-delay synapses before the pass ends */
-        const int j = P.off + i;
-        const unsigned char ho = P.has_out[j];
-        P.prev_spike[j] = ls;
-        if (ho & 1) P.last_spike[j] = t;
-        if (ho & 2) {            /* served by this CTA after its last tile; beyond 16, by the CTA that closes the pass */
-          const int q = atomicAdd(&sh.zl_n, 1);
-          if (q < 16) sh.zl_j[q] = j; else P.zlist[atomicAdd(P.zcount, 1u)] = j;
+          P.spk_last[j] = (int)k;
+          P.prev_spike[j] = ls;
+          if (meta & FLAG_OUT) P.last_spike[j] = t;
+          if (P.spk_hist) P.spk_hist[(size_t)j * P.hist_depth + hist_slot(P, (int)k)] = (int)k;
+          if (PIPE && (meta & FLAG_ZERO)) {  /* zero-delay synapses: served by this CTA after its last tile; beyond 16, by the CTA that closes the pass */
+            const int q = atomicAdd(&sh.zl_n, 1);
+            if (q < 16) sh.zl_j[q] = j; else P.zlist[atomicAdd(P.zcount, 1u)] = j;
+          }
         }
       }
     }
@@ -745,6 +765,61 @@ __device__ __forceinline__ void spike_local(const Params& P, int j, long long k,
   atomicAdd(&P.del_slots[j & (CNT_SLOTS - 1)], n);
 }
 
+/* Lane-per-spike delivery.  due_segment: the synapses of the spike in ring entry sp that are due in slot k, as a segment
+ * (first record, count) of its delay-sorted row, straight from the row's per-delay offsets.  skip_respiked: leave out
+ * neurons that spiked again in step k (serial schedule with long delays: k_spike_new delivers for them). */
+__device__ __forceinline__ void due_segment(const Params& P, const long long k, const unsigned long long sp, const bool skip_respiked,
+                                            long long& ra, unsigned& cnt) {
+  const unsigned pos = (unsigned)sp & P.cap_mask;
+  const int j = P.spk_neuron[pos];
+  const int age = (int)(k - (long long)P.spk_step[pos]);
+  if (age > P.max_delay || age < 0) return;
+  if (skip_respiked && P.spk_last[j] == (int)k) return;
+  const unsigned short* o = P.row_doff + (size_t)j * P.doff_stride + age;
+  const unsigned a0 = o[0], a1 = o[1];
+  ra = P.row_ptr[j] + a0;
+  cnt = a1 - a0;
+}
+
+/* The warp walks the concatenation of its lanes' segments 32 synapses at a time, two rounds of loads in flight (the
+ * segments are very uneven, 0..~100 synapses, so one thread per segment would wait for the longest). */
+__device__ __forceinline__ void deliver_flat(const Params& P, long long* const pout, const long long ra, const unsigned cnt,
+                                             const unsigned lane, unsigned long long& delivered) {
+  unsigned incl = cnt;                                   /* inclusive prefix sum of the segment lengths */
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane >= d) incl += v;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned excl = incl - cnt;
+  for (unsigned base = 0; base < total; base += 64) {
+    SynHot q[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned idx = base + 32 * u + lane;
+      unsigned owner = 0;                                /* the last lane whose exclusive prefix is <= idx (binary search over the warp) */
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const unsigned probe = owner + step;
+        const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
+        if (probe < 32 && e <= idx) owner = probe;
+      }
+      const long long ra_o = __shfl_sync(0xffffffffu, ra, owner);
+      const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
+      ok[u] = idx < total;
+      if (ok[u]) q[u] = P.hot[ra_o + (idx - ex_o)];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (ok[u]) {
+        ++delivered;
+        if (q[u].amp != 0.0) add_increment(P, pout, q[u].chan, q[u].tgt, q[u].amp);
+      }
+  }
+}
+
 /* p0..p6 for ONE synapse of a spike of step ks (spike time ts, previous spike of the neuron `last`); slot >= 0: deliver
  * it too if it is due in that slot.  Zero-delay synapses were handled by spike_local at the spike's own step. */
 __device__ __forceinline__ void stp_apply(const Params& P, const long long slot, long long* const pout, const long long r,
@@ -815,30 +890,20 @@ __device__ __forceinline__ void ahead_phase(const Params& P, const long long k, 
 
   /* ---- level 1: ring entries ---- */
   const bool stp0 = part < ntasks;
-  int sj = 0, dj = -1;
+  int sj = 0;
   long long sks = 0;
-  int dage = 0;
   if (stp0) {
     const unsigned pos = (unsigned)(mark + part / chunks) & P.cap_mask;
     sj = P.spk_neuron[pos];
     sks = (long long)P.spk_step[pos];
   }
-  if (spw && lane < spw && first0 + lane < mark) {
-    const unsigned pos = (unsigned)(first0 + lane) & P.cap_mask;
-    dj = P.spk_neuron[pos];
-    dage = (int)(k - (long long)P.spk_step[pos]);
-  }
-  /* ---- level 2: rows ---- */
-  long long sr0 = 0, sr1 = 0, dra = 0;
-  double slast = 0.0;
+  /* ---- levels 1-2 of the warp's first group, level 2 of the STP task: rows ---- */
+  long long dra = 0;
   unsigned dcnt = 0;
+  if (spw && lane < spw && first0 + lane < mark) due_segment(P, k, first0 + lane, false, dra, dcnt);
+  long long sr0 = 0, sr1 = 0;
+  double slast = 0.0;
   if (stp0) { sr0 = P.row_ptr[sj]; sr1 = P.row_ptr[sj + 1]; slast = P.prev_spike[sj]; }
-  if (dj >= 0 && dage <= P.max_delay) {
-    const unsigned short* o = P.row_doff + (size_t)dj * P.doff_stride + dage;
-    const unsigned a0 = o[0], a1 = o[1];
-    dra = P.row_ptr[dj] + a0;
-    dcnt = a1 - a0;
-  }
   /* ---- level 3: synapse records ---- */
   const unsigned schunk = part % chunks;
   const long long sr = sr0 + (long long)schunk * blockDim.x + threadIdx.x;
@@ -854,52 +919,9 @@ __device__ __forceinline__ void ahead_phase(const Params& P, const long long k, 
     if (first != first0) {               /* further groups of this warp (only when there are more than 32 spikes per warp) */
       ra = 0;
       cnt = 0;
-      if (lane < spw && first + lane < mark) {
-        const unsigned pos = (unsigned)(first + lane) & P.cap_mask;
-        const int j = P.spk_neuron[pos];
-        const int age = (int)(k - (long long)P.spk_step[pos]);
-        if (age <= P.max_delay) {
-          const unsigned short* o = P.row_doff + (size_t)j * P.doff_stride + age;
-          const unsigned a0 = o[0], a1 = o[1];
-          ra = P.row_ptr[j] + a0;
-          cnt = a1 - a0;
-        }
-      }
+      if (lane < spw && first + lane < mark) due_segment(P, k, first + lane, false, ra, cnt);
     }
-    unsigned incl = cnt;                                   /* inclusive prefix sum of the segment lengths */
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-      if ((int)lane >= d) incl += v;
-    }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned excl = incl - cnt;
-    for (unsigned base = 0; base < total; base += 64) {    /* two rounds of loads in flight */
-      SynHot q[2];
-      bool ok[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const unsigned idx = base + 32 * u + lane;
-        /* owner = the last lane whose exclusive prefix is <= idx (binary search over the warp) */
-        unsigned owner = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const unsigned probe = owner + step;
-          const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
-          if (probe < 32 && e <= idx) owner = probe;
-        }
-        const long long ra_o = __shfl_sync(0xffffffffu, ra, owner);
-        const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
-        ok[u] = idx < total;
-        if (ok[u]) q[u] = P.hot[ra_o + (idx - ex_o)];
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (ok[u]) {
-          ++delivered;
-          if (q[u].amp != 0.0) add_increment(P, pout, q[u].chan, q[u].tgt, q[u].amp);
-        }
-    }
+    deliver_flat(P, pout, ra, cnt, lane, delivered);
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
   if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
@@ -928,70 +950,69 @@ __global__ void __launch_bounds__(STP_BLOCK) k_stp_flush(const __grid_constant__
 __global__ void k_set_mark(const __grid_constant__ Params P) { *P.stp_mark = *P.head; }
 
 /*
- * Spike delivery.  Order-7 pathways (`g_X_post += ...` after `delay = dtax`, codes/CortexNetwork.py:367-372,463-468) for
- * every synapse whose delay elapses now, `last_spike_pre = t` (p5), and the SpikeGeneratorGroup events of this step.
- * One warp per ACTIVE spike: the spike history is the delay queue.  A row is sorted by delay and carries a 16-entry
- * bucket index, so the warp reads only the ~1/16 of the row that can be due and compares its uint16 delay column with
- * the spike's age.
- * FUSED = true: this kernel handles only spikes of EARLIER steps while k_spike_new (p0..p6 + zero-delay deliveries of
- * this step's spikes) runs concurrently on a second stream; legal only while max_delay < refractory steps, because then
- * no neuron can have a new spike and an undelivered older one at once, so no delivery can read an amplitude that
- * another CTA is rewriting.
+ * The serial schedule (delays that can outlast the refractory period, partitioned networks, the cooperative plan): after
+ * the state update of step k, two concurrent launches make slot k.
+ *
+ * k_spike_new: pathways p0..p6 (`u`, `R`, `a_syn`, failure draw at the presynaptic spike, codes/CortexNetwork.py:351-366)
+ * for the spikes of THIS step plus their zero-delay deliveries.  A task is one block of STP_BLOCK consecutive synapses of
+ * one spike's row, stp_chunks tasks per spike, so a spike's row is rewritten by several CTAs at once; the previous spike
+ * time it needs was saved by note_spike.
+ * LONG = true (some delay >= refractory steps): the neuron may still have older spikes in flight whose deliveries must
+ * use the amplitudes just rewritten.  Their steps are in the neuron's history; every thread checks ITS synapse
+ * against them and delivers it if one of them is due now, while k_deliver<DELIVER_MAIN> skips every neuron that spiked in
+ * this step.
  */
-/* Pathways p0..p6 + the zero-delay deliveries + p5 for the spikes of THIS step, one CTA per new spike (fused mode). */
-/* LONG = true (some delay >= refractory steps): the neuron may still have older spikes in flight whose deliveries must
- * use the amplitudes just rewritten; their steps are in the per-neuron history spk_hist, and warp 0 delivers
- * what is due from them now, while k_deliver<DELIVER_MAIN> skips every neuron that spiked in this step. */
 template <bool LONG>
 __device__ __forceinline__ void spike_new_phase(const Params& P, const long long k) {
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
   long long* const pout = pend_of_slot(P, k);
-  const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];
+  const unsigned long long lo_new = P.step_end[((int)k + P.W - 1) % P.W];
   const unsigned long long hi = *P.head;
-  if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[k % P.W] = hi;
-  unsigned long long events = 0, delivered0 = 0;
-  for (unsigned long long sp = lo_new + blockIdx.x; sp < hi; sp += gridDim.x) {
-    const int j = P.spk_neuron[(unsigned)sp & P.cap_mask];
-    const double last = P.last_spike[j];
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[(int)k % P.W] = hi;
+  unsigned long long delivered = 0;
+  const unsigned chunks = (unsigned)P.stp_chunks;
+  const unsigned ntasks = (unsigned)(hi - lo_new) * chunks;
+  for (unsigned task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const unsigned chunk = task % chunks;
+    const int j = P.spk_neuron[(unsigned)(lo_new + task / chunks) & P.cap_mask];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-    for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-      SynStp sy = P.stp[r];
+    const double last = P.prev_spike[j];
+    if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
+    int older[17];                                             /* ages of the neuron's older spikes that can still deliver, else -1 */
+    if (LONG) {
+      const int* hist = P.spk_hist + (size_t)j * P.hist_depth;
+      const int maxd = P.row_maxd[j];
+#pragma unroll
+      for (int q = 0; q < 17; ++q) {
+        older[q] = -1;
+        if (q < P.hist_depth) {
+          const int age = (int)(k - (long long)hist[q]);
+          if (age > 0 && age <= maxd) older[q] = age;
+        }
+      }
+    }
+    for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x) {
       const SynHot sh = P.hot[r];
-      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t,
-                                        last, P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig),
-                                        (unsigned long long)k);
+      SynStp sy = P.stp[r];
+      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t, last,
+                                        P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)k);
       P.stp[r].u = sy.u;
       P.stp[r].R = sy.R;
       P.hot[r].amp = amp;
-      if (sh.delay == 0) {
-        ++delivered0;
+      bool due = sh.delay == 0;
+      if (LONG) {
+#pragma unroll
+        for (int q = 0; q < 17; ++q) if ((int)sh.delay == older[q]) due = true;
+      }
+      if (due) {
+        ++delivered;
         if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
       }
     }
-    if (threadIdx.x == 0) events += (unsigned long long)(r1 - r0);
-    __syncthreads();                                           /* every thread has read last_spike[j]; the row is rewritten */
-    if (threadIdx.x == 0 && (P.has_out[j] & 1)) P.last_spike[j] = t;   /* p5 */
-    if (LONG) {
-      if (threadIdx.x < 32) {
-        int* hist = P.spk_hist + (size_t)j * P.hist_depth;
-        const int maxd = P.row_maxd[j];
-        for (int q = 0; q < P.hist_depth; ++q) {
-          const int age = (int)(k - (long long)hist[q]);
-          if (age > 0 && age <= maxd) delivered0 += deliver_row_due(P, pout, j, age, lane);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          for (int q = P.hist_depth - 1; q > 0; --q) hist[q] = hist[q - 1];
-          hist[0] = (int)k;
-        }
-      }
-      __syncthreads();
-    }
   }
-  if (threadIdx.x == 0 && events) atomicAdd(&P.counters[CNT_SYN_EVENTS], events);
-  delivered0 = (unsigned long long)warp_sum((double)delivered0);
-  if (lane == 0 && delivered0) atomicAdd(&P.counters[CNT_DELIVERIES], delivered0);
+  delivered = (unsigned long long)warp_sum((double)delivered);
+  if (lane == 0 && delivered) atomicAdd(&P.del_slots[(blockIdx.x * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], delivered);
 }
 
 template <bool LONG>
@@ -1016,6 +1037,16 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
   const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   unsigned long long delivered = 0;
+  if (P.row_doff) {                    /* one LANE per spike of an earlier step, spread evenly over the warps of the grid */
+    const unsigned nact = (unsigned)(lo_new - lo);
+    const unsigned spw = min(32u, (nact + warps - 1) / warps);
+    for (unsigned long long first = lo + (unsigned long long)wid * spw; first < lo_new && spw; first += (unsigned long long)warps * spw) {
+      long long ra = 0;
+      unsigned cnt = 0;
+      if (lane < spw && first + lane < lo_new) due_segment(P, k, first + lane, MODE == DELIVER_MAIN, ra, cnt);
+      deliver_flat(P, pout, ra, cnt, lane, delivered);
+    }
+  } else
   for (unsigned long long sp = lo + wid; sp < lo_new; sp += warps) {     /* one warp per spike of an earlier step */
     const unsigned pos = (unsigned)sp & P.cap_mask;
     const int j = P.spk_neuron[pos];
@@ -1232,13 +1263,13 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
       hhd_subexpr(P.cc, p, x, s1);
       hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1);
       n_bad += !(isfinite(x[0]) && isfinite(x[1]));
-      const int lastk = meta >> 2;
+      const int lastk = meta >> META_SHIFT;
       spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
       SubExpr sx;
       hhd_subexpr(P.cc, p, x, sx);
       const double band = hhd_div(sx.D0, p.tauw);
       wcross = (x[1] > sx.w_V - band) && (x[1] < sx.w_V + band) && (x[0] <= p.VT);
-      meta = ((spiked ? (int)k : lastk) << 2) | (spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0);
+      meta = ((spiked ? (int)k : lastk) << META_SHIFT) | (meta & (FLAG_OUT | FLAG_ZERO)) | (spiked ? FLAG_SPIKED : 0) | (wcross ? FLAG_WCROSS : 0);
       n_wc += wcross;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, spiked);
@@ -1392,7 +1423,7 @@ __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P
       const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
       P.spk_neuron[pos] = src[1 + q];
       P.spk_step[pos] = (int)k;
-      P.spk_last[src[1 + q]] = (int)k;
+      note_spike(P, src[1 + q], (int)k, (double)k * P.dt);
     }
   }
   __syncthreads();
@@ -1598,7 +1629,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
   {
     std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms);
-    std::vector<int> lk((size_t)h->N, -(1 << 30));   /* lastspike = -2^28 steps, no flags */
+    std::vector<int> lk((size_t)h->N, -(1 << 30));   /* lastspike = -2^26 steps, no flags */
     cudaMemcpyAsync(P.last_spike, ls.data(), ls.size() * 8, cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(P.meta, lk.data(), lk.size() * 4, cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -1673,6 +1704,7 @@ extern "C" int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_co
 
 extern "C" int hhd_set_has_outgoing(hhd_handle h, const uint8_t* has_out_global) {
   if (!h || !has_out_global) return fail(h, HHD_E_ARG, "null argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_has_outgoing after run");
   cudaSetDevice(h->cfg.device);
   h->has_out_host.assign(has_out_global, has_out_global + h->NG);
   h->has_out_given = true;
@@ -1781,13 +1813,16 @@ __global__ void k_syn_buckets(int NG, const long long* row_ptr, const SynHot* ho
   if (b == 0) row_maxd[j] = r1 > r0 ? hot[r1 - 1].delay : 0;      /* rows are sorted by delay */
 }
 
-/* has_out bit 1: the row starts with zero-delay synapses (rows are sorted by delay) */
-__global__ void k_mark_zero_delay(int NG, const long long* row_ptr, const SynHot* hot, unsigned char* has_out) {
+/* has_out bit 1: the row starts with zero-delay synapses (rows are sorted by delay); both bits are copied into the
+ * local neurons' meta words */
+__global__ void k_mark_flags(int NG, int N, int off, const long long* row_ptr, const SynHot* hot, unsigned char* has_out, int* meta) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= NG) return;
   const long long r0 = row_ptr[j], r1 = row_ptr[j + 1];
   const unsigned char z = (r1 > r0 && hot[r0].delay == 0) ? 2 : 0;
-  has_out[j] = (unsigned char)((has_out[j] & 1) | z);
+  const unsigned char ho = (unsigned char)((has_out[j] & 1) | z);
+  has_out[j] = ho;
+  if (j >= off && j < off + N) meta[j - off] = (meta[j - off] & ~(FLAG_OUT | FLAG_ZERO)) | ((ho & 1) ? FLAG_OUT : 0) | ((ho & 2) ? FLAG_ZERO : 0);
 }
 
 /* row_doff[j][d] = offset inside row j of the first synapse whose delay is >= d, d = 0 .. max_delay + 1; also the longest row */
@@ -1870,7 +1905,7 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     P.row_bkt = bkt;
   }
   P.row_doff = nullptr;
-  if (maxd < P.refr_steps && HHD_NEURON_PREFETCH == 2) {     /* what the pipelined schedule needs (finalize_setup decides) */
+  if ((size_t)h->NG * (size_t)(maxd + 2) * 2 <= ((size_t)4 << 30)) {     /* per-delay offsets: lane-per-spike delivery */
     unsigned short* doff = nullptr;
     int* dmax_row = nullptr;
     const int stride = maxd + 2;
@@ -2165,9 +2200,9 @@ static int finalize_setup(hhd_handle h) {
     if (!rc) rc = upload(h, P.spk_last, never.data(), never.size());
     if (rc) return rc;
   }
-  P.hist_depth = (int)(P.max_delay / refr) + 1;
+  P.hist_depth = (int)(P.max_delay / refr) + 2;      /* the spike being processed + every older one that can still be in flight */
   if (P.max_delay >= P.refr_steps) {
-    if (P.hist_depth > 16) return fail(h, HHD_E_ARG, "delays of more than 16 refractory periods are not supported");
+    if (P.hist_depth > 17) return fail(h, HHD_E_ARG, "delays of more than 16 refractory periods are not supported");
     std::vector<int> never((size_t)h->NG * P.hist_depth, -(1 << 30));
     rc = dev_alloc(h, &P.spk_hist, never.size(), false);
     if (!rc) rc = upload(h, P.spk_hist, never.data(), never.size());
@@ -2206,11 +2241,6 @@ static int finalize_setup(hhd_handle h) {
   h->stp_grid = h->sm_count * 4;
   h->deliver_grid = h->sm_count * 16;          /* 16 CTAs x 128 threads = one full wave; >= 1 warp per active spike at 1M neurons */
   if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
-  h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
-  h->kernels_per_step = 3;
-  /* pipelined schedule: graph plan, single rank, no neuron with a new spike and an undelivered older one */
-  h->pipelined = h->fused && h->cfg.n_ranks == 1 && P.row_doff && !getenv("HHD_NO_PIPELINE");
-  h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
     unsigned short* rmax = nullptr;
@@ -2220,7 +2250,24 @@ static int finalize_setup(hhd_handle h) {
     P.row_bkt = bkt;
     P.row_maxd = rmax;
     P.bkt_width = 1;
+    unsigned short* doff = nullptr;
+    rc = dev_alloc(h, &doff, (size_t)h->NG * 2, true);
+    if (rc) return rc;
+    P.row_doff = doff;
+    P.doff_stride = 2;
+    P.stp_chunks = 1;
   }
+  h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
+  h->kernels_per_step = 3;
+  /* pipelined schedule: graph plan, single rank, no neuron with a new spike and an undelivered older one */
+  {
+    const bool can = h->fused && h->cfg.n_ranks == 1 && P.row_doff && HHD_NEURON_PREFETCH == 2;
+    if (h->cfg.plan == HHD_PLAN_PIPELINED && !can)
+      return fail(h, HHD_E_ARG, "HHD_PLAN_PIPELINED needs max delay < refractory period and a single rank");
+    /* opt-in: measured 61.1 vs 59.6 us per step against the serial schedule on 1M neurons (profiles/r1_notes.md) */
+    h->pipelined = can && (h->cfg.plan == HHD_PLAN_PIPELINED || (h->cfg.plan == HHD_PLAN_AUTO && getenv("HHD_PIPELINE") && atoi(getenv("HHD_PIPELINE"))));
+  }
+  h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
   {
     const int inst = h->cfg.instance_size > 0 ? h->cfg.instance_size : h->N;
     const bool can = h->cfg.n_ranks == 1 && P.max_delay < P.refr_steps && inst <= RES_MAX_CLUSTER * RES_BLOCK && h->N % inst == 0 &&
@@ -2271,10 +2318,8 @@ static int finalize_setup(hhd_handle h) {
   }
   if (getenv("HHD_DEBUG_TIMES")) { rc = dev_alloc(h, &P.dbg_times, (size_t)16 * 4096, true); if (rc) return rc; }
   if (h->resident || h->gridplan) h->pipelined = false;
-  if (h->pipelined) {
-    k_mark_zero_delay<<<(h->NG + 255) / 256, 256, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, const_cast<unsigned char*>(P.has_out));
-    CU(cudaGetLastError());
-  }
+  k_mark_flags<<<(h->NG + 255) / 256, 256, 0, h->stream>>>(h->NG, h->N, P.off, P.row_ptr, P.hot, const_cast<unsigned char*>(P.has_out), P.meta);
+  CU(cudaGetLastError());
   if (h->pipelined) {
     h->kernels_per_step = 1;
     const char* env = getenv("HHD_AHEAD_CTAS");
@@ -2530,7 +2575,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   int rc = 0;
   if (!h->started && (rc = finalize_setup(h))) return rc;
   if (n_steps == 0) return HHD_OK;
-  if (h->step + n_steps >= (1ll << 29) - 1) return fail(h, HHD_E_ARG, "step index would exceed 2^29");
+  if (h->step + n_steps >= (1ll << 27) - 1) return fail(h, HHD_E_ARG, "step index would exceed 2^27");
   if (h->ext_dirty && (rc = rebuild_ext(h))) return rc;
   if ((rc = grow_monitors(h, n_steps))) return rc;
   const int prev_n_mon = h->P.n_mon;

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HHD_LIB") or os.path.join(_HERE, "csrc", "libhhd.so")
 ABI_VERSION = 1
 METHODS = {"euler": 0, "rk2": 1, "rk4": 2, "rk23": 3, "gsl_rk2": 3}
 ACCUM = {"fp64": 0, "fixed": 1}
-PLANS = {"auto": 0, "graph": 1, "resident": 2, "persistent": 3}
+PLANS = {"auto": 0, "graph": 1, "resident": 2, "persistent": 3, "pipelined": 4}
 REDUCE = {"none": 0, "sum": 1, "mean": 2}
 PARAM_ROWS = ["C", "g_L", "E_L", "delta_T", "V_up", "tau_w", "b", "V_r", "V_T", "I_ref", "V_dep", "I_DC"]
 VARS = ["V", "w", "g_AMPA_on", "g_AMPA_off", "g_GABA_on", "g_GABA_off", "g_NMDA_on", "g_NMDA_off",

@@ -46,7 +46,7 @@ def same(gpu, cpu, syn=True):
     return len(ci)
 
 
-@pytest.mark.parametrize("plan", ["graph", "resident", "persistent"])
+@pytest.mark.parametrize("plan", ["graph", "resident", "persistent", "pipelined"])
 @pytest.mark.parametrize("n", [1, 31, 129, 300])
 def test_ragged_sizes_with_random_synapses(n, plan):
     rng = np.random.default_rng(n)

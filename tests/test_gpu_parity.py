@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 STATE = ["V", "w", "g_AMPA_on", "g_AMPA_off", "g_GABA_on", "g_GABA_off", "g_NMDA_on", "g_NMDA_off"]
 
 
-PLANS = ["graph", "resident", "persistent"]   # CUDA graphs of grid-wide kernels / one cluster per instance / one cooperative launch
+PLANS = ["graph", "resident", "persistent", "pipelined"]   # CUDA graphs of grid-wide kernels / one cluster per instance / one cooperative launch / one launch per step
 
 
 def gpu_cpu(g, plan, **kw):
