@@ -45,6 +45,7 @@
 #include "hhd_model.cuh"
 
 #define MAX_MON 16
+#define MAX_RANKS 16
 #define MAX_RED 4   /* reduced (sum/mean) monitors: their per-thread accumulators live in registers */
 #ifndef NEURON_BLOCK
 #define NEURON_BLOCK 128
@@ -58,7 +59,7 @@
 #define RES_MAX_CLUSTER 16
 #define DELAY_BUCKETS 16
 
-enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_N };
+enum { CNT_SYN_EVENTS = 0, CNT_DELIVERIES, CNT_EXT, CNT_SPIKES, CNT_WCROSS, CNT_NONFINITE, CNT_OVERFLOW, CNT_TIMEOUT, CNT_N };
 #define CNT_SLOTS 256   /* the delivery counter is spread over 256 addresses: thousands of warps bump it every step, and
                            same-address atomics serialise in one L2 slice */
 enum { FLAG_SPIKED = 1, FLAG_WCROSS = 2, FLAG_HAS_PREV = 2, FLAG_OUT = 4, FLAG_ZERO = 8, META_SHIFT = 4 };   /* FLAG_OUT / FLAG_ZERO: copies of the
@@ -156,6 +157,12 @@ struct Params {
   int n_ranks, xchg_cap;
   int* xchg_send;              /* [1 + xchg_cap] */
   int* xchg_recv;              /* [n_ranks][1 + xchg_cap] */
+  /* peer-memory exchange (k_exchange): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] ints followed by
+   * MAX_RANKS arrival flags, mapped into this process (CUDA IPC over NVLink); peer_buf[rank] is the own one; NULL = the
+   * NCCL all-gather is used instead */
+  int rank;
+  int* peer_buf[MAX_RANKS];
+  unsigned int* xchg_dead;     /* set when a peer did not arrive within the time limit: later steps do not wait again */
   /* cluster-resident plan: the network is n_inst independent instances of inst_size neurons, one thread-block cluster each */
   int inst_size, n_inst, res_cap, res_cluster;
   unsigned int* res_store;     /* [n_inst][2 + W + 2*res_cap] head, pad, end[W], neuron[cap], step[cap]: the instance's spike list between launches */
@@ -1433,6 +1440,76 @@ __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P
   }
 }
 
+/*
+ * The exchange of a partitioned network as ONE launch over peer memory instead of ncclAllGather + k_append (the all-gather
+ * costs 18-20 us per step for half a kilobyte of spikes; this is a store over NVLink and a flag).  The block writes this
+ * rank's (count, ids...) list of step k into slot [k & 1][rank] of EVERY rank's receive buffer, fences, raises its flag
+ * (k + 1) on every rank, waits until every rank's flag in its own buffer has reached k + 1, and appends all lists to the
+ * ring in rank order exactly as k_append does.  Two parities suffice: a rank can only write step k + 2 after it has
+ * consumed everybody's step k + 1, which a peer only sends after it has consumed step k.  A peer that does not arrive
+ * within 20 s (it died) is reported through CNT_TIMEOUT instead of hanging the device.
+ */
+__global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Params P, const int step_offset) {
+  const long long k = *P.base_step + step_offset;
+  const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
+  const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
+  __shared__ unsigned long long base_sh[MAX_RANKS + 1];
+  const int n_mine = min(P.xchg_send[0], P.xchg_cap);
+  for (int r = 0; r < P.n_ranks; ++r) {
+    int* dst = P.peer_buf[r] + ((size_t)par * P.n_ranks + me) * slot;
+    for (int q = tid; q < n_mine; q += blockDim.x) dst[1 + q] = P.xchg_send[1 + q];
+    if (tid == 0) dst[0] = n_mine;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < P.n_ranks) {
+    volatile int* flag = P.peer_buf[tid] + flags_off + me;
+    *flag = (int)(k + 1);
+    __threadfence_system();
+    volatile int* mine = P.peer_buf[me] + flags_off + tid;
+    if (!*(volatile unsigned int*)P.xchg_dead) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*mine < (int)(k + 1)) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) {
+          *P.xchg_dead = 1u;
+          atomicAdd(&P.counters[CNT_TIMEOUT], 1ull);
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int* recv = P.peer_buf[me] + (size_t)par * P.n_ranks * slot;
+  if (tid == 0) {
+    unsigned long long b = *P.head;
+    for (int r = 0; r < P.n_ranks; ++r) {
+      base_sh[r] = b;
+      b += (unsigned long long)min(max(__ldcg(recv + (size_t)r * slot), 0), P.xchg_cap);
+    }
+    base_sh[P.n_ranks] = b;
+  }
+  __syncthreads();
+  for (int r = 0; r < P.n_ranks; ++r) {
+    const int* src = recv + (size_t)r * slot;
+    const int n = (int)(base_sh[r + 1] - base_sh[r]);
+    for (int q = tid; q < n; q += blockDim.x) {
+      const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
+      const int j = __ldcg(src + 1 + q);             /* written by another GPU: not through this SM's L1 */
+      P.spk_neuron[pos] = j;
+      P.spk_step[pos] = (int)k;
+      note_spike(P, j, (int)k, (double)k * P.dt);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *P.head = base_sh[P.n_ranks];
+    P.xchg_send[0] = 0;
+  }
+}
+
 __global__ void k_advance(long long* base_step, int n) { *base_step += n; }
 
 __global__ void k_read_var(const __grid_constant__ Params P, int var, double* out) {
@@ -1501,6 +1578,8 @@ struct hhd_engine {
   hhd_counters cnt;
   int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
   bool pipelined = false;
+  bool p2p = false;                 /* spike exchange over mapped peer memory (k_exchange) instead of NCCL */
+  void* peer_mapped[MAX_RANKS] = {};/* cudaIpcOpenMemHandle results, closed in hhd_destroy */
 #ifdef HHD_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
@@ -1647,6 +1726,7 @@ extern "C" void hhd_destroy(hhd_handle h) {
 #ifdef HHD_WITH_NCCL
   if (h->comm) ncclCommDestroy(h->comm);
 #endif
+  for (int r = 0; r < MAX_RANKS; ++r) if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
@@ -2174,6 +2254,63 @@ static const void* neuron_fn_of(int method, bool timed, bool pipe) {
 
 static unsigned long long next_pow2(unsigned long long v) { unsigned long long p = 1; while (p < v) p <<= 1; return p; }
 
+#ifdef HHD_WITH_NCCL
+/* Map every rank's receive buffer into this process (CUDA IPC; the handles travel through the NCCL communicator) so that
+ * k_exchange can write spike lists and flags straight into peer memory.  Collective: every rank calls it from its first
+ * hhd_run.  Any failure on any rank (no peer access, IPC not permitted in this container, HHD_NO_P2P set) leaves all ranks
+ * on the NCCL all-gather. */
+static int setup_p2p(hhd_handle h) {
+  Params& P = h->P;
+  const int R = P.n_ranks;
+  h->p2p = false;
+  if (!h->comm_ready || R > MAX_RANKS) return 0;
+  const size_t n_int = (size_t)2 * R * (1 + (size_t)P.xchg_cap) + MAX_RANKS;
+  int* buf = nullptr;
+  int rc = dev_alloc(h, &buf, n_int, true);
+  if (rc) return rc;
+  int ok = getenv("HHD_NO_P2P") ? 0 : 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok && cudaIpcGetMemHandle(&mine, buf) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  unsigned char *d_mine = nullptr, *d_all = nullptr;
+  int* d_ok = nullptr;
+  rc = dev_alloc(h, &d_mine, 64, true);
+  if (!rc) rc = dev_alloc(h, &d_all, (size_t)64 * R, true);
+  if (!rc) rc = dev_alloc(h, &d_ok, 1, true);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+  if (ncclAllGather(d_mine, d_all, 64, ncclUint8, h->comm, h->stream) != ncclSuccess) return fail(h, HHD_E_COMM, "all-gather of the IPC handles failed");
+  std::vector<cudaIpcMemHandle_t> all((size_t)R);
+  CU(cudaMemcpyAsync(all.data(), d_all, (size_t)64 * R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < R; ++r) P.peer_buf[r] = nullptr;
+  P.peer_buf[P.rank] = buf;
+  for (int r = 0; r < R && ok; ++r) {
+    if (r == P.rank) continue;
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    h->peer_mapped[r] = ptr;
+    P.peer_buf[r] = (int*)ptr;
+  }
+  CU(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, h->stream));
+  if (ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream) != ncclSuccess) return fail(h, HHD_E_COMM, "all-reduce failed");
+  int all_ok = 0;
+  CU(cudaMemcpyAsync(&all_ok, d_ok, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  dev_free(h, d_mine); dev_free(h, d_all); dev_free(h, d_ok);
+  h->p2p = all_ok != 0;
+  if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] rank %d: spike exchange over %s\n", P.rank, h->p2p ? "peer memory (k_exchange)" : "NCCL all-gather");
+  if (!h->p2p) {
+    for (int r = 0; r < R; ++r) {
+      if (h->peer_mapped[r]) { cudaIpcCloseMemHandle(h->peer_mapped[r]); h->peer_mapped[r] = nullptr; }
+      P.peer_buf[r] = nullptr;
+    }
+  }
+  return 0;
+}
+#endif
+
 static int finalize_setup(hhd_handle h) {
   Params& P = h->P;
   if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
@@ -2218,7 +2355,12 @@ static int finalize_setup(hhd_handle h) {
     P.xchg_cap = env && atoi(env) > 0 ? atoi(env) : std::min(h->NG, 4096 + h->NG / (16 * P.n_ranks));
     rc = dev_alloc(h, &P.xchg_send, (size_t)1 + P.xchg_cap, true);
     if (!rc) rc = dev_alloc(h, &P.xchg_recv, (size_t)P.n_ranks * (1 + P.xchg_cap), true);
+    if (!rc) rc = dev_alloc(h, &P.xchg_dead, 1, true);
     if (rc) return rc;
+    P.rank = h->cfg.rank;
+#ifdef HHD_WITH_NCCL
+    if ((rc = setup_p2p(h))) return rc;
+#endif
   }
   {
     /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than tiles */
@@ -2407,6 +2549,18 @@ static void launch_neuron(hhd_handle h, int offset) {
   launch_pdl(h, fn, h->neuron_grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset);
 }
 
+#ifdef HHD_WITH_NCCL
+/* This step's spike indices, every rank to every rank: one launch over peer memory, or NCCL when the buffers could not be mapped */
+static void launch_exchange(hhd_handle h, int offset) {
+  if (h->p2p) {
+    k_exchange<<<1, 256, 0, h->stream>>>(h->P, offset);
+  } else {
+    ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
+    k_append<<<1, 256, 0, h->stream>>>(h->P, offset);
+  }
+}
+#endif
+
 static void launch_step(hhd_handle h, int offset) {
   if (h->pipelined) {            /* one launch per step: state update + the synaptic work that is one step ahead */
     launch_neuron<true>(h, offset);
@@ -2415,8 +2569,7 @@ static void launch_step(hhd_handle h, int offset) {
   launch_neuron<true>(h, offset);
 #ifdef HHD_WITH_NCCL
   if (h->cfg.n_ranks > 1) {   /* the one real exchange of the path: this step's spike indices, every rank to every rank */
-    ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
-    k_append<<<1, 256, 0, h->stream>>>(h->P, offset);
+    launch_exchange(h, offset);
   }
 #endif
   if (h->fused) {
@@ -2654,6 +2807,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   h->cnt.neuron_updates += n_steps * (long long)h->N;
   unsigned long long c[CNT_N];
   CU(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+  if (c[CNT_TIMEOUT]) return fail(h, HHD_E_COMM, "a peer rank did not deliver its spikes within 20 s (spike exchange over peer memory)");
   if (c[CNT_OVERFLOW]) return fail(h, HHD_E_CAPACITY, "a device buffer overflowed (monitor capacity, or more spikes in one step than the exchange buffer holds: HHD_XCHG_CAP)");
   {
     unsigned long long slots[CNT_SLOTS];
@@ -2706,8 +2860,7 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
     }
 #ifdef HHD_WITH_NCCL
     if (h->cfg.n_ranks > 1) {   /* the exchange is accounted to slot 1 */
-      ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
-      k_append<<<1, 256, 0, h->stream>>>(h->P, (int)s);
+      launch_exchange(h, (int)s);
     }
 #endif
     if (!h->fused) k_spike_new<true><<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
