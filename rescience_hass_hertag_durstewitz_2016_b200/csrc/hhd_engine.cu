@@ -699,11 +699,11 @@ template <int METHOD, bool STEP, bool TIMED = false, bool PIPE = false>
 __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ NeuronShared sh;
-  pdl_trigger();
   pdl_wait();
   neuron_shared_init(P, sh);
   unsigned bar_parity = 0;
   neuron_phase<METHOD, STEP, TIMED, PIPE>(P, *P.base_step + step_offset, reinterpret_cast<NeuronStage*>(smem_raw), sh, bar_parity);
+  pdl_trigger();     /* at the END: a dependent launched earlier would take the SM resources this grid's own CTAs still need */
 }
 
 /* buffer that collects the deliveries of slot k */
@@ -1024,9 +1024,9 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
 
 template <bool LONG>
 __global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
-  pdl_trigger();
   pdl_wait();
   spike_new_phase<LONG>(P, *P.base_step + step_offset);
+  pdl_trigger();
 }
 
 /* MODE: DELIVER_FUSED (max_delay < refractory steps) or DELIVER_MAIN (longer delays).  Either way this launch delivers
@@ -1086,9 +1086,9 @@ __device__ __forceinline__ void ext_events(const Params& P, const long long k, l
 
 template <int MODE>
 __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
-  pdl_trigger();
   pdl_wait();
   deliver_phase<MODE>(P, *P.base_step + step_offset);
+  pdl_trigger();
 }
 
 /* ================================================================================================================== *
@@ -2586,7 +2586,7 @@ static void launch_step(hhd_handle h, int offset) {
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
     k_spike_new<true><<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
     cudaEventRecord(h->ev_join, h->stream2);
-    k_deliver<DELIVER_MAIN><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, offset);
+    launch_pdl(h, k_deliver<DELIVER_MAIN>, h->deliver_grid, DELIVER_BLOCK, 0, h->stream, offset);
     cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   }
 }
