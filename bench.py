@@ -240,7 +240,7 @@ def workload_config(args, net, world):
                 method=args.method, dt_ms=args.dt, time_steps_per_step=args.window, accumulate=args.accum,
                 monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
                 l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
-                parallelism="%d GPU(s), columns partitioned, NCCL all-gather of spike indices every time step" % world if world > 1 else "1 GPU")
+                parallelism="%d GPU(s), columns partitioned, spike indices exchanged every time step over IPC-mapped peer memory (NCCL all-gather as fallback)" % world if world > 1 else "1 GPU")
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------

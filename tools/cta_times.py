@@ -1,3 +1,5 @@
+"""Per-CTA timing of the last two k_neuron launches of a run: HHD_DEBUG_TIMES=out.txt python bench.py ... ; python tools/cta_times.py out.txt
+(the engine writes out.txt = block, start, after the synaptic share, end of tiles, end [ns, %globaltimer] and out.txt.passes = first start / close per step)."""
 import numpy as np, sys
 a=np.loadtxt(sys.argv[1],dtype=np.int64)
 n=len(a)//2; X=a[n:] if a[n:,1].min()>a[:n,1].min() else a[:n]
