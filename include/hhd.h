@@ -216,6 +216,33 @@ int hhd_current_step(hhd_handle h, int64_t* step);
 int hhd_comm_unique_id(uint8_t out_id[128]);                       /* rank 0, then broadcast by the host program */
 int hhd_comm_init(hhd_handle h, const uint8_t id[128]);            /* collective over cfg.n_ranks handles */
 
+/* ---- spike-train analyses on the device --------------------------------------------------------------
+ * Stand-alone (no engine handle): spikes as (neuron, t_ms) arrays in time order — t_ms are the very floats the reference's
+ * code would see (`SpikeMonitor.t / ms`; step * dt for hhd_read_spikes' steps).  All buffers are host memory.  The results are the integer sufficient statistics of the reference's analyses; the
+ * coefficients follow on the host from the reference's formulas (rescience_hass_hertag_durstewitz_2016_b200/analysis.py). */
+enum hhd_bin_rule {
+  HHD_BIN_TRUNC = 0,    /* ((t - t0) / bin).astype(int)       codes/AuxiliarEquations.py:544 (set_binary_vector) */
+  HHD_BIN_FLOORDIV = 1  /* ((t - t0) // bin).astype(int)      codes/AuxiliarEquations.py:434 (pop_rate), codes_revision/AnalysesTools.py:193, 218 */
+};
+int hhd_an_words(int64_t n_bins);                                  /* uint64 words per bit-packed row: ceil(n_bins / 64) + 1 */
+/* Binary spike trains of the selected neurons (row q = neuron sel[q]): bit b of a row is set when the neuron has a spike with
+ * t0 <= t < t1 in bin b.  out_bits [n_sel][hhd_an_words(n_bins)], out_bins [n_sel][n_bins] of 0/1 and
+ * out_bin_counts [n_bins] (neurons active per bin: pop_rate's column sum) may each be NULL.
+ * Replaces set_binary_vector / get_binned_spiking_trains / the loop of pop_rate (file:line above). */
+int hhd_an_binned_trains(int32_t device, int64_t n_spikes, const int32_t* neuron, const double* t_ms,
+                         int32_t n_sel, const int32_t* sel, double t0_ms, double t1_ms, double bin_ms, int32_t rule,
+                         int64_t n_bins, uint64_t* out_bits, uint8_t* out_bins, int32_t* out_bin_counts);
+/* For every lag L >= 0 (in bins) and every ORDERED pair (i, j): out_sxy[l][i][j] = sum_{t < n_bins - L} x_i[t] x_j[t + L];
+ * out_head[l][i] = sum_{t < n_bins - L} x_i[t], out_tail[l][i] = sum_{t >= L} x_i[t].  Everything Pearson(t_vec1, t_vec2, lag)
+ * (codes/AuxiliarEquations.py:571-595) and Series.corr(Series.shift(lag)) (codes_revision/AnalysesTools.py:231-240) need. */
+int hhd_an_lagged_counts(int32_t device, int32_t n_sel, int64_t n_bins, const uint64_t* bits, int32_t n_lags, const int32_t* lags,
+                         int32_t* out_sxy, int32_t* out_head, int32_t* out_tail);
+/* Per selected neuron: number of inter-spike intervals, their mean [ms] and CV = np.std(ISI) / np.mean(ISI) (NaN without
+ * intervals), of the spikes with t0 <= t < t1 when has_window.  codes_revision/AnalysesTools.py:421-429 (ISIstats). */
+int hhd_an_isi_stats(int32_t device, int64_t n_spikes, const int32_t* neuron, const double* t_ms,
+                     int32_t n_sel, const int32_t* sel, int32_t has_window, double t0_ms, double t1_ms,
+                     double* out_mean, double* out_cv, int32_t* out_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,79 @@
+"""Golden vectors for the spike-train analyses, produced by the REFERENCE's own functions
+(/root/reference/codes/AuxiliarEquations.py and codes_revision/AnalysesTools.py, imported with stubs for the modules
+they import but do not need here: brian2, matplotlib, scipy.integrate.quadrature).  Run in the build container:
+    python tests/golden/make_golden_analysis.py
+writes tests/golden/analysis_golden.npz (inputs + outputs)."""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def main():
+    _stub("matplotlib", pyplot=_stub("matplotlib.pyplot"))
+    _stub("brian2", ms=1e-3, pA=1e-12)
+    import scipy.integrate
+    if not hasattr(scipy.integrate, "quadrature"):
+        scipy.integrate.quadrature = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+    sys.path.insert(0, os.path.join(REF, "codes"))
+    import AuxiliarEquations as AE
+    sys.path.pop(0)
+    sys.path.insert(0, os.path.join(REF, "codes_revision"))
+    import AnalysesTools as AT
+    sys.path.pop(0)
+
+    rng = np.random.default_rng(20161)
+    dt = 0.05
+    n, T = 7, 400.0
+    trains = []
+    for i in range(n):
+        k = int(rng.integers(0, 40)) if i != 3 else 0                 # one silent train
+        steps = np.sort(rng.choice(np.arange(int(T / dt)), size=k, replace=False))
+        trains.append(steps * dt)
+    trains[5] = np.concatenate([trains[5], [120.0, 120.05, 121.95]])   # two spikes in one bin, bin edges
+    trains[5].sort()
+    out = {"n": n, "dt": dt}
+    for i, t in enumerate(trains):
+        out["train_%d" % i] = t
+
+    t0, t1, t_bin = 10.0, 390.0, 2.0
+    out["codes_args"] = np.array([t0, t1, t_bin, -10.0, 12.0])
+    out["codes_binary_5"] = AE.set_binary_vector(trains[5], t0, t1, t_bin)
+    group = [trains[i] for i in (0, 1, 2, 4, 5, 6)]
+    lag_array, corr = AE.Pearson_correlation_group(group, t0, t1, t_bin, -10.0, 12.0)
+    out["codes_group_lags"], out["codes_group_corr"] = lag_array, corr
+    out["codes_zero_lag_group"] = np.asarray(AE.Zero_lag_Pearson_correlation_group(group, t0, t1, t_bin))
+    la, c01 = AE.Pearson_correlation(trains[0], trains[1], t0, t1, t_bin, -10.0, 12.0)
+    out["codes_pair01_corr"] = c01
+    tt, rate = AE.pop_rate(trains, 0.0, 400.0, 5.0)
+    out["codes_pop_rate_t"], out["codes_pop_rate"] = tt, rate
+    tt, rate = AE.pop_rate(trains, 0.0, 400.0, 5.0, sigma=2.0)
+    out["codes_pop_rate_sigma2"] = rate
+
+    idcs = [0, 1, 2, 4, 5, 6]
+    lags = [-3, 0, 1, 4]
+    res = AT.get_correlations_from_spike_trains(trains, (10, 389.3), idcs=idcs, delta_t=2, lags=lags)
+    for name, v in zip(("lags", "auto_mean", "auto_std", "cross_mean", "cross_std"), res):
+        out["rev_corr_" + name] = np.asarray(v)
+    out["rev_corr_args"] = np.array([10, 389.3, 2])
+    out["rev_corr_idcs"] = np.array(idcs)
+    out["rev_corr_lags_in"] = np.array(lags)
+    mean, cv = AT.get_ISI_stats_from_spike_trains(trains, neuron_idcs=[0, 1, 2, 4, 5, 6], tlim=(5.0, 395.0))
+    out["rev_isi_mean"], out["rev_isi_cv"] = np.asarray(mean), np.asarray(cv)
+    np.savez_compressed(os.path.join(HERE, "analysis_golden.npz"), **out)
+    print("wrote analysis_golden.npz:", sorted(out))
+
+
+if __name__ == "__main__":
+    main()
