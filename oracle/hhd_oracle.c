@@ -115,6 +115,7 @@ struct hhd_engine {
   double* par[HHD_N_PARAMS];
   double* x[8];
   double* last_spike;       /* [NG], ms, the model's custom variable (written by pathway p5) */
+  double* hstep;            /* [N] adaptive integrator: step size carried from one dt to the next (use_last_timestep) */
   int64_t* lastspike_step;  /* [N], Brian's internal `lastspike` as a step index */
   uint8_t* has_out;         /* [NG] */
   int has_out_given;
@@ -177,6 +178,8 @@ int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   for (int i = 0; i < HHD_N_PARAMS; ++i) h->par[i] = (double*)calloc((size_t)h->N, sizeof(double));
   for (int i = 0; i < 8; ++i) h->x[i] = (double*)calloc((size_t)h->N, sizeof(double));
   h->last_spike = (double*)malloc((size_t)h->NG * sizeof(double));
+  h->hstep = (double*)malloc((size_t)h->N * sizeof(double));
+  for (int i = 0; i < h->N; ++i) h->hstep[i] = cfg->dt_ms;
   h->lastspike_step = (int64_t*)malloc((size_t)h->N * sizeof(int64_t));
   h->has_out = (uint8_t*)calloc((size_t)h->NG, 1);
   h->cur_spikes = (int32_t*)malloc((size_t)h->N * sizeof(int32_t));
@@ -199,7 +202,7 @@ void hhd_destroy(hhd_handle h) {
   if (!h) return;
   for (int i = 0; i < HHD_N_PARAMS; ++i) free(h->par[i]);
   for (int i = 0; i < 8; ++i) free(h->x[i]);
-  free(h->last_spike); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch); free(h->iac_table); free(h->iac_col);
+  free(h->last_spike); free(h->hstep); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch); free(h->iac_table); free(h->iac_col);
   free(h->src); free(h->tgt); free(h->chan); free(h->gmax); free(h->U); free(h->tau_rec); free(h->tau_fac);
   free(h->pfail); free(h->delay_steps); free(h->u); free(h->R); free(h->a_syn); free(h->failure); free(h->touched);
   free(h->row_ptr); free(h->row_syn);
@@ -460,18 +463,32 @@ static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], doub
  * reproduces it bit for bit (the growth exponent is -1/4 instead of GSL's -1/3 for that reason).
  */
 #define RK23_MAX_SUBSTEPS 4096
-static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], double t0, double ls, double iac0, double iac1) {
+/*
+ * `gsl_rk2`: what Brian 2's GSL state updater runs per neuron and dt —
+ *   stepper   gsl_odeiv2_step_rk2: k1 = f(y), k2 = f(y + h/2 k1), k3 = f(y + h(-k1 + 2 k2)), y+ = y + h (k1 + 4 k2 + k3)/6,
+ *             yerr = h (k2 - (k1 + 4 k2 + k3)/6)   [|.| = h |k1 - 2 k2 + k3| / 6]
+ *   control   gsl_odeiv2_control_standard, eps_abs = 1e-6 in SI units of every variable, eps_rel = 0, order 2:
+ *             r = max |yerr_i| / eps_abs;  r > 1.1: h <- h max(0.2, 0.9 r^(-1/2)), retry;  r < 0.5: h <- h clamp(0.9 r^(-1/3), 1, 5)
+ *   evolve    gsl_odeiv2_evolve_apply: a step that would pass the end of the dt interval is truncated ("final step") and
+ *             its size is NOT taken as the suggestion for the next interval; a rejected final step is retried as a normal one
+ *   carry     the suggestion survives from one dt to the next (Brian's use_last_timestep) in h->hstep.
+ * The only liberties: hhd_cbrt for r^(-1/3) (within 2 ulp of pow; the same code runs on the GPU), a floor of 2^-20 dt on the
+ * step size instead of GSL's "step size too small" error, and NaN errors accept the step.
+ */
+static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], double t0, double ls, double iac0, double iac1, double* hcar) {
   const double dt = h->cfg.dt_ms;
   static const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
-  double t = 0.0, hs = dt;
+  double t = 0.0, h0 = *hcar;
   for (int it = 0; it < RK23_MAX_SUBSTEPS && t < dt; ++it) {
-    if (t + hs > dt) hs = dt - t;
+    double hs = h0;
+    int final_step = 0;
+    if (hs > dt - t) { hs = dt - t; final_step = 1; }     /* evolve.c: if (h0 > t1 - t) { h0 = t1 - t; final_step = 1; } */
     double k1[8], k2[8], k3[8], y[8], ynew[8];
     deriv(h, p, x, t0 + t, ls, iac0, k1);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
     deriv(h, p, y, t0 + (t + 0.5 * hs), ls, iac0, k2);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    deriv(h, p, y, t0 + (t + hs), ls, (t + hs) >= dt ? iac1 : iac0, k3);
+    deriv(h, p, y, t0 + (t + hs), ls, final_step ? iac1 : iac0, k3);
     double rmax = 0.0;
     for (int v = 0; v < 8; ++v) {
       ynew[v] = x[v] + hs * (((k1[v] + 4.0 * k2[v]) + k3[v]) / 6.0);
@@ -482,21 +499,24 @@ static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], doubl
     if (rmax > 1.1 && hs > dt * 9.5367431640625e-07) {     /* 2^-20 dt floor */
       double f = 0.9 / sqrt(rmax);
       if (f < 0.2) f = 0.2;
-      hs = hs * f;
+      h0 = hs * f;                                 /* retried as a normal step */
       continue;
     }
     for (int v = 0; v < 8; ++v) x[v] = ynew[v];
-    t = t + hs;
+    t = final_step ? dt : t + hs;
+    double hn = hs;
     if (rmax < 0.5) {
       double f = 5.0;
-      if (rmax > 0.0) {
-        f = 0.9 / sqrt(sqrt(rmax));
+      if (rmax > 9.765625e-4) {                    /* below 2^-10 the factor is clamped to 5 anyway (0.9 / 5)^3 = 0.0058 */
+        f = 0.9 / hhd_cbrt(rmax);
         if (f > 5.0) f = 5.0;
         if (f < 1.0) f = 1.0;
       }
-      hs = hs * f;
+      hn = hs * f;
     }
+    if (!final_step) h0 = hn;                      /* no suggestion from a truncated step */
   }
+  *hcar = h0;
 }
 
 /* I_AC of local neuron i at step s: TimedArray semantics (first row before the table, last row after it). */
@@ -579,7 +599,7 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
     double x[8];
     for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
     const double iac0 = iac_at(h, i, k), iac1 = iac_at(h, i, k + 1);
-    if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i], iac0, iac1);
+    if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i], iac0, iac1, &h->hstep[i]);
     else integrate_fixed(h, &p, x, t, h->last_spike[off + i], iac0, iac1);
     for (int v = 0; v < 8; ++v) h->x[v][i] = x[v];
     if (!isfinite(x[HHD_V]) || !isfinite(x[HHD_W])) bad++;
@@ -880,6 +900,7 @@ int hhd_comm_init(hhd_handle h, const uint8_t id[128]) { (void)id; return fail(h
 
 /* Plain exports of the shared math so tests can compare them with libm / a reference Philox. */
 double hhdo_exp(double x) { return hhd_exp(x); }
+double hhdo_cbrt(double x) { return hhd_cbrt(x); }
 double hhdo_philox_u01(uint64_t seed, uint64_t index, uint64_t step, uint32_t stream) { return hhd_philox_u01(seed, index, step, stream); }
 int64_t hhdo_delay_steps(double delay_ms, double dt_ms) { return hhd_delay_steps(delay_ms, dt_ms); }
 int64_t hhdo_timestep(double t_ms, double dt_ms) { return hhd_timestep(t_ms, dt_ms); }

@@ -99,6 +99,7 @@ struct Params {
   double* par[HHD_N_PARAMS];
   double* x[8];
   double* last_spike;          /* [NG] */
+  double* hstep;               /* [n_pad] adaptive method: the step size a neuron carries from one dt to the next */
   int* meta;                   /* [N] lastspike_step << META_SHIFT | flags (of the previous step; FLAG_OUT, FLAG_ZERO static) */
   const unsigned char* has_out;/* [NG] */
   long long* pend;             /* [2][3][n_pad] synaptic increments summed per (channel, target): fp64 bits (HHD_ACCUM_FP64)
@@ -571,7 +572,9 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     if (live) {
       /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
 #if !(HHD_EXPERIMENT & 2)
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S, iac0, iac1);
+      double hcar = METHOD == 3 ? P.hstep[i] : 0.0;
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S, iac0, iac1, &hcar);
+      if (METHOD == 3) P.hstep[i] = hcar;
 #endif
       bad = !(isfinite(x[0]) && isfinite(x[1]));
       /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
@@ -1197,7 +1200,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
 
   double x[8];
   NeuronPar p;
-  double ls = 0.0;
+  double ls = 0.0, hcar = P.dt;    /* hcar: the adaptive method's carried step size */
   int meta = 0;
   bool has_out = false;
   if (live) {
@@ -1206,6 +1209,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
     p = load_par(P, i);
     ls = P.last_spike[P.off + i];
     meta = P.meta[i];
+    if (METHOD == 3) hcar = P.hstep[i];
     has_out = (P.has_out[P.off + i] & 1) != 0;
   }
   unsigned long long n_events = 0, n_deliv = 0, n_ext = 0;
@@ -1268,7 +1272,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
     if (live) {
       SubExpr s1;
       hhd_subexpr(P.cc, p, x, s1);
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1);
+      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, s1, 0.0, 0.0, &hcar);
       n_bad += !(isfinite(x[0]) && isfinite(x[1]));
       const int lastk = meta >> META_SHIFT;
       spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
@@ -1387,6 +1391,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
 #pragma unroll
     for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
     P.meta[i] = meta;
+    if (METHOD == 3) P.hstep[i] = hcar;
   }
   if (rank == 0) {
     if (tid == 0) store[0] = list_sh->head;
@@ -1683,6 +1688,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   for (int p = 0; p < HHD_N_PARAMS && !rc; ++p) rc = dev_alloc(h, &P.par[p], n_pad);
   for (int v = 0; v < 8 && !rc; ++v) rc = dev_alloc(h, &P.x[v], n_pad);
   if (!rc) rc = dev_alloc(h, &P.last_spike, h->NG, false);
+  if (!rc && cfg->method == HHD_RK23_ADAPTIVE) rc = dev_alloc(h, &P.hstep, n_pad, false);
   if (!rc) rc = dev_alloc(h, &P.meta, h->N, false);
   unsigned char* ho = nullptr;
   if (!rc) rc = dev_alloc(h, &ho, h->NG);
@@ -1710,6 +1716,10 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
     std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms);
     std::vector<int> lk((size_t)h->N, -(1 << 30));   /* lastspike = -2^26 steps, no flags */
     cudaMemcpyAsync(P.last_spike, ls.data(), ls.size() * 8, cudaMemcpyHostToDevice, h->stream);
+    if (P.hstep) {
+      std::vector<double> h0(n_pad, cfg->dt_ms);
+      cudaMemcpy(P.hstep, h0.data(), h0.size() * 8, cudaMemcpyHostToDevice);
+    }
     cudaMemcpyAsync(P.meta, lk.data(), lk.size() * 4, cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
   }

@@ -95,7 +95,8 @@ __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPa
 template <int METHOD>
 __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t,
                                               double ls, double dt, const SubExpr& s1, const double iac0 = 0.0,
-                                              const double iac1 = 0.0) {   /* I_AC of this step / of the next (stage at t+dt) */
+                                              const double iac1 = 0.0,     /* I_AC of this step / of the next (stage at t+dt) */
+                                              double* hcar = nullptr) {    /* adaptive method only: the carried step size */
   double k1[8], y[8];
   SubExpr sk;
   hhd_rhs(cc, p, x, t, ls, s1, k1);
@@ -132,17 +133,20 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   for (int v = 0; v < 8; ++v) x[v] = x[v] + hhd_div(((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v], 6.0);
 }
 
-/* METHOD 3: the gsl_rk2 stand-in — embedded RK2(3) with per-neuron sub-stepping inside dt; operation for operation the
- * function integrate_rk23 of oracle/hhd_oracle.c (IEEE sqrt only), see there for the controller. */
+/* METHOD 3: `gsl_rk2` — embedded RK2(3) (gsl_odeiv2_step_rk2) under GSL's standard step-size control with per-neuron
+ * sub-stepping inside dt and the step size carried from one dt to the next; operation for operation the function
+ * integrate_rk23 of oracle/hhd_oracle.c, see there for the algorithm and its sources. */
 template <>
 __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const NeuronPar& p, double x[8], double t0,
                                                  double ls, double dt, const SubExpr& s1, const double iac0,
-                                                 const double iac1) {
+                                                 const double iac1, double* hcar) {
   const double inv_tol[8] = {1e3, 1e-6, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3};
-  double t = 0.0, hs = dt;
+  double t = 0.0, h0 = *hcar;
   bool first = true;
   for (int it = 0; it < 4096 && t < dt; ++it) {
-    if (t + hs > dt) hs = dt - t;
+    double hs = h0;
+    bool final_step = false;
+    if (hs > dt - t) { hs = dt - t; final_step = true; }
     double k1[8], k2[8], k3[8], y[8], ynew[8];
     SubExpr sk;
     if (first) hhd_rhs(cc, p, x, t0 + t, ls, s1, k1);
@@ -153,7 +157,7 @@ __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const N
     hhd_deriv(cc, p, y, t0 + (t + 0.5 * hs), ls, k2, sk, iac0);
 #pragma unroll
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    hhd_deriv(cc, p, y, t0 + (t + hs), ls, k3, sk, (t + hs) >= dt ? iac1 : iac0);
+    hhd_deriv(cc, p, y, t0 + (t + hs), ls, k3, sk, final_step ? iac1 : iac0);
     double rmax = 0.0;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -165,22 +169,25 @@ __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const N
     if (rmax > 1.1 && hs > dt * 9.5367431640625e-07) {
       double f = hhd_div(0.9, sqrt(rmax));
       if (f < 0.2) f = 0.2;
-      hs = hs * f;
+      h0 = hs * f;
       continue;
     }
 #pragma unroll
     for (int v = 0; v < 8; ++v) x[v] = ynew[v];
-    t = t + hs;
+    t = final_step ? dt : t + hs;
+    double hn = hs;
     if (rmax < 0.5) {
       double f = 5.0;
-      if (rmax > 0.0) {
-        f = hhd_div(0.9, sqrt(sqrt(rmax)));
+      if (rmax > 9.765625e-4) {
+        f = hhd_div(0.9, hhd_cbrt(rmax));
         if (f > 5.0) f = 5.0;
         if (f < 1.0) f = 1.0;
       }
-      hs = hs * f;
+      hn = hs * f;
     }
+    if (!final_step) h0 = hn;
   }
+  *hcar = h0;
 }
 
 /* Derived variable (id >= 8, != last_spike) from subexpressions already evaluated at the sampled state. */

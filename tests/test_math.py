@@ -81,3 +81,16 @@ def test_step_rounding_rules():
     assert lib.hhdo_timestep(5.0, 0.05) == 100
     assert lib.hhdo_timestep(5.0, 0.01) == 500
     assert lib.hhdo_timestep(0.3, 0.1) == 3          # 0.3/0.1 = 2.9999999999999996 without the epsilon
+
+
+def test_cbrt_within_two_ulp():
+    """hhd_cbrt (growth factor of the adaptive integrator's step-size controller): same code on host and device."""
+    lib = _lib()
+    lib.hhdo_cbrt.restype = C.c_double
+    lib.hhdo_cbrt.argtypes = [C.c_double]
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([10.0 ** rng.uniform(-9, 9, 5000), rng.uniform(9.765625e-4, 0.5, 5000), [1.0, 8.0, 27.0, 0.125, 0.5]])
+    for x in xs:
+        got, ref = lib.hhdo_cbrt(float(x)), float(np.cbrt(np.longdouble(x)))
+        assert abs(got - ref) <= 2 * math.ulp(ref), x
+    assert lib.hhdo_cbrt(27.0) == 3.0 and lib.hhdo_cbrt(0.125) == 0.5
