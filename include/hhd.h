@@ -155,6 +155,14 @@ int hhd_set_idc(hhd_handle h, const double* idc);
  * neuron i (-1: no timed current).  Runge-Kutta stages evaluated at t + dt read row s + 1.  Call before the first hhd_run. */
 int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const double* table, const int32_t* col_of_neuron);
 
+/* Conductance noise: replaces the `noise` variant of the model equations (codes/CortexNetwork.py:157-230, 391-394),
+ * `dg_X_off/dt = -g_X_off/tau_off_X + xi_X * sqrt(2 * noise_D * nCon) * nS/sqrt(ms)` for X = AMPA, GABA, NMDA with independent
+ * white noises.  sigma[i] = sqrt(2 * noise_D * nCon[i]) in nS/sqrt(ms) per LOCAL neuron; as Brian's stochastic `euler`
+ * updater does, every step adds sigma * sqrt(dt) * N(0,1) after the deterministic update.  The Gaussian numbers come from
+ * Philox keyed by (seed, global neuron, step) — reproducible, not Brian's Mersenne-Twister stream.  Needs HHD_EULER (Brian
+ * refuses the other methods for stochastic equations).  Call before the first hhd_run. */
+int hhd_set_noise(hhd_handle h, const double* sigma);
+
 /* ---- synapses: replaces Synapses(...).connect(i,j) + per-synapse assignments + delays/orders,
  *      codes/CortexNetwork.py:343-482 (revision: CortexSetup.py:62-91,239-308) ---------------------------------- */
 /* src, tgt are GLOBAL neuron ids; every tgt must be local to this handle.  chan in {0,1,2}.  delay_ms -> steps as

@@ -50,6 +50,7 @@
 #define hhd_clear_monitor hhdo_clear_monitor
 #define hhd_run hhdo_run
 #define hhd_set_timed_current hhdo_set_timed_current
+#define hhd_set_noise hhdo_set_noise
 #define hhd_set_idc hhdo_set_idc
 #define hhd_profile_kernels hhdo_profile_kernels
 #define hhd_spike_count hhdo_spike_count
@@ -115,6 +116,7 @@ struct hhd_engine {
   double* par[HHD_N_PARAMS];
   double* x[8];
   double* last_spike;       /* [NG], ms, the model's custom variable (written by pathway p5) */
+  double* noise_sigma;      /* [N] nS/sqrt(ms), NULL = no conductance noise */
   double* hstep;            /* [N] adaptive integrator: step size carried from one dt to the next (use_last_timestep) */
   int64_t* lastspike_step;  /* [N], Brian's internal `lastspike` as a step index */
   uint8_t* has_out;         /* [NG] */
@@ -202,7 +204,7 @@ void hhd_destroy(hhd_handle h) {
   if (!h) return;
   for (int i = 0; i < HHD_N_PARAMS; ++i) free(h->par[i]);
   for (int i = 0; i < 8; ++i) free(h->x[i]);
-  free(h->last_spike); free(h->hstep); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch); free(h->iac_table); free(h->iac_col);
+  free(h->last_spike); free(h->hstep); free(h->noise_sigma); free(h->lastspike_step); free(h->has_out); free(h->cur_spikes); free(h->cur_wcross); free(h->flag_scratch); free(h->iac_table); free(h->iac_col);
   free(h->src); free(h->tgt); free(h->chan); free(h->gmax); free(h->U); free(h->tau_rec); free(h->tau_fac);
   free(h->pfail); free(h->delay_steps); free(h->u); free(h->R); free(h->a_syn); free(h->failure); free(h->touched);
   free(h->row_ptr); free(h->row_syn);
@@ -249,6 +251,16 @@ int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const d
   memcpy(h->iac_table, table, (size_t)n_steps * n_cols * 8);
   memcpy(h->iac_col, col_of_neuron, (size_t)h->N * 4);
   h->iac_steps = n_steps; h->iac_cols = n_cols;
+  return HHD_OK;
+}
+
+int hhd_set_noise(hhd_handle h, const double* sigma) {
+  if (!h || !sigma) return fail(h, HHD_E_ARG, "null argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_noise after run");
+  if (h->cfg.method != HHD_EULER) return fail(h, HHD_E_ARG, "conductance noise needs the euler method (stochastic equations)");
+  free(h->noise_sigma);
+  h->noise_sigma = (double*)malloc((size_t)h->N * 8);
+  memcpy(h->noise_sigma, sigma, (size_t)h->N * 8);
   return HHD_OK;
 }
 
@@ -601,6 +613,16 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
     const double iac0 = iac_at(h, i, k), iac1 = iac_at(h, i, k + 1);
     if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i], iac0, iac1, &h->hstep[i]);
     else integrate_fixed(h, &p, x, t, h->last_spike[off + i], iac0, iac1);
+    if (h->noise_sigma && h->noise_sigma[i] != 0.0) {
+      /* Euler-Maruyama term of Brian's stochastic `euler` updater: x + dt f(x) + xi sigma, xi = sqrt(dt) N(0,1) */
+      const double sg = h->noise_sigma[i] * sqrt(h->cfg.dt_ms);
+      double z0, z1, z2, z3;
+      hhd_normal2(h->cfg.seed, (uint64_t)(off + i), (uint64_t)k, 2, &z0, &z1);
+      hhd_normal2(h->cfg.seed, (uint64_t)(off + i), (uint64_t)k, 3, &z2, &z3);
+      x[HHD_G_AMPA_OFF] = x[HHD_G_AMPA_OFF] + z0 * sg;
+      x[HHD_G_GABA_OFF] = x[HHD_G_GABA_OFF] + z1 * sg;
+      x[HHD_G_NMDA_OFF] = x[HHD_G_NMDA_OFF] + z2 * sg;
+    }
     for (int v = 0; v < 8; ++v) h->x[v][i] = x[v];
     if (!isfinite(x[HHD_V]) || !isfinite(x[HHD_W])) bad++;
   }
@@ -901,6 +923,8 @@ int hhd_comm_init(hhd_handle h, const uint8_t id[128]) { (void)id; return fail(h
 /* Plain exports of the shared math so tests can compare them with libm / a reference Philox. */
 double hhdo_exp(double x) { return hhd_exp(x); }
 double hhdo_cbrt(double x) { return hhd_cbrt(x); }
+double hhdo_log(double x) { return hhd_log(x); }
+void hhdo_normal2(uint64_t seed, uint64_t index, uint64_t step, uint32_t stream, double* z) { hhd_normal2(seed, index, step, stream, &z[0], &z[1]); }
 double hhdo_philox_u01(uint64_t seed, uint64_t index, uint64_t step, uint32_t stream) { return hhd_philox_u01(seed, index, step, stream); }
 int64_t hhdo_delay_steps(double delay_ms, double dt_ms) { return hhd_delay_steps(delay_ms, dt_ms); }
 int64_t hhdo_timestep(double t_ms, double dt_ms) { return hhd_timestep(t_ms, dt_ms); }

@@ -92,8 +92,7 @@ class CortexNetwork:
     def __init__(self, NeuPar, V0, STypPar, SynPar, SPMtx, group_distr, constant_current, fluctuating_current,
                  scales2, noise, method, time_step, simseed, simulation_dir, accum="fp64", device=0, plan="auto",
                  _engine_cls=None):
-        if isinstance(noise, (int, float)) and not isinstance(noise, bool):
-            raise NotImplementedError("the conductance-noise variant (codes/CortexNetwork.py:157-230) is not built yet (SURVEY §8f-4)")
+        self.noise = noise if (type(noise) is int or type(noise) is float) else None   # codes/CortexNetwork.py:157
         seed(simseed)
         self.time_step = float(time_step)
         self.group_distr = group_distr
@@ -143,6 +142,11 @@ class CortexNetwork:
             chan = (self.SynPar[0].astype(np.int64) - 1).astype(np.uint8)
             self.engine.set_synapses(self.source_arr, self.target_arr, chan, self.SynPar[4], self.SynPar[1],
                                      self.SynPar[2], self.SynPar[3], self.SynPar[6], self.SynPar[5])
+        if self.noise is not None:
+            # group.noise_D = noise; group.nCon[i] = incoming + outgoing synapses of i   (codes/CortexNetwork.py:391-394, 838-842);
+            # the equations add xi * sqrt(2 * noise_D * nCon) * nS/sqrt(ms) to dg_X_off/dt (:182-189)
+            nCon = np.bincount(self.target_arr, minlength=n) + np.bincount(self.source_arr, minlength=n)
+            self.engine.set_noise(np.sqrt(2 * self.noise * nCon.astype(np.float64)))
         # fluctuating_current = [start_ms, stop_ms, AC[stripe][group] expression strings in t (ms)] -> TimedArray `ta`
         # (codes/CortexNetwork.py:133-151): zeros before `start`, one sample per time step, last value held afterwards
         self.ta = []

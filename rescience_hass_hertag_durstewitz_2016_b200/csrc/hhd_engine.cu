@@ -150,6 +150,8 @@ struct Params {
   const long long* base_step;
   /* TimedArray current I_AC: table[iac_steps][iac_cols], column of local neuron i = iac_col[i] (-1: none); NULL = unused */
   const double* iac_table;
+  const double* noise_sigma;   /* [N] conductance noise, nS/sqrt(ms) (hhd_set_noise); NULL = none.  Handled by the TIMED variants. */
+  double sqrt_dt;
   const int* iac_col;
   long long iac_steps;
   int iac_cols;
@@ -575,6 +577,18 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       double hcar = METHOD == 3 ? P.hstep[i] : 0.0;
       hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S, iac0, iac1, &hcar);
       if (METHOD == 3) P.hstep[i] = hcar;
+      if (TIMED && METHOD == 0 && P.noise_sigma) {
+        /* Euler-Maruyama term of Brian's stochastic `euler` updater: x + dt f(x) + xi sigma, xi = sqrt(dt) N(0,1) */
+        const double sg = P.noise_sigma[i] * P.sqrt_dt;
+        if (sg != 0.0) {
+          double z0, z1, z2, z3;
+          hhd_normal2(P.seed, (unsigned long long)(P.off + i), (unsigned long long)k, 2, &z0, &z1);
+          hhd_normal2(P.seed, (unsigned long long)(P.off + i), (unsigned long long)k, 3, &z2, &z3);
+          x[3] = x[3] + z0 * sg;
+          x[5] = x[5] + z1 * sg;
+          x[7] = x[7] + z2 * sg;
+        }
+      }
 #endif
       bad = !(isfinite(x[0]) && isfinite(x[1]));
       /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
@@ -1792,6 +1806,21 @@ extern "C" int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_co
   return HHD_OK;
 }
 
+extern "C" int hhd_set_noise(hhd_handle h, const double* sigma) {
+  if (!h || !sigma) return fail(h, HHD_E_ARG, "null argument");
+  if (h->started) return fail(h, HHD_E_STATE, "set_noise after run");
+  if (h->cfg.method != HHD_EULER) return fail(h, HHD_E_ARG, "conductance noise needs the euler method (stochastic equations)");
+  cudaSetDevice(h->cfg.device);
+  double* ds = nullptr;
+  int rc = dev_alloc(h, &ds, (size_t)h->N, false);
+  if (!rc) rc = upload(h, ds, sigma, (size_t)h->N);
+  if (rc) return rc;
+  h->P.noise_sigma = ds;
+  h->P.sqrt_dt = sqrt(h->cfg.dt_ms);
+  h->graph_dirty = true;
+  return HHD_OK;
+}
+
 extern "C" int hhd_set_has_outgoing(hhd_handle h, const uint8_t* has_out_global) {
   if (!h || !has_out_global) return fail(h, HHD_E_ARG, "null argument");
   if (h->started) return fail(h, HHD_E_STATE, "set_has_outgoing after run");
@@ -2381,7 +2410,7 @@ static int finalize_setup(hhd_handle h) {
       CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
       int q = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, NEURON_BLOCK, NEURON_SMEM));
-      if (timed == (P.iac_table != nullptr)) occ = std::min(occ, q);
+      if (timed == (P.iac_table != nullptr || P.noise_sigma != nullptr)) occ = std::min(occ, q);
     }
     const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
     const char* env = getenv("HHD_NEURON_CTAS_PER_SM");
@@ -2423,7 +2452,7 @@ static int finalize_setup(hhd_handle h) {
   {
     const int inst = h->cfg.instance_size > 0 ? h->cfg.instance_size : h->N;
     const bool can = h->cfg.n_ranks == 1 && P.max_delay < P.refr_steps && inst <= RES_MAX_CLUSTER * RES_BLOCK && h->N % inst == 0 &&
-                     !h->cross_instance && h->NG == h->N && !P.iac_table;
+                     !h->cross_instance && h->NG == h->N && !P.iac_table && !P.noise_sigma;
     if (h->cfg.plan == HHD_PLAN_RESIDENT && !can)
       return fail(h, HHD_E_ARG, "HHD_PLAN_RESIDENT needs independent instances of at most %d neurons (instance_size), no synapse "
                   "between instances, max delay < refractory period and a single rank", RES_MAX_CLUSTER * RES_BLOCK);
@@ -2438,7 +2467,7 @@ static int finalize_setup(hhd_handle h) {
        * and smem opt-in for k_grid */
       const void* gfn[8] = {(const void*)k_grid<0>, (const void*)k_grid<1>, (const void*)k_grid<2>, (const void*)k_grid<3>,
                             (const void*)k_grid<0, true>, (const void*)k_grid<1, true>, (const void*)k_grid<2, true>, (const void*)k_grid<3, true>};
-      const int gm = h->cfg.method + (P.iac_table ? 4 : 0);
+      const int gm = h->cfg.method + ((P.iac_table || P.noise_sigma) ? 4 : 0);
       int per_sm = 0;
       CU(cudaFuncSetAttribute(gfn[gm], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfn[gm], NEURON_BLOCK, NEURON_SMEM));
@@ -2495,7 +2524,7 @@ static int launch_grid(hhd_handle h, int n_steps) {
   at[0].val.cooperative = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  const bool timed = h->P.iac_table != nullptr;
+  const bool timed = h->P.iac_table != nullptr || h->P.noise_sigma != nullptr;
   cudaError_t e;
   switch (h->cfg.method) {
     case HHD_EULER: e = timed ? cudaLaunchKernelEx(&lc, k_grid<0, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<0, false>, h->P, n_steps); break;
@@ -2555,7 +2584,7 @@ static void launch_pdl(hhd_handle h, K kernel, int grid, int block, size_t smem,
 template <bool STEP>
 static void launch_neuron(hhd_handle h, int offset) {
   typedef void (*kern_t)(const Params, const int);
-  const kern_t fn = (kern_t)neuron_fn_of<STEP>(h->cfg.method, h->P.iac_table != nullptr, STEP && h->pipelined);
+  const kern_t fn = (kern_t)neuron_fn_of<STEP>(h->cfg.method, h->P.iac_table != nullptr || h->P.noise_sigma != nullptr, STEP && h->pipelined);
   launch_pdl(h, fn, h->neuron_grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset);
 }
 

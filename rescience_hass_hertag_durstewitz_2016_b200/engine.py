@@ -27,7 +27,7 @@ FUNCTIONS = [
     "abi_version", "create", "destroy", "last_error", "set_neurons", "set_has_outgoing", "set_channels", "set_synapses",
     "add_spike_source", "add_state_monitor", "set_monitor_active", "monitor_samples", "read_monitor",
     "read_monitor_dev", "clear_monitor", "run", "spike_count", "read_spikes", "read_state", "write_state",
-    "read_syn_state", "get_counters", "current_step", "comm_unique_id", "comm_init", "profile_kernels", "set_idc", "set_synapses_dev", "set_timed_current",
+    "read_syn_state", "get_counters", "current_step", "comm_unique_id", "comm_init", "profile_kernels", "set_idc", "set_synapses_dev", "set_timed_current", "set_noise",
 ]
 
 
@@ -173,6 +173,11 @@ class Engine:
             raise ValueError("col_of_neuron must have n_neurons entries")
         self._check(self._fn("set_timed_current")(self._h, C.c_int64(table.shape[0]), C.c_int32(table.shape[1]),
                                                    _ptr(table, _dp), _ptr(col, _ip)))
+
+    def set_noise(self, sigma):
+        """Conductance noise: sigma [N] = sqrt(2 * noise_D * nCon) in nS/sqrt(ms) (euler only)."""
+        a = _f64(sigma, self.n_neurons)
+        self._check(self._fn("set_noise")(self._h, _ptr(a, _dp)))
 
     def set_has_outgoing(self, has_out_global):
         a = np.ascontiguousarray(has_out_global, dtype=np.uint8)

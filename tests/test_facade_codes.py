@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+from rescience_hass_hertag_durstewitz_2016_b200.engine import HhdError
+
 from oracle_binding import OracleEngine, golden_groups, load_golden
 from rescience_hass_hertag_durstewitz_2016_b200.codes import CortexNetwork as CN
 from rescience_hass_hertag_durstewitz_2016_b200.codes.CortexNetwork import CortexNetwork, ms, mV, pA, sourcetarget
@@ -127,7 +129,7 @@ def test_regular_and_poisson_input_drive_the_targets():
 def test_unsupported_variants_fail_loudly():
     g = load_golden("net_n200_s0")
     groups = golden_groups(g)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(HhdError):            # stochastic equations need euler, as in Brian
         CortexNetwork(g["NeuPar"], g["V0"], g["STypPar"], g["SynPar"], (g["target_arr"], g["source_arr"]), groups, [], [],
                       NOSCALE, 0.5, "rk4", 0.05, 0, "", _engine_cls=OracleEngine)
     with pytest.raises(ValueError):
@@ -150,3 +152,20 @@ def test_fluctuating_current():
     assert np.all(I[pc23, :100] == 0) and I[pc23, 100:500].max() == pytest.approx(50.0, rel=1e-3)
     assert np.all(I[pc5, 100:] == 30.0) and np.all(I[other] == 0)
     assert np.all(I[pc23, 500:] == I[pc23, 499])                      # TimedArray holds its last value
+
+
+def test_noise_variant():
+    """`noise = D` (codes/Main.py:31): noise_D = D, nCon[i] = incoming + outgoing synapses of i, Euler-Maruyama on g_X_off."""
+    g = load_golden("net_n200_s0")
+    groups = [[list(map(int, s)) for s in grp] for grp in golden_groups(g)]
+    args = (g["NeuPar"], g["V0"], g["STypPar"], g["SynPar"], (g["target_arr"], g["source_arr"]), groups, [[0] * 14], [], NOSCALE)
+    quiet = CortexNetwork(*args, False, "euler", 0.05, 1, "", _engine_cls=OracleEngine)
+    noisy = CortexNetwork(*args, 0.0005, "euler", 0.05, 1, "", _engine_cls=OracleEngine)
+    for c in (quiet, noisy):
+        c.neuron_monitors([["g", ["g_AMPA"], [["all", "all"]]]])
+        c.run(20 * ms)
+    n = g["NeuPar"].shape[1]
+    ncon = np.bincount(g["target_arr"], minlength=n) + np.bincount(g["source_arr"], minlength=n)
+    gq, gn = quiet.neuronmonitors["g"].g_AMPA, noisy.neuronmonitors["g"].g_AMPA
+    assert not gq.any() and gn[ncon > 0].std() > 0
+    assert not gn[ncon == 0].any()                                    # nCon = 0: no noise

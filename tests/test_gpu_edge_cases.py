@@ -194,3 +194,26 @@ def test_timed_current(method, plan):
         res[kind] = (e, e.read_monitor(m))
     assert same(res["gpu"][0], res["cpu"][0]) > 200
     assert np.array_equal(res["gpu"][1], res["cpu"][1])
+
+
+@pytest.mark.parametrize("plan", ["graph", "persistent", "auto"])
+def test_conductance_noise_bit_exact(plan):
+    """`noise` variant: Euler-Maruyama term from Philox normals (hhd_normal2: polar method on hhd_log) — the same numbers on
+    both sides, so the whole network run is bit-identical; the resident plan steps aside; other methods are refused."""
+    g = load_golden("net_n200_s0")
+    n = g["NeuPar"].shape[1]
+    ncon = np.bincount(g["target_arr"], minlength=n) + np.bincount(g["source_arr"], minlength=n)
+    sigma = np.sqrt(2 * 0.002 * ncon.astype(np.float64))
+    res = {}
+    for kind in ("gpu", "cpu"):
+        e = make_engine(kind, g, method="euler", accum="fixed", seed=21, **({"plan": plan} if kind == "gpu" else {}))
+        e.set_noise(sigma)
+        m = e.add_state_monitor("g_NMDA_off", np.arange(0, n, 13, dtype=np.int32))
+        e.run(4000)
+        res[kind] = (e, e.read_monitor(m))
+    assert same(res["gpu"][0], res["cpu"][0]) > 100
+    assert np.array_equal(res["gpu"][1], res["cpu"][1])
+    assert res["gpu"][1].std() > 0
+    e = make_engine("gpu", g, method="rk4")
+    with pytest.raises(HhdError):
+        e.set_noise(sigma)

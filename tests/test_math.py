@@ -94,3 +94,29 @@ def test_cbrt_within_two_ulp():
         got, ref = lib.hhdo_cbrt(float(x)), float(np.cbrt(np.longdouble(x)))
         assert abs(got - ref) <= 2 * math.ulp(ref), x
     assert lib.hhdo_cbrt(27.0) == 3.0 and lib.hhdo_cbrt(0.125) == 0.5
+
+
+def test_log_and_normals():
+    """hhd_log (<= 2 ulp away from 1) and the polar-method Gaussian pair built on it (conductance-noise variant)."""
+    lib = _lib()
+    lib.hhdo_log.restype = C.c_double
+    lib.hhdo_log.argtypes = [C.c_double]
+    lib.hhdo_normal2.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]
+    rng = np.random.default_rng(2)
+    for x in np.concatenate([rng.uniform(1e-12, 0.9, 4000), rng.uniform(1.1, 1e6, 2000), [0.5, 0.25, 2.0]]):
+        got, ref = lib.hhdo_log(float(x)), float(np.log(np.longdouble(x)))
+        assert abs(got - ref) <= 2 * math.ulp(ref), x
+    assert lib.hhdo_log(1.0) == 0.0
+    z = (C.c_double * 2)()
+    zs = []
+    for i in range(20000):
+        lib.hhdo_normal2(7, i, 123, 2, z)
+        zs += [z[0], z[1]]
+    zs = np.asarray(zs)
+    assert abs(zs.mean()) < 0.02 and abs(zs.std() - 1) < 0.02
+    assert abs(((zs - zs.mean()) ** 4).mean() / zs.var() ** 2 - 3) < 0.1
+    assert abs(np.corrcoef(zs[0::2], zs[1::2])[0, 1]) < 0.03
+    lib.hhdo_normal2(7, 5, 123, 2, z)
+    a = (z[0], z[1])
+    lib.hhdo_normal2(7, 5, 123, 2, z)
+    assert a == (z[0], z[1])                                  # a pure function of (seed, index, step, stream)

@@ -207,3 +207,29 @@ def test_timed_current_follows_timedarray_semantics():
     tau = BASE["C"] / BASE["g_L"]
     gain = 1.0 / (BASE["g_L"] * math.sqrt(1.0 + (2 * math.pi * tau / 50.0) ** 2))
     assert (V.max() - V.min()) / 2 == pytest.approx(20.0 * gain, rel=0.02)
+
+
+def test_conductance_noise_is_an_ou_process():
+    """`noise` variant (codes/CortexNetwork.py:182-189): g_X_off is an Ornstein-Uhlenbeck process, Euler-Maruyama as Brian's
+    stochastic euler does it: stationary variance sigma^2 tau / 2 (discretisation: / (1 - dt / (2 tau))), zero mean, the three
+    channels independent; the injected neuron is clamped far below threshold so nothing else moves the conductances."""
+    n, dt, steps = 256, 0.05, 40000
+    e = engine(n, np.zeros(n), dt=dt, method="euler", seed=5)
+    sigma = np.full(n, 0.05)
+    sigma[: n // 2] = 0.0
+    e.set_noise(sigma)
+    mons = [e.add_state_monitor(v, np.arange(n, dtype=np.int32)) for v in ("g_AMPA_off", "g_GABA_off", "g_NMDA_off", "g_AMPA_on")]
+    e.run(steps)
+    tau = {"g_AMPA_off": 10.0, "g_GABA_off": 40.0, "g_NMDA_off": 75.0}
+    tr = {v: e.read_monitor(m) for v, m in zip(("g_AMPA_off", "g_GABA_off", "g_NMDA_off", "g_AMPA_on"), mons)}
+    assert not tr["g_AMPA_on"].any()                         # only the _off equations carry noise
+    for v, t in tau.items():
+        x = tr[v][int(10 * t / dt):]                          # after ten time constants
+        assert not x[:, : n // 2].any()                       # sigma = 0: untouched
+        var = x[:, n // 2:].var()
+        want = 0.05 ** 2 * t / 2 / (1 - dt / (2 * t))
+        n_eff = (n // 2) * (x.shape[0] * dt) / (2 * t)         # independent samples: one per two time constants and neuron
+        assert abs(var / want - 1) < 4 * np.sqrt(2 / n_eff), (v, var, want)
+        assert abs(x[:, n // 2:].mean()) < 4 * np.sqrt(want / (x[:, n // 2:].size * dt / (2 * t)))
+    a, b = tr["g_AMPA_off"][4000:, n // 2:], tr["g_GABA_off"][4000:, n // 2:]
+    assert abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 0.02
