@@ -1,27 +1,33 @@
 /*
- * hhd_engine.cu — sm_100a engine behind the C ABI of include/hhd.h (plan HHD_PLAN_GRAPH: grid-wide kernels).
+ * hhd_engine.cu — sm_100a engine behind the C ABI of include/hhd.h.  DESIGN.md §3-5 has the full picture.
  *
- * One time step = three kernels, captured STEPS_PER_GRAPH at a time into a CUDA graph:
+ * One time step of the default (graph) plan = three kernels, captured STEPS_PER_GRAPH at a time into a CUDA graph:
  *   k_neuron      persistent CTAs, one thread per neuron and tile, SoA fp64 staged by TMA bulk copies: finish the previous
  *                 step (w_crossing test on the stored state, pending synaptic increments, reset `V=V_r; w+=b`, w_crossing
  *                 projection), sample the monitors (Brian's `start` slot), integrate the 8 ODEs (euler / rk2 / rk4 /
- *                 adaptive rk2(3)), threshold + refractoriness, append spikes to the spike ring with one atomic per
- *                 warp (ballot compaction).  Replaces NeuronGroup's stateupdater/thresholder/resetter + StateMonitor +
+ *                 gsl_rk2; TimedArray current and conductance noise in the TIMED variants), threshold + refractoriness,
+ *                 append spikes to the spike ring with one atomic per warp (ballot compaction) and note what the synaptic
+ *                 kernels need of a spike.  Replaces NeuronGroup's stateupdater/thresholder/resetter + StateMonitor +
  *                 SpikeMonitor (codes/CortexNetwork.py:304-311, 487, 510).
- *   k_spike_new   [second stream] one CTA per NEW spike, threads over that neuron's CSR row: failure draw (Philox keyed by
+ *   k_spike_new   [second stream] pathways p0..p6 for the NEW spikes in 128-synapse tasks: failure draw (Philox keyed by
  *                 synapse and step), Tsodyks–Markram update of (u, R), the amplitude the delayed pathways will add
- *                 (pathways p0..p6, codes/CortexNetwork.py:360-366), zero-delay deliveries, `last_spike_pre = t`.
- *   k_deliver     [concurrently] one warp per ACTIVE older spike (any spike not older than its neuron's longest delay):
- *                 the row is sorted by delay and carries a 16-entry bucket index; the synapses whose delay equals the
- *                 spike's age add their CURRENT amplitude to the target's pending increments (pathways p7a..p9b with
- *                 `delay = dtax`, :367-372,463-468).  The spike history itself is the delay queue: no per-event queue
- *                 memory, bounded by one spike per neuron per refractory period, and values are read at delivery time
- *                 exactly as Brian's SpikeQueue does.  SpikeGeneratorGroup events (:570-622) as well.
+ *                 (codes/CortexNetwork.py:360-366), zero-delay deliveries; with delays beyond the refractory period also the
+ *                 deliveries that are due from older spikes of the same neuron.
+ *   k_deliver     [concurrently] one LANE per ACTIVE older spike: the row is sorted by delay and has per-delay offsets, so
+ *                 the lane gets exactly the synapses whose delay equals the spike's age; the warp walks its lanes'
+ *                 segments together and adds their CURRENT amplitudes to the targets' pending increments (pathways
+ *                 p7a..p9b with `delay = dtax`, :367-372,463-468).  The spike history itself is the delay queue: no
+ *                 per-event queue memory, bounded by one spike per neuron per refractory period, and values are read at
+ *                 delivery time exactly as Brian's SpikeQueue does.  SpikeGeneratorGroup events (:570-622) as well.
+ *   k_exchange    [partitioned networks] this step's spike lists, every rank to every rank, as stores + flags into
+ *                 IPC-mapped peer memory; ncclAllGather + k_append when the buffers cannot be mapped.
+ * Other plans on the same phase functions: k_resident (one thread-block cluster per small independent network, whole
+ * segments in one launch), k_grid (cooperative whole-run kernel, opt-in), k_neuron<.., PIPE> (one launch per step, opt-in).
  *
- * Data layout in HBM: structure of arrays, fp64; per neuron 8 state + 12 parameter doubles + last_spike + int32
- * lastspike step + 1 flag byte (≈ 240 B read+written per neuron-update, the roofline figure of SURVEY §8d);
- * per synapse (CSR by presynaptic neuron, sorted by delay) tgt int32, delay uint16, chan uint8, 5 fp64 parameters,
- * u, R, amplitude, original index uint32 (≈ 75 B).
+ * Data layout in HBM: structure of arrays, fp64; per neuron 8 state + 12 parameter doubles + last_spike + int32 meta word
+ * (≈ 240 B read+written per neuron-update, the roofline figure of SURVEY §8d); per synapse (CSR by presynaptic neuron,
+ * sorted by delay) a 16-byte record {target, delay, channel, amplitude} and a 64-byte record {U, tau_rec, tau_fac, g_max,
+ * p_fail, u, R, original index}.
  */
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
