@@ -1121,6 +1121,80 @@ __global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant
  * edges per step of the graph plan (~10 us of a 66 us step at 1M neurons).  Same phase functions, same results.
  * Requires max_delay < refractory steps and a single rank.
  * ================================================================================================================== */
+/*
+ * The exchange of a partitioned network as ONE launch over peer memory instead of ncclAllGather + k_append (the all-gather
+ * costs 18-20 us per step for half a kilobyte of spikes; this is a store over NVLink and a flag).  The block writes this
+ * rank's (count, ids...) list of step k into slot [k & 1][rank] of EVERY rank's receive buffer, fences, raises its flag
+ * (k + 1) on every rank, waits until every rank's flag in its own buffer has reached k + 1, and appends all lists to the
+ * ring in rank order exactly as k_append does.  Two parities suffice: a rank can only write step k + 2 after it has
+ * consumed everybody's step k + 1, which a peer only sends after it has consumed step k.  A peer that does not arrive
+ * within 20 s (it died) is reported through CNT_TIMEOUT instead of hanging the device.
+ */
+/* (one CTA; also called by block 0 of the cooperative whole-run kernel) */
+__device__ __forceinline__ void exchange_phase(const Params& P, const long long k) {
+  const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
+  const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
+  __shared__ unsigned long long base_sh[MAX_RANKS + 1];
+  const int n_mine = min(P.xchg_send[0], P.xchg_cap);
+  for (int r = 0; r < P.n_ranks; ++r) {
+    int* dst = P.peer_buf[r] + ((size_t)par * P.n_ranks + me) * slot;
+    for (int q = tid; q < n_mine; q += blockDim.x) dst[1 + q] = P.xchg_send[1 + q];
+    if (tid == 0) dst[0] = n_mine;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < P.n_ranks) {
+    volatile int* flag = P.peer_buf[tid] + flags_off + me;
+    *flag = (int)(k + 1);
+    __threadfence_system();
+    volatile int* mine = P.peer_buf[me] + flags_off + tid;
+    if (!*(volatile unsigned int*)P.xchg_dead) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*mine < (int)(k + 1)) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) {
+          *P.xchg_dead = 1u;
+          atomicAdd(&P.counters[CNT_TIMEOUT], 1ull);
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int* recv = P.peer_buf[me] + (size_t)par * P.n_ranks * slot;
+  if (tid == 0) {
+    unsigned long long b = *P.head;
+    for (int r = 0; r < P.n_ranks; ++r) {
+      base_sh[r] = b;
+      b += (unsigned long long)min(max(__ldcg(recv + (size_t)r * slot), 0), P.xchg_cap);
+    }
+    base_sh[P.n_ranks] = b;
+  }
+  __syncthreads();
+  for (int r = 0; r < P.n_ranks; ++r) {
+    const int* src = recv + (size_t)r * slot;
+    const int n = (int)(base_sh[r + 1] - base_sh[r]);
+    for (int q = tid; q < n; q += blockDim.x) {
+      const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
+      const int j = __ldcg(src + 1 + q);             /* written by another GPU: not through this SM's L1 */
+      P.spk_neuron[pos] = j;
+      P.spk_step[pos] = (int)k;
+      note_spike(P, j, (int)k, (double)k * P.dt);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *P.head = base_sh[P.n_ranks];
+    P.xchg_send[0] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Params P, const int step_offset) {
+  exchange_phase(P, *P.base_step + step_offset);
+}
+
 /* Grid-wide barrier for a cooperative launch (every CTA resident): one release-add per CTA on a monotone counter, one
  * thread per CTA spins with acquire loads.  The gpu-scope fences also invalidate the SM's L1 (CCTL.IVALL), so data other
  * SMs wrote before the barrier is re-read from L2 afterwards.  Measured ~4x cheaper than cooperative_groups' grid.sync()
@@ -1153,8 +1227,18 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
     neuron_phase<METHOD, true, TIMED, false>(P, k, st, sh, bar_parity);
     arrived += gridDim.x;
     grid_barrier(P.grid_bar, arrived);
-    spike_new_phase<false>(P, k);
-    deliver_phase<DELIVER_FUSED>(P, k);
+    if (P.n_ranks > 1) {                 /* partitioned network: block 0 exchanges the step's spikes over peer memory */
+      if (blockIdx.x == 0) exchange_phase(P, k);
+      arrived += gridDim.x;
+      grid_barrier(P.grid_bar, arrived);
+    }
+    if (P.max_delay < P.refr_steps) {
+      spike_new_phase<false>(P, k);
+      deliver_phase<DELIVER_FUSED>(P, k);
+    } else {
+      spike_new_phase<true>(P, k);
+      deliver_phase<DELIVER_MAIN>(P, k);
+    }
     arrived += gridDim.x;
     grid_barrier(P.grid_bar, arrived);
   }
@@ -1460,76 +1544,6 @@ __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    *P.head = base_sh[P.n_ranks];
-    P.xchg_send[0] = 0;
-  }
-}
-
-/*
- * The exchange of a partitioned network as ONE launch over peer memory instead of ncclAllGather + k_append (the all-gather
- * costs 18-20 us per step for half a kilobyte of spikes; this is a store over NVLink and a flag).  The block writes this
- * rank's (count, ids...) list of step k into slot [k & 1][rank] of EVERY rank's receive buffer, fences, raises its flag
- * (k + 1) on every rank, waits until every rank's flag in its own buffer has reached k + 1, and appends all lists to the
- * ring in rank order exactly as k_append does.  Two parities suffice: a rank can only write step k + 2 after it has
- * consumed everybody's step k + 1, which a peer only sends after it has consumed step k.  A peer that does not arrive
- * within 20 s (it died) is reported through CNT_TIMEOUT instead of hanging the device.
- */
-__global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Params P, const int step_offset) {
-  const long long k = *P.base_step + step_offset;
-  const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
-  const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
-  __shared__ unsigned long long base_sh[MAX_RANKS + 1];
-  const int n_mine = min(P.xchg_send[0], P.xchg_cap);
-  for (int r = 0; r < P.n_ranks; ++r) {
-    int* dst = P.peer_buf[r] + ((size_t)par * P.n_ranks + me) * slot;
-    for (int q = tid; q < n_mine; q += blockDim.x) dst[1 + q] = P.xchg_send[1 + q];
-    if (tid == 0) dst[0] = n_mine;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < P.n_ranks) {
-    volatile int* flag = P.peer_buf[tid] + flags_off + me;
-    *flag = (int)(k + 1);
-    __threadfence_system();
-    volatile int* mine = P.peer_buf[me] + flags_off + tid;
-    if (!*(volatile unsigned int*)P.xchg_dead) {
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (*mine < (int)(k + 1)) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) {
-          *P.xchg_dead = 1u;
-          atomicAdd(&P.counters[CNT_TIMEOUT], 1ull);
-          break;
-        }
-      }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  const int* recv = P.peer_buf[me] + (size_t)par * P.n_ranks * slot;
-  if (tid == 0) {
-    unsigned long long b = *P.head;
-    for (int r = 0; r < P.n_ranks; ++r) {
-      base_sh[r] = b;
-      b += (unsigned long long)min(max(__ldcg(recv + (size_t)r * slot), 0), P.xchg_cap);
-    }
-    base_sh[P.n_ranks] = b;
-  }
-  __syncthreads();
-  for (int r = 0; r < P.n_ranks; ++r) {
-    const int* src = recv + (size_t)r * slot;
-    const int n = (int)(base_sh[r + 1] - base_sh[r]);
-    for (int q = tid; q < n; q += blockDim.x) {
-      const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
-      const int j = __ldcg(src + 1 + q);             /* written by another GPU: not through this SM's L1 */
-      P.spk_neuron[pos] = j;
-      P.spk_step[pos] = (int)k;
-      note_spike(P, j, (int)k, (double)k * P.dt);
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
     *P.head = base_sh[P.n_ranks];
     P.xchg_send[0] = 0;
   }
@@ -2477,9 +2491,9 @@ static int finalize_setup(hhd_handle h) {
       int per_sm = 0;
       CU(cudaFuncSetAttribute(gfn[gm], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfn[gm], NEURON_BLOCK, NEURON_SMEM));
-      const bool gcan = HHD_NEURON_PREFETCH >= 2 && h->cfg.n_ranks == 1 && h->fused && per_sm > 0 && h->NG == h->N;
+      const bool gcan = HHD_NEURON_PREFETCH >= 2 && per_sm > 0 && (h->cfg.n_ranks == 1 ? h->NG == h->N : h->p2p);
       if (h->cfg.plan == HHD_PLAN_PERSISTENT && !gcan)
-        return fail(h, HHD_E_ARG, "HHD_PLAN_PERSISTENT needs max delay < refractory period and a single rank");
+        return fail(h, HHD_E_ARG, "HHD_PLAN_PERSISTENT: a partitioned network needs the peer-memory spike exchange");
       const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
       const int ggrid = std::max(1, std::min(tiles, h->sm_count * per_sm));
       h->gridplan = !h->resident && gcan &&

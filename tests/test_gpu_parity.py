@@ -62,11 +62,12 @@ def test_network_fixed_accumulation_bit_exact(method, plan):
         assert gc[k] == cc[k], k
 
 
-def test_multicolumn_long_delays_fixed_bit_exact():
+@pytest.mark.parametrize("plan", ["auto", "persistent"])
+def test_multicolumn_long_delays_fixed_bit_exact(plan):
     """5 columns: inter-column delays exceed the refractory period, so a second spike can change the amplitude of a
     delivery still in flight — both engines must agree on that too."""
     g = load_golden("net_n60x5_s1")
-    gpu, cpu = pair(g, method="rk2", accum="fixed", seed=3)
+    gpu, cpu = gpu_cpu(g, plan, method="rk2", accum="fixed", seed=3)
     assert gpu.read_syn_state("delay_steps").max() > 100
     for e in (gpu, cpu):
         e.run(20000)

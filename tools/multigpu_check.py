@@ -26,7 +26,7 @@ def main():
         gnet, locs = partition_network(g["NeuPar"], g["V0"], g["SynPar"], g["source_arr"], g["target_arr"], default_idc(g), world)
         loc = locs[rank]
         e = Engine(loc["n_local"], 0.05, method="rk2", accum="fixed", seed=23, device=lr, rank=rank, n_ranks=world,
-                   n_global=loc["n_global"], global_offset=loc["global_offset"], plan="graph")
+                   n_global=loc["n_global"], global_offset=loc["global_offset"], plan=os.environ.get("HHD_CHECK_PLAN", "graph"))
         load_partition(e, loc, g["STypPar"])
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
