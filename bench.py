@@ -195,7 +195,7 @@ def cpu_sample(args, seconds, threads):
     t0 = time.perf_counter()
     e.run(5)
     per = max((time.perf_counter() - t0) / 5, 1e-7)
-    nsteps = int(max(4, min(args.window * 2, seconds / per)))
+    nsteps = int(max(4, min(args.window * 20, seconds / per)))     # about `seconds` of CPU work, at most 2 s of biological time
     t0 = time.perf_counter()
     e.run(nsteps)
     el = time.perf_counter() - t0
