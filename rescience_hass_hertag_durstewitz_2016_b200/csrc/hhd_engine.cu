@@ -1136,17 +1136,18 @@ __device__ __forceinline__ void exchange_phase(const Params& P, const long long 
   const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
   __shared__ unsigned long long base_sh[MAX_RANKS + 1];
   const int n_mine = min(P.xchg_send[0], P.xchg_cap);
-  for (int r = 0; r < P.n_ranks; ++r) {
+  /* one warp per peer, all peers at once: list, system-scope fence by every writing lane, then the flag */
+  const int lane = tid & 31, warp = tid >> 5, n_warps = (int)blockDim.x >> 5;
+  for (int r = warp; r < P.n_ranks; r += n_warps) {
     int* dst = P.peer_buf[r] + ((size_t)par * P.n_ranks + me) * slot;
-    for (int q = tid; q < n_mine; q += blockDim.x) dst[1 + q] = P.xchg_send[1 + q];
-    if (tid == 0) dst[0] = n_mine;
+    for (int q = lane; q < n_mine; q += 32) dst[1 + q] = P.xchg_send[1 + q];
+    if (lane == 0) dst[0] = n_mine;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *(volatile int*)(P.peer_buf[r] + flags_off + me) = (int)(k + 1);
   }
-  __threadfence_system();
   __syncthreads();
   if (tid < P.n_ranks) {
-    volatile int* flag = P.peer_buf[tid] + flags_off + me;
-    *flag = (int)(k + 1);
-    __threadfence_system();
     volatile int* mine = P.peer_buf[me] + flags_off + tid;
     if (!*(volatile unsigned int*)P.xchg_dead) {
       unsigned long long t0, t1;
