@@ -2443,6 +2443,8 @@ static int finalize_setup(hhd_handle h) {
   h->stp_grid = h->sm_count * 4;
   h->deliver_grid = h->sm_count * 16;          /* 16 CTAs x 128 threads = one full wave; >= 1 warp per active spike at 1M neurons */
   if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
+  if (getenv("HHD_DELIVER_CTAS_PER_SM") && atoi(getenv("HHD_DELIVER_CTAS_PER_SM")) > 0) h->deliver_grid = h->sm_count * atoi(getenv("HHD_DELIVER_CTAS_PER_SM"));
+  if (getenv("HHD_STP_CTAS_PER_SM") && atoi(getenv("HHD_STP_CTAS_PER_SM")) > 0) h->stp_grid = h->sm_count * atoi(getenv("HHD_STP_CTAS_PER_SM"));
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
     unsigned short* rmax = nullptr;
