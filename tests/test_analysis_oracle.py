@@ -62,3 +62,17 @@ def test_abi_exports_analysis_symbols():
     for name in ("hhd_an_words", "hhd_an_binned_trains", "hhd_an_lagged_counts", "hhd_an_isi_stats"):
         assert hasattr(lib, name), name
     assert lib.hhd_an_words(ctypes.c_int64(64)) == 2
+
+
+def test_analyses_have_no_cpu_fallback():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the failure path is exercised on the CPU box")
+    from rescience_hass_hertag_durstewitz_2016_b200 import analysis as an
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import HhdError
+    from rescience_hass_hertag_durstewitz_2016_b200.codes import AuxiliarEquations as AE
+    with pytest.raises(HhdError):
+        an.lagged_counts(an.pack_bits(np.eye(3, 70, dtype=int)), 70, [0, 1])
+    with pytest.raises(HhdError):
+        AE.Zero_lag_Pearson_correlation_group([np.array([1.0, 5.0]), np.array([2.0])], 0.0, 10.0, 1.0)
