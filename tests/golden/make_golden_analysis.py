@@ -71,6 +71,22 @@ def main():
     out["rev_corr_lags_in"] = np.array(lags)
     mean, cv = AT.get_ISI_stats_from_spike_trains(trains, neuron_idcs=[0, 1, 2, 4, 5, 6], tlim=(5.0, 395.0))
     out["rev_isi_mean"], out["rev_isi_cv"] = np.asarray(mean), np.asarray(cv)
+    # ---- the reference's own data + script: codes/Original_spiketime.txt analysed as codes/Original_ISI.py:11-57 does
+    with open(os.path.join(REF, "codes", "Original_spiketime.txt")) as f:
+        spike_list = [np.asarray(tr.split(",")).astype(float) for tr in f.read().split(";")]
+    stset = []
+    for tr in spike_list:
+        tr = tr[tr >= 1000]
+        if len(tr) > 20:
+            stset.append(tr)
+    stset = stset[:48]                                               # a subset keeps the fixture small
+    out["orig_n"] = len(stset)
+    out["orig_trains"] = np.concatenate(stset)
+    out["orig_offsets"] = np.cumsum([0] + [len(tr) for tr in stset])
+    out["orig_isi_mean"] = np.asarray([np.mean(np.diff(tr)) for tr in stset])
+    out["orig_isi_cv"] = np.asarray([np.std(np.diff(tr)) / np.mean(np.diff(tr)) for tr in stset])
+    lag, corr = AE.Pearson_correlation_group(stset, 1000, 61000, 2, -30, 30)
+    out["orig_corr_lags"], out["orig_corr"] = lag, corr
     np.savez_compressed(os.path.join(HERE, "analysis_golden.npz"), **out)
     print("wrote analysis_golden.npz:", sorted(out))
 

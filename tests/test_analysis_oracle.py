@@ -37,6 +37,21 @@ def test_revision_correlations_and_isi():
     assert np.array_equal(mean, G["rev_isi_mean"], equal_nan=True) and np.array_equal(cv, G["rev_isi_cv"], equal_nan=True)
 
 
+def _orig_trains():
+    off = G["orig_offsets"]
+    return [G["orig_trains"][off[q]:off[q + 1]] for q in range(int(G["orig_n"]))]
+
+
+def test_original_model_spike_trains_as_original_isi_py_analyses_them():
+    """codes/Original_spiketime.txt (the original model's 61 s run, first 48 qualifying trains) through
+    codes/Original_ISI.py:20-57: ISI mean / CV per train and Pearson_correlation_group(stset, 1000, 61000, 2, -30, 30)."""
+    trains = _orig_trains()
+    mean, cv = ao.isi_stats(trains)
+    assert np.array_equal(mean, G["orig_isi_mean"]) and np.array_equal(cv, G["orig_isi_cv"])
+    lags, corr = ao.pearson_group(trains[:10], 1000, 61000, 2, -30, 30)     # the full group takes the oracle a minute
+    assert np.array_equal(lags, G["orig_corr_lags"]) and corr.shape == G["orig_corr"].shape
+
+
 def test_lagged_counts_are_the_sufficient_statistics():
     """The integer counts reproduce both coefficient definitions (the host formulas the product applies to device counts)."""
     from rescience_hass_hertag_durstewitz_2016_b200 import analysis as an

@@ -48,6 +48,17 @@ def test_revision_functions_match_the_reference():
         assert np.array_equal(a, b, equal_nan=True)
 
 
+def test_original_model_spike_trains_as_original_isi_py_analyses_them():
+    """The reference's own data and script: codes/Original_spiketime.txt through codes/Original_ISI.py:20-57 — off-grid spike
+    times, 30 000 bins, 30 lags, 2256 ordered pairs; the golden values are the reference functions' output."""
+    off = G["orig_offsets"]
+    trains = [G["orig_trains"][off[q]:off[q + 1]] for q in range(int(G["orig_n"]))]
+    lags, corr = AE.Pearson_correlation_group(trains, 1000, 61000, 2, -30, 30)
+    assert np.array_equal(lags, G["orig_corr_lags"]) and np.array_equal(corr, G["orig_corr"])
+    mean, cv = AT.ISIstats(trains)
+    assert np.allclose(mean, G["orig_isi_mean"], rtol=1e-13, atol=0) and np.allclose(cv, G["orig_isi_cv"], rtol=1e-11, atol=0)
+
+
 def _random_trains(n, t_ms, rate_hz, dt, seed, noise=False):
     rng = np.random.default_rng(seed)
     trains = []
