@@ -5,7 +5,8 @@ the GPU against the numbers the paper publishes — the only way the chaotic dyn
 Published (content.tex:239, 318, 359, 382): mean ISI 523 +- 655 ms (rk4), 511 +- 665 (gsl_rk2), 516 +- 680 (original model);
 CV 1.13 +- 0.49 / 0.97 +- 0.45 / 1.10 +- 0.45; spiking neurons (> 10 spikes / 30 s) 20.66 +- 2.55 % (range 16.95-27.62),
 pyramidal cells 12.28 +- 2.81 % (8.12-20.12) over 25 network realisations.  Measured here on B200 (round 1, seeds 0-2,
-one network realisation): mean ISI 412-435 +- 570-596 ms, CV 0.93-0.94 +- 0.45, spiking 19.1-19.7 %, PC 10.9-11.5 %.
+one network realisation): mean ISI 412-435 +- 570-596 ms, CV 0.93-0.94 +- 0.45, spiking 19.1-19.7 %, PC 10.9-11.5 % (rk4);
+405-421 +- 549-557 ms, CV 0.94-0.95, 19.3-19.4 %, PC 11.1-11.3 % (gsl_rk2).
 Tolerances: mean ISI within -35 % / +35 % of 523 ms, CV within 0.25 of 1.10, fractions inside the published ranges.
 """
 import os
@@ -21,11 +22,12 @@ from oracle_binding import golden_groups, load_golden
 pytestmark = pytest.mark.gpu
 
 
-def test_isi_statistics_match_the_paper_regime():
+@pytest.mark.parametrize("method", ["rk4", "gsl_rk2"])      # codes/Main_ISI.py and codes/Mainrk2_ISI.py
+def test_isi_statistics_match_the_paper_regime(method):
     from longrun_stats import stats
     g = load_golden("net_n1000_s0_full")
     n = g["NeuPar"].shape[1]
-    e = make_engine("gpu", g, method="rk4", seed=0)
+    e = make_engine("gpu", g, method={"gsl_rk2": "rk23"}.get(method, method), seed=0)
     e.run(int(61000 / 0.05))
     i, s = e.spikes()
     st = stats(i, s, n, 0.05, 61000.0, golden_groups(g))
