@@ -18,7 +18,7 @@ import numpy as np
 from ..engine import Engine, channels_from_STypPar, gsyn_factors, neuron_rows_from_NeuPar
 from ..monitors import SpikeMonitorView, StateMonitorView
 from ..units import *  # noqa: F401,F403  (the scripts get ms, mV, pA ... through `from CortexNetwork import *`)
-from .. import units
+from .. import stimuli, units
 
 GROUP_NAMES = ["PC_L23", "IN_L_L23", "IN_L_d_L23", "IN_CL_L23", "IN_CL_AC_L23", "IN_CC_L23", "IN_F_L23",
                "PC_L5", "IN_L_L5", "IN_L_d_L5", "IN_CL_L5", "IN_CL_AC_L5", "IN_CC_L5", "IN_F_L5"]
@@ -191,78 +191,18 @@ class CortexNetwork:
                                   "(codes/CortexNetwork.py:521) and is unused by every script")
 
     # ---- external input -------------------------------------------------------------------------------------------------
-    def _attach_sources(self, n_sources, spk_src, spk_t, syn_src, syn_tgt, syn_type, syn_gmax, pfail):
-        syn_type = np.asarray(syn_type)
-        mask = np.where(syn_type == 1, 0b101, 0b010).astype(np.uint8)   # type 1 feeds AMPA and NMDA, type 2 GABA (:609-611)
-        dt = self.time_step
-        steps = np.floor((np.asarray(spk_t, dtype=np.float64) + 1e-3 * dt) / dt).astype(np.int64)
-        pairs = np.stack([np.asarray(spk_src, dtype=np.int64), steps], axis=1) if len(steps) else np.zeros((0, 2), dtype=np.int64)
-        if len(pairs) and len(np.unique(pairs, axis=0)) != len(pairs):
-            raise ValueError("a source spikes more than once during one time step (SpikeGeneratorGroup refuses that as well)")
-        self.engine.add_spike_source(n_sources, spk_src, spk_t, syn_src, syn_tgt, mask, syn_gmax, np.full(len(syn_src), float(pfail)))
-
     def poisson_input(self, PoissonInput):
         """[[N, type, rate_Hz, g_max_nS, p_fail, start_ms, stop_ms, [[group, stripe, pCon], ...]], ...]
-        (codes/CortexNetwork.py:525-622).  Spike times: cumulative sums of exponential intervals clipped below at one
-        time step, drawn with np.random in the reference's order."""
-        spk_src, spk_t, syn_src, syn_tgt, syn_type, syn_gmax = [], [], [], [], [], []
-        n_tot, pfail = 0, 0.0
-        for n_inp, type_inp, freq, gmax, pfail, start, stop, targets in PoissonInput:
-            src_all, tgt_all = [], []
-            inp_group = np.arange(n_tot, n_tot + n_inp)
-            for i in range(n_inp):
-                lamb = 1000 / freq
-                n_draw = int(round(2 * (stop - start) / lamb, 0))
-                # np.clip(x, time_step, np.NaN) in the reference (:547): with the numpy it pins (1.16) a NaN bound is ignored,
-                # i.e. intervals are only bounded below by one time step
-                t = start + np.cumsum(np.maximum(-lamb * np.log(1 - np.random.rand(n_draw)), self.time_step))
-                t = t[t < stop]
-                spk_t.extend(t)
-                spk_src.extend([n_tot + i] * len(t))
-                for group, stripe, pcon in targets:
-                    target_group = np.asarray(self.group_distr[group][stripe]).astype(np.int64)
-                    n_target = int(round(pcon * len(target_group), 0))
-                    order = list(range(len(target_group) * n_inp))
-                    np.random.shuffle(order)
-                    pick = np.asarray(order[:n_target], dtype=np.int64)
-                    tgt_all.extend(target_group[pick // n_inp])
-                    src_all.extend(inp_group[pick % n_inp])
-            syn_src.extend(src_all)
-            syn_tgt.extend(tgt_all)
-            syn_type.extend([type_inp] * len(src_all))
-            syn_gmax.extend([gmax] * len(src_all))
-            n_tot += n_inp
-        # `poissonsynapse.failure_rate = pfailinp`: the LAST set's value applies to all sets (:613; SURVEY App. B.2)
-        self._attach_sources(n_tot, spk_src, spk_t, syn_src, syn_tgt, syn_type, syn_gmax, pfail)
-        self.poisson_spikes = (np.asarray(spk_src), np.asarray(spk_t) * units.ms)
+        (codes/CortexNetwork.py:525-622); drawn by stimuli.draw_poisson_input with np.random in the reference's order."""
+        s = stimuli.draw_poisson_input(PoissonInput, self.group_distr, self.time_step)
+        stimuli.attach(self.engine, s, self.time_step)
+        self.poisson_spikes = (s["spk_src"], s["spk_t"] * units.ms)
 
     def regular_input(self, RegularInput):
         """[[N, type, n_spikes, g_max_nS, p_fail, start_ms, stop_ms, targets], ...]   (codes/CortexNetwork.py:624-719)"""
-        spk_src, spk_t, syn_src, syn_tgt, syn_type, syn_gmax = [], [], [], [], [], []
-        n_tot, pfail = 0, 0.0
-        for n_inp, type_inp, n_spikes, gmax, pfail, start, stop, targets in RegularInput:
-            if (stop - start) / (n_spikes - 1) < self.time_step:
-                print("WARNING: time step is larger than spikes intervals")
-            src_all, tgt_all = [], []
-            inp_group = np.arange(n_tot, n_tot + n_inp)
-            for i in range(n_inp):
-                spk_t.extend(np.linspace(start, stop, n_spikes))
-                spk_src.extend([n_tot + i] * n_spikes)
-                for group, stripe, pcon in targets:
-                    target_group = np.asarray(self.group_distr[group][stripe]).astype(np.int64)
-                    n_target = int(round(pcon * len(target_group), 0))
-                    order = list(range(len(target_group) * n_inp))
-                    np.random.shuffle(order)
-                    pick = np.asarray(order[:n_target], dtype=np.int64)
-                    tgt_all.extend(target_group[pick // n_inp])
-                    src_all.extend(inp_group[pick % n_inp])
-            syn_src.extend(src_all)
-            syn_tgt.extend(tgt_all)
-            syn_type.extend([type_inp] * len(src_all))
-            syn_gmax.extend([gmax] * len(src_all))
-            n_tot += n_inp
-        self._attach_sources(n_tot, spk_src, spk_t, syn_src, syn_tgt, syn_type, syn_gmax, pfail)
-        self.regular_spikes = (np.asarray(spk_src), np.asarray(spk_t) * units.ms)
+        s = stimuli.draw_regular_input(RegularInput, self.group_distr, self.time_step)
+        stimuli.attach(self.engine, s, self.time_step)
+        self.regular_spikes = (s["spk_src"], s["spk_t"] * units.ms)
 
     # ---- run --------------------------------------------------------------------------------------------------------------
     def run(self, t):
@@ -272,13 +212,14 @@ class CortexNetwork:
 
     # ---- index helpers (codes/CortexNetwork.py:820-984) ---------------------------------------------------------------
     def get_source_from_target(self, ind):
-        return self.source_arr[np.where(self.target_arr == ind)[0]]
+        return self.source_arr[np.where(np.isin(self.target_arr, ind))[0]]        # scalar or array, as the reference (:820-826)
 
     def get_target_from_source(self, ind):
-        return self.target_arr[np.where(self.source_arr == ind)[0]]
+        return self.target_arr[np.where(np.isin(self.source_arr, ind))[0]]
 
     def get_connections_count(self, ind):
-        return len(self.get_source_from_target(ind))
+        """incoming + outgoing synapses (codes/CortexNetwork.py:838-842: the nCon of the noise term)"""
+        return len(self.get_source_from_target(ind)) + len(self.get_target_from_source(ind))
 
     def get_neurons_from_synapses(self, ind):
         return self.target_arr[ind], self.source_arr[ind]

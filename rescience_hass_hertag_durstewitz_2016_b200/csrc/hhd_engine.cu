@@ -2045,7 +2045,14 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     P.row_bkt = bkt;
   }
   P.row_doff = nullptr;
-  if ((size_t)h->NG * (size_t)(maxd + 2) * 2 <= ((size_t)4 << 30)) {     /* per-delay offsets: lane-per-spike delivery */
+  {
+    /* an STP task is one block of a spiking neuron's row: as many tasks per spike as 1.25 mean rows need.  Needed by
+     * k_spike_new whichever delivery index is built below. */
+    const double mean_row = (double)nsyn / std::max(1, h->NG);
+    P.stp_chunks = std::max(1, (int)std::ceil(1.25 * mean_row / NEURON_BLOCK));
+  }
+  /* HHD_NO_DOFF=1 forces the 16-bucket fallback index (tests) */
+  if (!getenv("HHD_NO_DOFF") && (size_t)h->NG * (size_t)(maxd + 2) * 2 <= ((size_t)4 << 30)) {     /* per-delay offsets: lane-per-spike delivery */
     unsigned short* doff = nullptr;
     int* dmax_row = nullptr;
     const int stride = maxd + 2;
@@ -2061,9 +2068,6 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     if (max_row < 65536) {
       P.row_doff = doff;
       P.doff_stride = stride;
-      /* an STP task is one block of a spiking neuron's row: as many tasks per spike as 1.25 mean rows need */
-      const double mean_row = (double)nsyn / std::max(1, h->NG);
-      P.stp_chunks = std::max(1, (int)std::ceil(1.25 * mean_row / NEURON_BLOCK));
     } else {
       dev_free(h, doff);
     }
@@ -2461,6 +2465,7 @@ static int finalize_setup(hhd_handle h) {
     P.doff_stride = 2;
     P.stp_chunks = 1;
   }
+  if (P.stp_chunks < 1) return fail(h, HHD_E_STATE, "internal: stp_chunks not set");
   h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
   h->kernels_per_step = 3;
   /* pipelined schedule: graph plan, single rank, no neuron with a new spike and an undelivered older one */

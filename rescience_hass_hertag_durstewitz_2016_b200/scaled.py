@@ -27,6 +27,52 @@ def tile_columns(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_columns, ji
                 I_DC=idc, n_per_column=n1)
 
 
+# BASELINE config 3 (codes/Main_poisson.py:29-30, 145-150; codes/Main_regular.py:29-30, 165-172): dt = 0.01 ms, 4 s,
+# Poisson = 100 sources x 30 Hz x 100 ms, 2 nS, pCon 0.1 onto PC_L23 at 1000 ms and onto PC_L5 at 2500 ms;
+# regular = 1 source, 250 spikes in 5 ms at 1000 ms and 500 spikes in 5 ms at 2500 ms, 0.1 nS, pCon 0.1 onto PC_L23.
+POISSON_STIMULI = [[100, 1, 30, 2, 0, 1000, 1100, [[0, 0, 0.1]]], [100, 1, 30, 2, 0, 2500, 2600, [[7, 0, 0.1]]]]
+REGULAR_STIMULI = [[1, 1, 250, 0.1, 0, 1000, 1005, [[0, 0, 0.1]]], [1, 1, 500, 0.1, 0, 2500, 2505, [[0, 0, 0.1]]]]
+
+
+def shift_stimuli(stimuli_list, factor):
+    """The same stimulus sets with their times scaled (tests run a shortened protocol)."""
+    return [[a, b, c, d, e, t0 * factor, t0 * factor + (t1 - t0), tg] for a, b, c, d, e, t0, t1, tg in stimuli_list]
+
+
+def instances_with_stimuli(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, group_distr, n_instances, dt,
+                           poisson=None, regular=None, seed=0):
+    """BASELINE config 3: `n_instances` independent copies of one column in ONE engine (no synapse between copies), each
+    with its OWN draw of the Poisson / regular stimuli — instance q draws with np.random.seed(seed + q) exactly as a
+    separate run of codes/Main_poisson.py / Main_regular.py would (stimuli.draw_*).  Even instances get the Poisson
+    protocol, odd ones the regular protocol when both are given.
+    -> (network dict of tile_columns, stimulus dict for Engine.add_spike_source with global source / target ids)."""
+    from . import stimuli as st
+    net = tile_columns(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_instances)
+    n1 = net["n_per_column"]
+    parts, n_src = [], 0
+    state = np.random.get_state()
+    try:
+        for q in range(int(n_instances)):
+            np.random.seed(int(seed) + q)
+            use_poisson = poisson is not None and (regular is None or q % 2 == 0)
+            s = st.draw_poisson_input(poisson, group_distr, dt) if use_poisson else st.draw_regular_input(regular, group_distr, dt)
+            st.check_one_spike_per_step(s["spk_src"], s["spk_t"], dt)
+            parts.append(dict(spk_src=s["spk_src"] + n_src, spk_t=s["spk_t"], syn_src=s["syn_src"] + n_src,
+                              syn_tgt=s["syn_tgt"] + q * n1, mask=st.channel_mask(s["syn_type"]), gmax=s["syn_gmax"],
+                              pfail=np.full(len(s["syn_src"]), s["pfail"])))
+            n_src += s["n_sources"]
+    finally:
+        np.random.set_state(state)
+    stim = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    stim["n_sources"] = n_src
+    return net, stim
+
+
+def attach_stimuli(engine, stim):
+    engine.add_spike_source(stim["n_sources"], stim["spk_src"], stim["spk_t"], stim["syn_src"], stim["syn_tgt"], stim["mask"],
+                            stim["gmax"], stim["pfail"])
+
+
 def tile_synapses_device(SynPar, source_arr, target_arr, n_columns, n_per_column, device, id_offset=0):
     """The synapse arrays of `tile_columns`, built as torch CUDA tensors directly in HBM (PyTorch is used for device
     buffers only): -> (src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms) for Engine.set_synapses_dev.

@@ -218,3 +218,104 @@ def test_resident_plan_refuses_what_it_cannot_do():
     e = make_engine("gpu", g, plan="resident")
     with pytest.raises(HhdError):
         e.run(10)
+
+
+@pytest.mark.parametrize("golden,method", [("net_n200_s0", "rk4"), ("net_n60x5_s1", "rk2")])
+def test_bucket_index_fallback_bit_exact(golden, method, monkeypatch):
+    """The 16-bucket delay index (used when a row has >= 65536 synapses or the per-delay offsets would not fit) must run
+    pathways p0..p6 like the default index does (round-1 advisor finding: `stp_chunks` stayed 0 there and all recurrent
+    transmission was silently dead).  HHD_NO_DOFF=1 forces the fallback."""
+    g = load_golden(golden)
+    monkeypatch.setenv("HHD_NO_DOFF", "1")
+    gpu = make_engine("gpu", g, plan="graph", method=method, accum="fixed", seed=11)
+    monkeypatch.delenv("HHD_NO_DOFF")
+    cpu = make_engine("cpu", g, method=method, accum="fixed", seed=11)
+    for e in (gpu, cpu):
+        e.run(8000)
+    gi, gs = gpu.spikes()
+    ci, cs = cpu.spikes()
+    gc, cc = gpu.counters(), cpu.counters()
+    assert cc["syn_events"] > 10000 and gc["syn_events"] == cc["syn_events"] and gc["syn_deliveries"] == cc["syn_deliveries"]
+    assert np.array_equal(gi, ci) and np.array_equal(gs, cs)
+    for v in STATE:
+        assert np.array_equal(gpu.read_state(v), cpu.read_state(v)), v
+    for v in ("u", "R", "a"):
+        assert np.array_equal(gpu.read_syn_state(v), cpu.read_syn_state(v)), v
+
+
+@pytest.mark.parametrize("plan", ["graph", "resident"])
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_baseline_column_full_run_bit_exact(method, plan):
+    """BASELINE config 1 at size: the reference's default column (1003 neurons, 293 599 synapses, the reference's own
+    NetworkSetup output for seed 0), 2 s = 40 000 steps at dt 0.05, order-independent accumulation: spikes, state and
+    synaptic state bit-identical to the oracle for the whole run."""
+    g = load_golden("net_n1000_s0_full")
+    gpu, cpu = gpu_cpu(g, plan, method=method, accum="fixed", seed=0)
+    for e in (gpu, cpu):
+        e.run(40000)
+    gi, gs = gpu.spikes()
+    ci, cs = cpu.spikes()
+    assert len(ci) > 3000
+    assert np.array_equal(gi, ci) and np.array_equal(gs, cs)
+    for v in STATE + ["last_spike"]:
+        assert np.array_equal(gpu.read_state(v), cpu.read_state(v)), v
+    for v in ("u", "R", "a", "delay_steps"):
+        assert np.array_equal(gpu.read_syn_state(v), cpu.read_syn_state(v)), v
+    gc, cc = gpu.counters(), cpu.counters()
+    for k in ("spikes", "w_crossings", "syn_events", "syn_deliveries", "neuron_updates", "nonfinite"):
+        assert gc[k] == cc[k], k
+
+
+def test_baseline_column_fp64_horizon():
+    """Same column with the reference's accumulation semantics (fp64 atomics in arrival order): the horizon up to which
+    the spike lists are identical, stated and bounded from below (north_star: 'a stated pre-divergence horizon')."""
+    g = load_golden("net_n1000_s0_full")
+    gpu, cpu = gpu_cpu(g, "auto", method="rk4", accum="fp64", seed=0)
+    for e in (gpu, cpu):
+        e.run(10000)
+    gi, gs = gpu.spikes()
+    ci, cs = cpu.spikes()
+    k = first_divergence(gi, gs, ci, cs)
+    horizon_ms = (min(gs[k], cs[k]) if k < min(len(gs), len(cs)) else 10000) * 0.05
+    print("1003-neuron column, fp64 atomics: divergence horizon %.1f ms (%d identical spikes of %d)" % (horizon_ms, k, len(ci)))
+    assert horizon_ms >= 50.0
+    assert abs(len(gi) - len(ci)) <= 0.1 * len(ci)
+
+
+@pytest.mark.parametrize("plan", ["graph", "resident"])
+def test_config3_batched_instances_with_stimuli_bit_exact(plan):
+    """BASELINE config 3 composite: independent instances in one engine at dt = 0.01 ms, rk4, each with its own draw of
+    the Poisson (100 sources x 30 Hz x 100 ms, 2 nS, pCon 0.1: codes/Main_poisson.py:145-150) or regular (250 / 500
+    spikes in 5 ms, 0.1 nS: codes/Main_regular.py:165-172) stimuli, on a 10x shortened protocol (pulses at 100 and
+    250 ms of 400 ms), bit-identical to the oracle."""
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine, load_codes_network
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import (POISSON_STIMULI, REGULAR_STIMULI, attach_stimuli,
+                                                                  instances_with_stimuli, shift_stimuli)
+    from oracle_binding import OracleEngine
+    g = load_golden("net_n200_s0")
+    n1, n_inst, dt = 207, 8, 0.01
+    net, stim = instances_with_stimuli(g["NeuPar"], g["V0"], g["SynPar"], g["source_arr"], g["target_arr"], default_idc(g),
+                                       golden_groups(g), n_inst, dt, shift_stimuli(POISSON_STIMULI, 0.1),
+                                       shift_stimuli(REGULAR_STIMULI, 0.1), seed=5)
+    assert stim["n_sources"] == 4 * 200 + 4 * 2
+    out = {}
+    for name, cls, kw in (("gpu", Engine, dict(plan=plan, instance_size=n1)), ("cpu", OracleEngine, {})):
+        e = cls(n1 * n_inst, dt, method="rk4", accum="fixed", seed=3, **kw)
+        load_codes_network(e, net["NeuPar"], net["V0"], g["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+        attach_stimuli(e, stim)
+        e.run(40000)
+        out[name] = (e.spikes(), [e.read_state(v) for v in STATE], e.counters())
+        e.close()
+    (ci, cs), cx, cc = out["cpu"]
+    (gi, gs), gx, gc = out["gpu"]
+    assert cc["ext_events"] > 5000 and gc["ext_events"] == cc["ext_events"]
+    # the stimulated layer responds: more PC_L23 spikes in the 30 ms after the pulse than in the 30 ms before it
+    pc23 = np.concatenate([np.asarray(golden_groups(g)[0][0]) + q * n1 for q in range(n_inst)])
+    sel = np.isin(ci, pc23)
+    t = cs[sel] * dt
+    assert ((t >= 100) & (t < 130)).sum() > ((t >= 70) & (t < 100)).sum()
+    assert np.array_equal(gi, ci) and np.array_equal(gs, cs)
+    for a, b in zip(gx, cx):
+        assert np.array_equal(a, b)
+    for k in ("spikes", "syn_events", "syn_deliveries", "w_crossings"):
+        assert gc[k] == cc[k], k
