@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--dt", type=float, default=0.05)
     ap.add_argument("--window", type=int, default=2000, help="time steps per bench step")
     ap.add_argument("--accum", default="fp64", choices=["fp64", "fixed"])
-    ap.add_argument("--plan", default="auto", choices=["auto", "graph", "resident", "persistent", "pipelined"])
+    ap.add_argument("--plan", default="auto", choices=["auto", "graph", "resident"])
     ap.add_argument("--idc-scale", type=float, default=1.0, help="scale the background current (0: silent network, timing experiments)")
     ap.add_argument("--instances", action="store_true", help="treat every column as an independent instance (config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")

@@ -60,11 +60,10 @@ typedef enum { HHD_ACCUM_FP64 = 0, HHD_ACCUM_FIXED = 1 } hhd_accum;
 /* Execution plan for hhd_run (same results, different launch structure). */
 typedef enum {
   HHD_PLAN_AUTO = 0,
-  HHD_PLAN_GRAPH = 1,     /* 3 grid-wide kernels per step, captured in CUDA graphs (any N, HBM-bound regime) */
+  HHD_PLAN_GRAPH = 1,     /* 2 grid-wide kernels per step (k_neuron, k_synapse), captured in CUDA graphs (any N, HBM-bound regime) */
   HHD_PLAN_RESIDENT = 2,  /* persistent thread-block-cluster kernel, state in registers (N small, latency-bound regime) */
-  HHD_PLAN_PERSISTENT = 3,/* one cooperative launch per segment: the graph plan's phases separated by grid barriers */
-  HHD_PLAN_PIPELINED = 4  /* one launch per step: the state update also does the synaptic work that is one step ahead (needs
-                             max delay < refractory period, a single rank); opt-in, AUTO never picks it */
+  HHD_PLAN_PERSISTENT = 3,/* removed in round 2 (cooperative whole-run kernel: measured slower); hhd_run returns HHD_E_ARG */
+  HHD_PLAN_PIPELINED = 4  /* removed in round 2 (one launch per step: measured no faster); hhd_run returns HHD_E_ARG */
 } hhd_plan;
 
 typedef struct {
@@ -207,7 +206,8 @@ int hhd_run(hhd_handle h, int64_t n_steps);          /* continues from the curre
 
 /* Measurement aid (bench.py roofline): runs n_steps like hhd_run but launches the kernels one by one with a CUDA event
  * between them on the handle's stream and returns the mean device time per launch of each kernel in microseconds:
- * us[0] state update (k_neuron), us[1] spike-time STP (k_stp), us[2] delivery (k_deliver). */
+ * us[0] state update (k_neuron), us[1] the spike exchange when it is the NCCL all-gather fallback (else 0: over peer
+ * memory it happens inside the two kernels), us[2] slot `synapses` (k_synapse: spike-time STP + delivery). */
 int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]);
 
 /* ---- results ---------------------------------------------------------------------------------------------------- */

@@ -1,33 +1,34 @@
 /*
  * hhd_engine.cu — sm_100a engine behind the C ABI of include/hhd.h.  DESIGN.md §3-5 has the full picture.
  *
- * One time step of the default (graph) plan = three kernels, captured STEPS_PER_GRAPH at a time into a CUDA graph:
- *   k_neuron      persistent CTAs, one thread per neuron and tile, SoA fp64 staged by TMA bulk copies: finish the previous
- *                 step (w_crossing test on the stored state, pending synaptic increments, reset `V=V_r; w+=b`, w_crossing
- *                 projection), sample the monitors (Brian's `start` slot), integrate the 8 ODEs (euler / rk2 / rk4 /
- *                 gsl_rk2; TimedArray current and conductance noise in the TIMED variants), threshold + refractoriness,
- *                 append spikes to the spike ring with one atomic per warp (ballot compaction) and note what the synaptic
- *                 kernels need of a spike.  Replaces NeuronGroup's stateupdater/thresholder/resetter + StateMonitor +
- *                 SpikeMonitor (codes/CortexNetwork.py:304-311, 487, 510).
- *   k_spike_new   [second stream] pathways p0..p6 for the NEW spikes in 128-synapse tasks: failure draw (Philox keyed by
- *                 synapse and step), Tsodyks–Markram update of (u, R), the amplitude the delayed pathways will add
- *                 (codes/CortexNetwork.py:360-366), zero-delay deliveries; with delays beyond the refractory period also the
- *                 deliveries that are due from older spikes of the same neuron.
- *   k_deliver     [concurrently] one LANE per ACTIVE older spike: the row is sorted by delay and has per-delay offsets, so
- *                 the lane gets exactly the synapses whose delay equals the spike's age; the warp walks its lanes'
- *                 segments together and adds their CURRENT amplitudes to the targets' pending increments (pathways
- *                 p7a..p9b with `delay = dtax`, :367-372,463-468).  The spike history itself is the delay queue: no
- *                 per-event queue memory, bounded by one spike per neuron per refractory period, and values are read at
- *                 delivery time exactly as Brian's SpikeQueue does.  SpikeGeneratorGroup events (:570-622) as well.
- *   k_exchange    [partitioned networks] this step's spike lists, every rank to every rank, as stores + flags into
- *                 IPC-mapped peer memory; ncclAllGather + k_append when the buffers cannot be mapped.
- * Other plans on the same phase functions: k_resident (one thread-block cluster per small independent network, whole
- * segments in one launch), k_grid (cooperative whole-run kernel, opt-in), k_neuron<.., PIPE> (one launch per step, opt-in).
+ * One time step of the grid-wide (graph) plan = two kernels, captured STEPS_PER_GRAPH at a time into a CUDA graph:
+ *   k_neuron      persistent CTAs, every WARP its own TMA pipeline over 32-neuron blocks (one 5 KB bulk copy per tile):
+ *                 finish the previous step (w_crossing test on the stored state, pending synaptic increments, reset
+ *                 `V=V_r; w+=b`, w_crossing projection), sample the monitors (Brian's `start` slot), integrate the 8 ODEs
+ *                 (euler / rk2 / rk4 / gsl_rk2; TimedArray current and conductance noise in the TIMED variants),
+ *                 threshold + refractoriness, append spikes to the spike ring with one atomic per warp (ballot
+ *                 compaction) and note what the synaptic kernel needs of a spike.  Replaces NeuronGroup's
+ *                 stateupdater/thresholder/resetter + StateMonitor + SpikeMonitor (codes/CortexNetwork.py:304-311, 487, 510).
+ *                 On a partitioned network its last CTA also pushes the step's spike list into every peer's memory.
+ *   k_synapse     slot `synapses`, CTAs in two roles.  Spike-time half: pathways p0..p6 for the NEW spikes in 128-synapse
+ *                 tasks — failure draw (Philox keyed by synapse and step), Tsodyks–Markram update of (u, R), the amplitude
+ *                 the delayed pathways will add (codes/CortexNetwork.py:360-366), zero-delay deliveries; with delays
+ *                 beyond the refractory period also the deliveries that are due from older spikes of the same neuron
+ *                 (SURVEY F5).  Delivery half: one LANE per ACTIVE older spike — the row is sorted by delay and has
+ *                 per-delay offsets, so the lane gets exactly the synapses whose delay equals the spike's age; the warp
+ *                 walks its lanes' segments together and adds their CURRENT amplitudes to the targets' pending increments
+ *                 (pathways p7a..p9b with `delay = dtax`, :367-372,463-468).  The spike history itself is the delay queue:
+ *                 no per-event queue memory, bounded by one spike per neuron per refractory period, and values are read
+ *                 at delivery time exactly as Brian's SpikeQueue does.  SpikeGeneratorGroup events (:570-622) as well.
+ *                 On a partitioned network its CTA 0 first receives the peers' spike lists (recv_spikes).
+ * The other plan on the same arithmetic: k_resident (one thread-block cluster per small independent network, whole
+ * segments in one launch).  Round 1's cooperative whole-run kernel and one-launch-per-step schedule were measured slower
+ * (profiles/r1_notes.md) and are gone.
  *
- * Data layout in HBM: structure of arrays, fp64; per neuron 8 state + 12 parameter doubles + last_spike + int32 meta word
- * (≈ 240 B read+written per neuron-update, the roofline figure of SURVEY §8d); per synapse (CSR by presynaptic neuron,
- * sorted by delay) a 16-byte record {target, delay, channel, amplitude} and a 64-byte record {U, tau_rec, tau_fac, g_max,
- * p_fail, u, R, original index}.
+ * Data layout in HBM: per block of 32 neurons 20 rows of 32 doubles (8 state + 12 parameters, 5120 B contiguous), blocked
+ * pending increments and meta words, last_spike per global neuron (≈ 240 B read+written per neuron-update, the roofline
+ * figure of SURVEY §8d); per synapse (CSR by presynaptic neuron, sorted by delay) a 16-byte record {target, delay,
+ * channel, amplitude} and a 64-byte record {U, tau_rec, tau_fac, g_max, p_fail, u, R, original index}.
  */
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
@@ -50,7 +51,7 @@
 #include "../../include/hhd.h"
 #include "hhd_model.cuh"
 
-#define MAX_MON 16
+#define MAX_MON 12   /* with 12 the static shared memory of k_neuron still lets five CTAs share an SM */
 #define MAX_RANKS 16
 #define MAX_RED 4   /* reduced (sum/mean) monitors: their per-thread accumulators live in registers */
 #ifndef NEURON_BLOCK
@@ -102,17 +103,15 @@ struct Params {
   double dt;
   unsigned long long seed;
   ChannelConst cc;
-  double* par[HHD_N_PARAMS];
-  double* x[8];
+  double* nb;                  /* [n_pad / 32][NB_FIELDS][32] neuron blocks: 8 state rows + 12 parameter rows (nb_index) */
   double* last_spike;          /* [NG] */
   double* hstep;               /* [n_pad] adaptive method: the step size a neuron carries from one dt to the next */
-  int* meta;                   /* [N] lastspike_step << META_SHIFT | flags (of the previous step; FLAG_OUT, FLAG_ZERO static) */
+  int* meta;                   /* [n_pad] lastspike_step << META_SHIFT | flags (of the previous step; FLAG_OUT, FLAG_ZERO static) */
   const unsigned char* has_out;/* [NG] */
-  long long* pend;             /* [2][3][n_pad] synaptic increments summed per (channel, target): fp64 bits (HHD_ACCUM_FP64)
-                                  or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED).  The deliveries of slot k go to buffer
-                                  (k+1)&1; the state-update pass of step k+1 consumes and clears it.  Two buffers, so that
-                                  the pipelined schedule can fill one while the state update drains the other. */
-  long long n_pad;             /* neurons rounded up to whole tiles */
+  long long* pend;             /* [2][n_pad / 32][3][32] (pend_index) synaptic increments summed per (channel, target): fp64
+                                  bits (HHD_ACCUM_FP64) or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED).  The deliveries of
+                                  slot k go to buffer (k+1)&1; the state-update pass of step k+1 consumes and clears it. */
+  long long n_pad;             /* neurons rounded up to whole 32-neuron blocks */
   /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
   const long long* row_ptr;    /* [NG+1] */
   SynHot* hot;
@@ -120,10 +119,10 @@ struct Params {
   const unsigned short* row_maxd; /* [NG] largest delay (steps) in the row */
   const unsigned int* row_bkt; /* [NG][DELAY_BUCKETS] offset inside the row of the first synapse with delay >= b*bkt_width */
   int bkt_width;
-  const unsigned short* row_doff; /* [NG][max_delay + 2] offset inside the row of the first synapse with delay >= d (pipelined
-                                     schedule: one thread per active spike reads exactly its due synapses); NULL = not built */
-  unsigned long long* dbg_times;   /* HHD_DEBUG_TIMES: [grid][4] globaltimer at start / after ahead_phase / end of the tiles / end */
-  int doff_stride, stp_chunks, ahead_ctas, dyn_tiles;    /* max_delay + 2; ceil(longest row / NEURON_BLOCK) */
+  const unsigned short* row_doff; /* [NG][max_delay + 2] offset inside the row of the first synapse with delay >= d (one
+                                     lane per active spike reads exactly its due synapses); NULL = not built */
+  unsigned long long* dbg_times;   /* HHD_DEBUG_TIMES: [4096 steps][8] %globaltimer stamps (dbg_stamp) */
+  int doff_stride, stp_chunks;     /* max_delay + 2; STP tasks per spike */
   long long syn_id_base;
   /* spike ring */
   int* spk_neuron;             /* global ids */
@@ -135,13 +134,9 @@ struct Params {
   int* spk_last;               /* [NG] step of the latest spike of every (global) neuron, written when the spike is appended */
   unsigned long long* head;    /* monotone count of spikes appended */
   unsigned long long* step_end;/* [W] head value at the end of step (k % W) */
-  /* pipelined schedule (see k_neuron<.., PIPE>): */
-  double* prev_spike;          /* [NG] last_spike of a neuron before its latest spike (the STP update runs one pass later) */
-  unsigned long long* stp_mark;/* ring position below which pathways p0..p6 have been applied */
-  unsigned int* pass_done;     /* CTAs that finished the current pass */
-  unsigned int* tile_ctr;      /* tiles handed out in the current pass beyond the first two of every CTA */
-  unsigned int* zcount;        /* spikes of the current step whose row starts with zero-delay synapses ... */
-  int* zlist;                  /* [N] ... and their neurons; the last CTA of the pass serves them (spike_local) */
+  double* prev_spike;          /* [NG] last_spike of a neuron before its latest spike (read by the STP update of that spike) */
+  unsigned int* pass_done;     /* CTAs of k_neuron that finished the current pass (the last one closes it) */
+  double* mon_part;            /* [MAX_RED][grid] per-CTA partial sums of the reduced monitors of the current pass */
   /* external input events, grouped by step */
   const int* ext_ptr;          /* [ext_last - ext_first + 2] */
   long long ext_first, ext_last;
@@ -152,7 +147,6 @@ struct Params {
   MonDesc* mon;                /* [MAX_MON] device */
   unsigned long long* counters;
   unsigned long long* del_slots;  /* [CNT_SLOTS] */
-  unsigned long long* grid_bar;   /* arrival counter of the cooperative plan's grid barrier */
   const long long* base_step;
   /* TimedArray current I_AC: table[iac_steps][iac_cols], column of local neuron i = iac_col[i] (-1: none); NULL = unused */
   const double* iac_table;
@@ -166,26 +160,19 @@ struct Params {
   int n_ranks, xchg_cap;
   int* xchg_send;              /* [1 + xchg_cap] */
   int* xchg_recv;              /* [n_ranks][1 + xchg_cap] */
-  /* peer-memory exchange (k_exchange): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] ints followed by
+  /* peer-memory exchange (push_spikes / recv_spikes): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] ints followed by
    * MAX_RANKS arrival flags, mapped into this process (CUDA IPC over NVLink); peer_buf[rank] is the own one; NULL = the
    * NCCL all-gather is used instead */
   int rank;
   int* peer_buf[MAX_RANKS];
   unsigned int* xchg_dead;     /* set when a peer did not arrive within the time limit: later steps do not wait again */
+  unsigned long long* xchg_done;/* k + 1 once CTA 0 of k_synapse has appended every rank's spikes of step k */
   /* cluster-resident plan: the network is n_inst independent instances of inst_size neurons, one thread-block cluster each */
   int inst_size, n_inst, res_cap, res_cluster;
   unsigned int* res_store;     /* [n_inst][2 + W + 2*res_cap] head, pad, end[W], neuron[cap], step[cap]: the instance's spike list between launches */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ NeuronPar load_par(const Params& P, int i) {
-  NeuronPar p;
-  p.C = __ldg(P.par[HHD_P_C] + i); p.gL = __ldg(P.par[HHD_P_GL] + i); p.EL = __ldg(P.par[HHD_P_EL] + i);
-  p.dT = __ldg(P.par[HHD_P_DELTAT] + i); p.Vup = __ldg(P.par[HHD_P_VUP] + i); p.tauw = __ldg(P.par[HHD_P_TAUW] + i);
-  p.b = __ldg(P.par[HHD_P_B] + i); p.Vr = __ldg(P.par[HHD_P_VR] + i); p.VT = __ldg(P.par[HHD_P_VT] + i);
-  p.Iref = __ldg(P.par[HHD_P_IREF] + i); p.Vdep = __ldg(P.par[HHD_P_VDEP] + i); p.IDC = __ldg(P.par[HHD_P_IDC] + i);
-  return p;
-}
 
 /* I_AC of a neuron whose column is `col` at step s: TimedArray semantics (first row before the table, last row after). */
 __device__ __forceinline__ double iac_at(const Params& P, int col, long long s) {
@@ -235,6 +222,26 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* The same with an L2 eviction-priority hint (createpolicy): the state rows of a 1M-neuron network (64 MB) fit in the
+ * 126 MB L2 and are read again one step later, the parameter rows (96 MB) only stream through. */
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(double* p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;\n" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 /* Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may be
  * scheduled while its predecessor in the stream is still draining; pdl_wait() blocks until that predecessor has
  * completed and its writes are visible, pdl_trigger() lets the successor start being scheduled.  Both are no-ops for a
@@ -243,63 +250,68 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #ifndef HHD_EXPERIMENT
-#define HHD_EXPERIMENT 0          /* timing experiments only (bit 0: no w_crossing test, bit 1: no integration) */
+#define HHD_EXPERIMENT 0          /* timing experiments only (2: no integration; 4: no evaluation of the stored state either) */
 #endif
-#ifndef HHD_NEURON_PREFETCH
-#define HHD_NEURON_PREFETCH 2     /* 3: TMA bulk copies + one mbarrier per WARP (warps of a CTA never wait for each other);
-                                     2: TMA + one mbarrier per CTA; 1: per-thread cp.async; 0: plain loads */
+#ifndef HHD_L2_HINTS
+#define HHD_L2_HINTS 1            /* L2 eviction priorities: keep the state rows, stream the parameter rows */
 #endif
 #ifndef HHD_NEURON_MINBLOCKS_EULER
-#define HHD_NEURON_MINBLOCKS_EULER 4   /* 128 registers: the single-evaluation kernel spills at the 96 a fifth CTA would allow */
+#define HHD_NEURON_MINBLOCKS_EULER 4   /* CTAs per SM the state-update kernel is compiled for (registers: 128 at 4, 96 at 5) */
 #endif
-#define NEURON_FIELDS 21   /* 8 state + 12 parameters + last_spike (the 3 pending-increment words are prefetched into
-                              registers one tile ahead: staging them would cost the fifth resident CTA per SM) */
-struct NeuronStage {
-  double f[NEURON_FIELDS][NEURON_BLOCK];
-  int meta[NEURON_BLOCK];
-};
-#define NEURON_STAGES 2
-#define NEURON_SMEM (HHD_NEURON_PREFETCH ? NEURON_STAGES * (int)sizeof(NeuronStage) : 0)
+#ifndef HHD_NEURON_MINBLOCKS_RK2
+#define HHD_NEURON_MINBLOCKS_RK2 4
+#endif
+#ifndef HHD_NEURON_MINBLOCKS_RK4
+#define HHD_NEURON_MINBLOCKS_RK4 3     /* also the adaptive method */
+#endif
 
 /*
- * State update, persistent over tiles of NEURON_BLOCK neurons.  Each thread owns one neuron per tile and prefetches the
- * 21 doubles + meta word of its NEXT tile into shared memory with cp.async while it integrates the current one, so the
- * HBM stream (240 B per neuron-update) and the fp64 pipe (≈350 instructions per euler update) overlap inside every warp
- * instead of alternating; a thread only ever reads the shared slots it filled itself, so no block barrier is needed.
- * METHOD: 0 euler, 1 rk2, 2 rk4, 3 adaptive rk2(3).  STEP = false: only finish the previous step (used once at the end of hhd_run so that
- * the state read back is the state after `resets`/`after_resets`).
- * meta = lastspike_step * 4 + flags (FLAG_SPIKED | FLAG_WCROSS of the previous step).
+ * Neuron data in HBM: blocks of 32 neurons ("warp tiles"), each block = NB_FIELDS rows of 32 doubles — 8 state rows
+ * (V, w, g_X_on/off) and 12 parameter rows — contiguous (5120 B), so that ONE bulk copy (cp.async.bulk, SASS UBLKCP)
+ * brings everything a warp needs for its tile, and the eight state rows a warp writes back are eight full 256-byte lines.
+ * The pending synaptic increments (3 x 32 x 8 B per block and parity) and the meta words (32 x 4 B) are blocked the same
+ * way and arrive on the same mbarrier.  (Round 1 kept 20 separate arrays: 20 copies per 128-neuron tile on ONE mbarrier
+ * per CTA, which tied the four warps of a CTA together tile by tile — 20 % of all warp stalls were that barrier.)
  */
-struct NeuronShared {            /* static shared memory of a CTA that runs neuron_phase */
-  double red[MAX_MON][NEURON_BLOCK / 32];
-  MonDesc mon[MAX_MON];          /* read once per CTA instead of once per tile from global memory */
-  unsigned long long cnt[3];
-  int is_last;                   /* pipelined schedule: this CTA is the last one of the pass to finish */
-  int zl_n, zl_j[16];            /* pipelined schedule: this CTA's spikes of the step whose rows start with zero-delay synapses */
-  int tile_fetch[2];             /* pipelined schedule: tile index the producer thread drew for the stage freed in iteration it (slot it & 1) */
-  unsigned long long full_bar[NEURON_STAGES * (HHD_NEURON_PREFETCH == 3 ? NEURON_BLOCK / 32 : 1)];
-};
+#define NB_LANES 32
+#define NB_STATE 8
+#define NB_FIELDS (NB_STATE + HHD_N_PARAMS)                 /* 20 */
+#define NB_BYTES (NB_FIELDS * NB_LANES * 8)                 /* 5120 */
+#define PEND_BYTES (3 * NB_LANES * 8)                       /* 768 */
+#define META_BYTES (NB_LANES * 4)                           /* 128 */
 
-/* Called once per CTA before the first neuron_phase: monitor descriptors, mbarriers. */
-__device__ __forceinline__ void neuron_shared_init(const Params& P, NeuronShared& sh) {
-  if (threadIdx.x < P.n_mon) sh.mon[threadIdx.x] = P.mon[threadIdx.x];
-#if HHD_NEURON_PREFETCH >= 2
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int q = 0; q < NEURON_STAGES * (HHD_NEURON_PREFETCH == 3 ? NEURON_BLOCK / 32 : 1); ++q) mbar_init(&sh.full_bar[q], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-#endif
-  __syncthreads();
+__device__ __host__ __forceinline__ size_t nb_index(int field, long long i) {
+  return ((size_t)(i >> 5) * NB_FIELDS + (size_t)field) * NB_LANES + (size_t)(i & 31);
+}
+__device__ __host__ __forceinline__ size_t pend_index(int c, long long i) {
+  return ((size_t)(i >> 5) * 3 + (size_t)c) * NB_LANES + (size_t)(i & 31);
 }
 
-__device__ __forceinline__ void spike_local(const Params& P, int j, long long k, double t);
+__device__ __forceinline__ NeuronPar load_par(const Params& P, int i) {
+  NeuronPar p;
+  const double* b = P.nb + nb_index(NB_STATE, i);
+  p.C = __ldg(b + HHD_P_C * NB_LANES); p.gL = __ldg(b + HHD_P_GL * NB_LANES); p.EL = __ldg(b + HHD_P_EL * NB_LANES);
+  p.dT = __ldg(b + HHD_P_DELTAT * NB_LANES); p.Vup = __ldg(b + HHD_P_VUP * NB_LANES); p.tauw = __ldg(b + HHD_P_TAUW * NB_LANES);
+  p.b = __ldg(b + HHD_P_B * NB_LANES); p.Vr = __ldg(b + HHD_P_VR * NB_LANES); p.VT = __ldg(b + HHD_P_VT * NB_LANES);
+  p.Iref = __ldg(b + HHD_P_IREF * NB_LANES); p.Vdep = __ldg(b + HHD_P_VDEP * NB_LANES); p.IDC = __ldg(b + HHD_P_IDC * NB_LANES);
+  return p;
+}
 
-/* What the appender of a spike (k_neuron on a single rank, k_append after the exchange) records besides the ring entry:
- * the neuron's previous spike time for the STP update that follows (p0..p6 read it, possibly from many CTAs), the new one
- * (p5: last_spike_pre = t, only neurons with outgoing synapses have that pathway), the step of its latest spike, and — when
- * delays can outlast the refractory period — its spike history.  Returns the has_out flags. */
-/* Two spikes of a neuron are at least refr_steps apart, and hist_depth = max_delay / refr_steps + 2: spikes that can both
+__device__ __forceinline__ void dbg_stamp(const Params& P, const long long k, const int q) {
+  if (P.dbg_times) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    P.dbg_times[(size_t)(k & 4095) * 8 + q] = g;
+  }
+}
+
+__device__ __forceinline__ void push_spikes(const Params& P, const long long k);
+
+/* What the appender of a spike (k_neuron on a single rank, recv_spikes / k_append after the exchange) records besides the
+ * ring entry: the neuron's previous spike time for the STP update that follows (p0..p6 read it, possibly from many CTAs),
+ * the new one (p5: last_spike_pre = t, only neurons with outgoing synapses have that pathway), the step of its latest
+ * spike, and — when delays can outlast the refractory period — its spike history.  Returns the has_out flags.
+ * Two spikes of a neuron are at least refr_steps apart, and hist_depth = max_delay / refr_steps + 2: spikes that can both
  * be in flight never share a slot, and a reader just skips entries whose age is not in (0, max_delay]. */
 __device__ __forceinline__ int hist_slot(const Params& P, const int k) { return (k / max(P.refr_steps, 1)) % P.hist_depth; }
 
@@ -311,205 +323,154 @@ __device__ __forceinline__ unsigned char note_spike(const Params& P, const int j
   if (P.spk_hist) P.spk_hist[(size_t)j * P.hist_depth + hist_slot(P, k)] = k;
   return ho;
 }
-__device__ __forceinline__ void ahead_phase(const Params& P, long long k, unsigned part, unsigned nparts);
 
-/* One pass over this CTA's tiles for time step k.  `bar_parity` carries the phase bit of every mbarrier across calls
- * (the cooperative whole-run kernel calls this once per step on the same barriers).
- * PIPE = true is the pipelined schedule: the pass is the ONLY launch of the step.  Besides the state update it
- *  - delivers, somewhere between two of its tiles, this CTA's share of slot k's synaptic events whose spikes are at
- *    least one step old, and applies p0..p6 to the spikes of step k-1 (ahead_phase) — into the pending buffer the NEXT
- *    pass consumes, so nothing here waits for it;
- *  - lets the thread that detects a spike do what must be visible to pass k+1: last_spike (p5) and the row's zero-delay
- *    synapses (spike_local);
- *  - has its last CTA publish the head of the spike ring as the end of step k. */
-template <int METHOD, bool STEP, bool TIMED, bool PIPE>
-__device__ __forceinline__ void neuron_phase(const Params& P, const long long k, NeuronStage* st, NeuronShared& sh,
-                                             unsigned& bar_parity) {
-  double (*red)[NEURON_BLOCK / 32] = sh.red;
-  MonDesc* mon_sh = sh.mon;
-  unsigned long long* cnt_sh = sh.cnt;
-  unsigned long long* full_bar = sh.full_bar;
+/* One warp's pipeline in shared memory: two stages of the 5 KB block, ONE buffer for the block's pending increments and
+ * meta words (they are taken into registers first thing, so the next tile's can be requested right away).  11 136 B per
+ * warp: five 128-thread CTAs per SM fit (5 x (44.5 KB + 1 KB) < 228 KB). */
+struct __align__(128) WarpStage {
+  double f[NB_FIELDS][NB_LANES];
+};
+struct __align__(128) WarpAux {
+  long long pend[3][NB_LANES];
+  int meta[NB_LANES];
+};
+#define NEURON_STAGES 2
+#define NEURON_WARPS (NEURON_BLOCK / 32)
+#define NEURON_WARP_SMEM (NEURON_STAGES * (int)sizeof(WarpStage) + (int)sizeof(WarpAux))
+#define NEURON_SMEM (NEURON_WARPS * NEURON_WARP_SMEM)
+
+template <bool MON>
+struct NeuronShared {            /* static shared memory of a CTA that runs neuron_phase */
+  double red[MON ? MAX_RED : 1][NEURON_WARPS];
+  MonDesc mon[MON ? MAX_MON : 1];/* read once per CTA instead of once per tile from global memory */
+  unsigned long long cnt[3];
+  int is_last;
+  unsigned long long full_bar[NEURON_WARPS][NEURON_STAGES + 1];   /* [..][NEURON_STAGES]: the pend/meta buffer */
+};
+
+/*
+ * State update of time step k, persistent over warp tiles.  Every WARP runs its own two-stage pipeline: lane 0 issues
+ * three bulk copies per tile (block, pending increments, meta words) onto the warp's mbarrier of that stage two tiles
+ * ahead; the warp waits on the barrier, takes its tile into registers, hands the stage back (__syncwarp + proxy fence) and
+ * integrates.  No CTA-wide barrier inside the loop: a warp never waits for another warp.
+ * METHOD: 0 euler, 1 rk2, 2 rk4, 3 adaptive rk2(3) (gsl_rk2).  STEP = false: only finish the previous step (once at the end
+ * of hhd_run, so that the state read back is the state after `resets` / `after_resets`).  TIMED: TimedArray current and
+ * conductance noise.  MON: state monitors are sampled (a variant without any monitor code runs when none is active).
+ * meta = lastspike_step << META_SHIFT | flags (FLAG_SPIKED | FLAG_HAS_PREV of the previous step; FLAG_OUT, FLAG_ZERO static).
+ */
+template <int METHOD, bool STEP, bool TIMED, bool MON>
+__device__ __forceinline__ void neuron_phase(const Params& P, const long long k, unsigned char* smem, NeuronShared<MON>& sh) {
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
+  const int warp = tid >> 5;
   const double t = (double)k * P.dt;
-  const int ntiles = (P.N + NEURON_BLOCK - 1) / NEURON_BLOCK;
-  if (tid < 3) cnt_sh[tid] = 0ull;
-  if (tid == 0) sh.zl_n = 0;
+  const int nblocks = (int)(P.n_pad >> 5);
+  if (STEP && blockIdx.x == 0 && tid == 0) dbg_stamp(P, k, 0);
+  if (tid < 3) sh.cnt[tid] = 0ull;
+  if (MON && tid < P.n_mon) sh.mon[tid] = P.mon[tid];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s <= NEURON_STAGES; ++s) mbar_init(&sh.full_bar[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   __syncthreads();
 
-#if HHD_NEURON_PREFETCH >= 2
-  /* mode 2: one barrier per stage for the CTA; mode 3: one per stage and warp */
-  constexpr int GROUP = HHD_NEURON_PREFETCH == 3 ? 32 : NEURON_BLOCK;      /* threads that share a barrier */
-  constexpr int NGROUPS = NEURON_BLOCK / GROUP;
-  const int grp = tid / GROUP, gl = tid % GROUP;
-  /* Producer = first thread of the group: twenty bulk copies (8 state + 12 parameter rows of the group's part of the
-   * tile; the arrays are padded to whole tiles) complete on the group's mbarrier of that stage; every thread fetches its
-   * own last_spike and meta word with cp.async. */
-  auto issue = [&](int tile, int s) {
-    const int i = tile * NEURON_BLOCK + tid;
-    if (tile < ntiles) {
-      if (gl == 0) {
-        const size_t o = (size_t)tile * NEURON_BLOCK + (size_t)grp * GROUP;
-        unsigned long long* bar = &full_bar[s * NGROUPS + grp];
-        mbar_expect_tx(bar, 20u * GROUP * 8u);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) tma_load_1d(&st[s].f[v][grp * GROUP], P.x[v] + o, GROUP * 8u, bar);
-#pragma unroll
-        for (int q = 0; q < HHD_N_PARAMS; ++q) tma_load_1d(&st[s].f[8 + q][grp * GROUP], P.par[q] + o, GROUP * 8u, bar);
-      }
-      if (i < P.N) {
-        cp_async8(&st[s].f[20][tid], P.last_spike + P.off + i);
-        cp_async4(&st[s].meta[tid], P.meta + i);
-      }
-    }
-    cp_async_commit();
-  };
-#else
-  auto issue = [&](int tile, int s) {
-    const int i = tile * NEURON_BLOCK + tid;
-    if (tile < ntiles && i < P.N) {
-#pragma unroll
-      for (int v = 0; v < 8; ++v) cp_async8(&st[s].f[v][tid], P.x[v] + i);
-#pragma unroll
-      for (int q = 0; q < HHD_N_PARAMS; ++q) cp_async8(&st[s].f[8 + q][tid], P.par[q] + i);
-      cp_async8(&st[s].f[20][tid], P.last_spike + P.off + i);
-      cp_async4(&st[s].meta[tid], P.meta + i);
-    }
-    cp_async_commit();
-  };
+  WarpStage* const st = reinterpret_cast<WarpStage*>(smem + (size_t)warp * NEURON_WARP_SMEM);
+  WarpAux* const aux = reinterpret_cast<WarpAux*>(st + NEURON_STAGES);
+  unsigned long long* const bar = sh.full_bar[warp];
+  long long* const pin = P.pend + (size_t)(k & 1) * 3 * (size_t)P.n_pad;     /* filled during slot k-1 */
+  const int gwarp = blockIdx.x * NEURON_WARPS + warp, nwarps = gridDim.x * NEURON_WARPS;
+
+#if HHD_L2_HINTS
+  const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 #endif
+  auto issue = [&](int blk, int s) {           /* lane 0 only */
+    if (blk < nblocks) {
+      mbar_expect_tx(&bar[s], NB_BYTES);
+#if HHD_L2_HINTS
+      const double* src = P.nb + (size_t)blk * (NB_FIELDS * NB_LANES);
+      tma_load_1d_hint(&st[s].f[0][0], src, NB_STATE * NB_LANES * 8, &bar[s], pol_keep);
+      tma_load_1d_hint(&st[s].f[NB_STATE][0], src + NB_STATE * NB_LANES, HHD_N_PARAMS * NB_LANES * 8, &bar[s], pol_stream);
+#else
+      tma_load_1d(&st[s].f[0][0], P.nb + (size_t)blk * (NB_FIELDS * NB_LANES), NB_BYTES, &bar[s]);
+#endif
+    }
+  };
+  auto issue_aux = [&](int blk) {              /* lane 0 only */
+    if (blk < nblocks) {
+      mbar_expect_tx(&bar[NEURON_STAGES], PEND_BYTES + META_BYTES);
+      tma_load_1d(&aux->pend[0][0], pin + (size_t)blk * (3 * NB_LANES), PEND_BYTES, &bar[NEURON_STAGES]);
+      tma_load_1d(&aux->meta[0], P.meta + (size_t)blk * NB_LANES, META_BYTES, &bar[NEURON_STAGES]);
+    }
+  };
 
   double mon_acc[MAX_RED];
 #pragma unroll
   for (int r = 0; r < MAX_RED; ++r) mon_acc[r] = 0.0;
   unsigned n_spk = 0, n_wc = 0, n_bad = 0;
+  unsigned parity = 0;                          /* bit s: phase of the stage's barrier */
 
-  auto stamp = [&](int q) {
-    if (STEP && P.dbg_times && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.dbg_times[((size_t)(k & 1) * 4096 + blockIdx.x) * 4 + q] = g;
-      if (blockIdx.x == 0 && q == 0) P.dbg_times[8 * 4096 + (k & 4095) * 2] = g; }
-  };
-  const bool DYN = PIPE && STEP && HHD_NEURON_PREFETCH == 2 && P.dyn_tiles > 0;
-  stamp(0);
-  /* Tiles.  Static (b, b + grid, b + 2 grid, ...) — except in the pipelined schedule, where every CTA first does its share
-   * of the synaptic work of slot k (ahead_phase; it takes a different time in every CTA) and the LAST tiles of the pass
-   * (two per CTA on average) come from a counter instead: whoever is done earlier integrates more.  Only the last ones,
-   * because a drawn index costs the producer warp the round trip of the atomic (the compiler cannot keep its result in a
-   * register across the integration, so the warp waits for it at once): ~1 us per draw, three draws instead of thirteen. */
-  int tile = blockIdx.x, tile_nxt = tile + (int)gridDim.x, dyn_base = 0;
-  int n_static = 1 << 30;            /* iterations whose tile is b + it * grid */
-  if (PIPE && STEP) {
-    if ((int)blockIdx.x < P.ahead_ctas) ahead_phase(P, k, blockIdx.x, (unsigned)P.ahead_ctas);
-    if (DYN) {
-      n_static = max(0, ntiles / (int)gridDim.x - P.dyn_tiles);
-      if (n_static < 2) n_static = 0;
-      dyn_base = n_static * (int)gridDim.x;
-      if (n_static == 0) {           /* small network: every tile is drawn */
-        if (tid < 2) sh.tile_fetch[tid] = (int)atomicAdd(P.tile_ctr, 1u);
-        __syncthreads();
-        tile = min(sh.tile_fetch[0], sh.tile_fetch[1]);
-        tile_nxt = max(sh.tile_fetch[0], sh.tile_fetch[1]);
-        __syncthreads();
-      }
-    }
+  int blk = gwarp;
+  if (lane == 0) {
+    issue_aux(blk);
+    issue(blk, 0);
+    issue(blk + nwarps, 1);
   }
-  stamp(1);
-  long long* const pin = P.pend + (size_t)(k & 1) * 3 * (size_t)P.n_pad;     /* filled during slot k-1 */
-  long long pd_next[3] = {0, 0, 0};
-  int col_next = -1;                 /* TimedArray column of the neuron (only read when a timed current is set) */
-#if HHD_NEURON_PREFETCH
-  issue(tile, 0);
-  if (tile < ntiles && tile * NEURON_BLOCK + tid < P.N) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) pd_next[c] = pin[(size_t)c * P.n_pad + tile * NEURON_BLOCK + tid];
-    if ((TIMED && P.iac_table)) col_next = P.iac_col[tile * NEURON_BLOCK + tid];
-  }
-#endif
-#if HHD_NEURON_PREFETCH >= 2
-  issue(tile_nxt, 1);                /* two tiles in flight from the start */
-#endif
-  /* PIPE: after its first two tiles a CTA draws its tiles from a counter (the synaptic share above takes a different
-   * time in every CTA; whoever is done earlier integrates more) — otherwise tile, tile + grid, tile + 2 grid, ... */
-  for (int it = 0; tile < ntiles; ++it) {
-    if (DYN && tid == 0 && it + 2 >= n_static) sh.tile_fetch[it & 1] = dyn_base + (int)atomicAdd(P.tile_ctr, 1u);
-    const int i = tile * NEURON_BLOCK + tid;
+  /* last_spike lives per GLOBAL neuron (other ranks' neurons too) and is fetched one tile ahead into a register */
+  double ls_next = (blk < nblocks && blk * NB_LANES + (int)lane < P.N) ? P.last_spike[P.off + blk * NB_LANES + lane] : 0.0;
+  int col_next = -1;
+  if (TIMED && P.iac_table && blk < nblocks && blk * NB_LANES + (int)lane < P.N) col_next = P.iac_col[blk * NB_LANES + lane];
+
+  for (int it = 0; blk < nblocks; ++it, blk += nwarps) {
+    const int s = it & 1;
+    const int i = blk * NB_LANES + lane;
     const bool live = i < P.N;
+    mbar_wait(&bar[NEURON_STAGES], (parity >> NEURON_STAGES) & 1u);
+    mbar_wait(&bar[s], (parity >> s) & 1u);
+    parity ^= (1u << s) | (1u << NEURON_STAGES);
     double x[8];
     NeuronPar p;
-    double ls = 0.0;
-    int meta = 0;
-    long long pd[3] = {0, 0, 0};
-    int col = -1;
-#if !HHD_NEURON_PREFETCH
-    if (live) {
 #pragma unroll
-      for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
-      p = load_par(P, i);
-      ls = P.last_spike[P.off + i];
-      meta = P.meta[i];
+    for (int v = 0; v < 8; ++v) x[v] = st[s].f[v][lane];
+    p.C = st[s].f[NB_STATE + HHD_P_C][lane]; p.gL = st[s].f[NB_STATE + HHD_P_GL][lane]; p.EL = st[s].f[NB_STATE + HHD_P_EL][lane];
+    p.dT = st[s].f[NB_STATE + HHD_P_DELTAT][lane]; p.Vup = st[s].f[NB_STATE + HHD_P_VUP][lane]; p.tauw = st[s].f[NB_STATE + HHD_P_TAUW][lane];
+    p.b = st[s].f[NB_STATE + HHD_P_B][lane]; p.Vr = st[s].f[NB_STATE + HHD_P_VR][lane]; p.VT = st[s].f[NB_STATE + HHD_P_VT][lane];
+    p.Iref = st[s].f[NB_STATE + HHD_P_IREF][lane]; p.Vdep = st[s].f[NB_STATE + HHD_P_VDEP][lane]; p.IDC = st[s].f[NB_STATE + HHD_P_IDC][lane];
+    long long pd[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) pd[c] = pin[(size_t)c * P.n_pad + i];
+    for (int c = 0; c < 3; ++c) pd[c] = aux->pend[c][lane];
+    const int meta = aux->meta[lane];
+    const double ls = ls_next;
+    const int col = col_next;
+    /* the warp holds its tile in registers: hand the stage back and request the tile after next */
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      issue_aux(blk + nwarps);
+      issue(blk + 2 * nwarps, s);
     }
-    if (false) {
-      const int s = 0;
-#elif HHD_NEURON_PREFETCH >= 2
-    const int s = it & 1;
-    cp_async_wait<1>();
-    mbar_wait(&full_bar[s * NGROUPS + grp], (bar_parity >> (s * NGROUPS + grp)) & 1u);
-    bar_parity ^= 1u << (s * NGROUPS + grp);
-    if (live) {
-#else
-    const int s = it & 1;
-    issue(tile + gridDim.x, s ^ 1);
-    cp_async_wait<1>();
-    if (live) {
-#endif
-#pragma unroll
-      for (int v = 0; v < 8; ++v) x[v] = st[s].f[v][tid];
-      p.C = st[s].f[8 + HHD_P_C][tid]; p.gL = st[s].f[8 + HHD_P_GL][tid]; p.EL = st[s].f[8 + HHD_P_EL][tid];
-      p.dT = st[s].f[8 + HHD_P_DELTAT][tid]; p.Vup = st[s].f[8 + HHD_P_VUP][tid]; p.tauw = st[s].f[8 + HHD_P_TAUW][tid];
-      p.b = st[s].f[8 + HHD_P_B][tid]; p.Vr = st[s].f[8 + HHD_P_VR][tid]; p.VT = st[s].f[8 + HHD_P_VT][tid];
-      p.Iref = st[s].f[8 + HHD_P_IREF][tid]; p.Vdep = st[s].f[8 + HHD_P_VDEP][tid]; p.IDC = st[s].f[8 + HHD_P_IDC][tid];
-      ls = st[s].f[20][tid];
-      meta = st[s].meta[tid];
+    {
+      const int in = (blk + nwarps) * NB_LANES + (int)lane;
+      const bool nlive = blk + nwarps < nblocks && in < P.N;
+      ls_next = nlive ? P.last_spike[P.off + in] : 0.0;
+      if (TIMED && P.iac_table) col_next = nlive ? P.iac_col[in] : -1;
     }
-#if HHD_NEURON_PREFETCH
-    {   /* pending increments: this tile's were requested one iteration ago, the next tile's are requested now */
-#pragma unroll
-      for (int c = 0; c < 3; ++c) pd[c] = pd_next[c];
-      const int in = tile_nxt * NEURON_BLOCK + tid;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) pd_next[c] = in < P.N ? pin[(size_t)c * P.n_pad + in] : 0;
-      col = col_next;
-      col_next = ((TIMED && P.iac_table) && in < P.N) ? P.iac_col[in] : -1;
-    }
-#else
-    if ((TIMED && P.iac_table) && live) col = P.iac_col[i];
-#endif
-#if HHD_NEURON_PREFETCH == 2
-    __syncthreads();   /* every thread holds its neuron of this tile in registers: stage s is free again */
-    const int tile_nn = (DYN && it + 2 >= n_static) ? sh.tile_fetch[it & 1] : tile + 2 * (int)gridDim.x;
-    issue(tile_nn, s);                 /* so the tile after next is requested NOW: two tiles in flight with two stages */
 
-#elif HHD_NEURON_PREFETCH == 3
-    __syncwarp();      /* the warp's part of stage s is free again */
-    const int tile_nn = tile + 2 * (int)gridDim.x;
-    issue(tile_nn, s);
-#else
-    const int tile_nn = tile + 2 * (int)gridDim.x;
-#endif
-    tile = tile_nxt;
-    tile_nxt = tile_nn;
     SubExpr S;
     bool wcross = false;
     double iac0 = 0.0, iac1 = 0.0;
-    if (live) {
+#if HHD_EXPERIMENT & 4
+    S.I_tot = x[0] + p.C + p.gL + p.EL + p.dT + p.Vup + p.tauw + p.b + p.Vr + p.VT + p.Iref + p.Vdep + p.IDC + (double)pd[0] + (double)pd[1] + (double)pd[2];   /* timing experiment: data movement only */
+    x[1] += S.I_tot * 1e-300;
+#else
+    {
       /* ---- the part of step k-1 that had to wait for that step's synaptic deliveries ------------------------------
        * x is the state right after the integration of step k-1.  Its subexpressions S decide the `w_crossing` event of
        * step k-1 (slot `thresholds`, codes/CortexNetwork.py:306) and — unless this neuron received input or was reset,
        * and then only their linear part changes — ARE the subexpressions of the first stage of step k: one evaluation
        * (two exponentials, three divisions) per neuron-step instead of two. */
       double iac_prev = 0.0, iac_now = 0.0, iac_nxt = 0.0;      /* I_AC at steps k-1, k, k+1 */
-      if ((TIMED && P.iac_table)) {
+      if (TIMED && P.iac_table) {
         iac_prev = iac_at(P, col, k - 1);
         iac_now = iac_at(P, col, k);
         iac_nxt = iac_at(P, col, k + 1);
@@ -526,7 +487,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
           const double inc = P.accum == HHD_ACCUM_FIXED ? (double)pd[c] * (1.0 / 1099511627776.0) : __longlong_as_double(pd[c]);
           x[2 + 2 * c] += inc;
           x[3 + 2 * c] += inc;
-          pin[(size_t)c * P.n_pad + i] = 0;
+          pin[pend_index(c, i)] = 0;
           new_g = true;
         }
       }
@@ -538,76 +499,81 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
         hhd_subexpr_new_g(P.cc, p, x, S);
       }
       if (wcross) x[1] = S.w_V - hhd_div(S.D0, p.tauw);      /* slot `after_resets`: w = w_V - D0/tau_w   (:311) */
-      if (iac_now != iac_prev) {          /* the clock moves on: I_inj of step k; again only the linear part changes */
+      if (TIMED && iac_now != iac_prev) {  /* the clock moves on: I_inj of step k; again only the linear part changes */
         S.I_inj = p.IDC + iac_now;
         hhd_subexpr_new_g(P.cc, p, x, S);
       }
       iac0 = iac_now;
       iac1 = iac_nxt;
     }
+#endif
+    double* const xo = P.nb + nb_index(0, i);
     if (!STEP) {
-      if (live) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
-        P.meta[i] = meta & ~3;
-      }
-      n_wc += wcross;
+      for (int v = 0; v < 8; ++v) xo[v * NB_LANES] = x[v];
+      P.meta[i] = meta & ~3;
+      n_wc += wcross && live;
       continue;
     }
 
     /* ---- slot `start`: monitors sample the pre-update state (codes/CortexNetwork.py:510) ----------------------------- */
-    for (int m = 0; m < P.n_mon; ++m) {
-      const MonDesc& md = mon_sh[m];
-      if (!md.active) continue;
-      const long long sample = k - md.k0;
-      if (sample < 0 || sample >= md.capacity) {
-        if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
-        continue;
-      }
-      int slot = -1;
-      if (live) slot = md.slot ? md.slot[i] : i;
-      if (slot >= 0) {
-        const double v = hhd_var_is_derived(md.var) ? hhd_var_from_subexpr(S, md.var) : hhd_var_value(P.cc, p, x, md.var, ls);
-        if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
-        else {
+    if (MON) {
+      for (int m = 0; m < P.n_mon; ++m) {
+        const MonDesc& md = sh.mon[m];
+        if (!md.active) continue;
+        const long long sample = k - md.k0;
+        if (sample < 0 || sample >= md.capacity) {
+          if (i == 0) atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+          continue;
+        }
+        int slot = -1;
+        if (live) slot = md.slot ? md.slot[i] : i;
+        if (slot >= 0) {
+          const double v = hhd_var_is_derived(md.var) ? hhd_var_from_subexpr(S, md.var) : hhd_var_value(P.cc, p, x, md.var, ls);
+          if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
+          else {                 /* branch-free, so that the accumulators stay in registers (an indexed update put them in local memory) */
 #pragma unroll
-          for (int r = 0; r < MAX_RED; ++r) if (r == md.red_slot) mon_acc[r] += v;
+            for (int r = 0; r < MAX_RED; ++r) mon_acc[r] += (r == md.red_slot) ? v : 0.0;
+          }
         }
       }
     }
 
-    bool spiked = false, bad = false;
-    if (live) {
-      /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
+    /* ---- slot `groups`: state update (:308-309) ------------------------------------------------------------ */
 #if !(HHD_EXPERIMENT & 2)
-      double hcar = METHOD == 3 ? P.hstep[i] : 0.0;
-      hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S, iac0, iac1, &hcar);
-      if (METHOD == 3) P.hstep[i] = hcar;
-      if (TIMED && METHOD == 0 && P.noise_sigma) {
-        /* Euler-Maruyama term of Brian's stochastic `euler` updater: x + dt f(x) + xi sigma, xi = sqrt(dt) N(0,1) */
-        const double sg = P.noise_sigma[i] * P.sqrt_dt;
-        if (sg != 0.0) {
-          double z0, z1, z2, z3;
-          hhd_normal2(P.seed, (unsigned long long)(P.off + i), (unsigned long long)k, 2, &z0, &z1);
-          hhd_normal2(P.seed, (unsigned long long)(P.off + i), (unsigned long long)k, 3, &z2, &z3);
-          x[3] = x[3] + z0 * sg;
-          x[5] = x[5] + z1 * sg;
-          x[7] = x[7] + z2 * sg;
-        }
+    double hcar = METHOD == 3 ? P.hstep[i] : 0.0;
+    hhd_integrate<METHOD>(P.cc, p, x, t, ls, P.dt, S, iac0, iac1, &hcar);
+    if (METHOD == 3) P.hstep[i] = hcar;
+    if (TIMED && METHOD == 0 && P.noise_sigma && live) {
+      /* Euler-Maruyama term of Brian's stochastic `euler` updater: x + dt f(x) + xi sigma, xi = sqrt(dt) N(0,1) */
+      const double sg = P.noise_sigma[i] * P.sqrt_dt;
+      if (sg != 0.0) {
+        double z0, z1, z2, z3;
+        hhd_normal2(P.seed, (unsigned long long)(P.off + i), (unsigned long long)k, 2, &z0, &z1);
+        hhd_normal2(P.seed, (unsigned long long)(P.off + i), (unsigned long long)k, 3, &z2, &z3);
+        x[3] = x[3] + z0 * sg;
+        x[5] = x[5] + z1 * sg;
+        x[7] = x[7] + z2 * sg;
       }
-#endif
-      bad = !(isfinite(x[0]) && isfinite(x[1]));
-      /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
-      const int lastk = meta >> META_SHIFT;
-      spiked = (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
-#pragma unroll
-      for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
-      P.meta[i] = ((spiked ? (int)k : lastk) << META_SHIFT) | (meta & (FLAG_OUT | FLAG_ZERO)) | (spiked ? FLAG_SPIKED : 0) | FLAG_HAS_PREV;
     }
+#endif
+    const bool bad = live && !(isfinite(x[0]) && isfinite(x[1]));
+    /* ---- slot `thresholds` (:304); the w_crossing test of this step runs at the start of the next pass ------------ */
+    const int lastk = meta >> META_SHIFT;
+    const bool spiked = live && (x[0] > p.Vup) && ((k - (long long)lastk) >= (long long)P.refr_steps);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+#if HHD_L2_HINTS
+      st_hint(xo + v * NB_LANES, x[v], pol_keep);
+#else
+      xo[v * NB_LANES] = x[v];
+#endif
+    }
+    P.meta[i] = ((spiked ? (int)k : lastk) << META_SHIFT) | (meta & (FLAG_OUT | FLAG_ZERO)) | (spiked ? FLAG_SPIKED : 0) | FLAG_HAS_PREV;
     /* ---- warp-ballot spike compaction: one atomic per warp that has spikes ----------------------------------- */
     const unsigned bal = __ballot_sync(0xffffffffu, spiked);
     if (bal) {
-      if (P.n_ranks > 1) {          /* partitioned network: the step's local spikes go to the all-gather send buffer */
+      if (P.n_ranks > 1) {          /* partitioned network: the step's local spikes go to the exchange's send list */
         int base = 0;
         if (lane == 0) base = atomicAdd(&P.xchg_send[0], __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -630,22 +596,12 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
           P.prev_spike[j] = ls;
           if (meta & FLAG_OUT) P.last_spike[j] = t;
           if (P.spk_hist) P.spk_hist[(size_t)j * P.hist_depth + hist_slot(P, (int)k)] = (int)k;
-          if (PIPE && (meta & FLAG_ZERO)) {  /* zero-delay synapses: served by this CTA after its last tile; beyond 16, by the CTA that closes the pass */
-            const int q = atomicAdd(&sh.zl_n, 1);
-            if (q < 16) sh.zl_j[q] = j; else P.zlist[atomicAdd(P.zcount, 1u)] = j;
-          }
         }
       }
     }
     n_spk += spiked;
-    n_wc += wcross;
+    n_wc += wcross && live;
     n_bad += bad;
-  }
-  cp_async_wait<0>();
-  stamp(2);
-  if (PIPE && STEP) {
-    __syncthreads();
-    if (tid < min(sh.zl_n, 16)) spike_local(P, sh.zl_j[tid], k, t);
   }
   if (!STEP) {                      /* only the w_crossing events found while finishing the last step are left to count */
     n_wc = __reduce_add_sync(0xffffffffu, n_wc);
@@ -654,80 +610,78 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   }
 
   /* ---- once per CTA: reduced monitors (LFP) and counters ------------------------------------------------------- */
-  for (int m = 0; m < P.n_mon; ++m) {
-    const MonDesc& md = mon_sh[m];
-    if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
-    const long long sample = k - md.k0;
-    if (sample < 0 || sample >= md.capacity) continue;
-    double mine = 0.0;
+  if (MON) {
 #pragma unroll
-    for (int r = 0; r < MAX_RED; ++r) if (r == md.red_slot) mine = mon_acc[r];
-    const double ws = warp_sum(mine);
-    if (lane == 0) red[m][tid >> 5] = ws;
+    for (int r = 0; r < MAX_RED; ++r) {
+      const double ws = warp_sum(mon_acc[r]);
+      if (lane == 0) sh.red[r][warp] = ws;
+    }
   }
   n_spk = __reduce_add_sync(0xffffffffu, n_spk);
   n_wc = __reduce_add_sync(0xffffffffu, n_wc);
   n_bad = __reduce_add_sync(0xffffffffu, n_bad);
-  __syncthreads();
   if (lane == 0) {
-    if (n_spk) atomicAdd(&cnt_sh[0], (unsigned long long)n_spk);
-    if (n_wc) atomicAdd(&cnt_sh[1], (unsigned long long)n_wc);
-    if (n_bad) atomicAdd(&cnt_sh[2], (unsigned long long)n_bad);
+    if (n_spk) atomicAdd(&sh.cnt[0], (unsigned long long)n_spk);
+    if (n_wc) atomicAdd(&sh.cnt[1], (unsigned long long)n_wc);
+    if (n_bad) atomicAdd(&sh.cnt[2], (unsigned long long)n_bad);
   }
   __syncthreads();
+  const bool closes = MON || P.n_ranks > 1;      /* someone has to know when the whole grid is done */
   if (tid == 0) {
-    if (cnt_sh[0]) atomicAdd(&P.counters[CNT_SPIKES], cnt_sh[0]);
-    if (cnt_sh[1]) atomicAdd(&P.counters[CNT_WCROSS], cnt_sh[1]);
-    if (cnt_sh[2]) atomicAdd(&P.counters[CNT_NONFINITE], cnt_sh[2]);
-    for (int m = 0; m < P.n_mon; ++m) {
-      const MonDesc& md = mon_sh[m];
-      if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
-      const long long sample = k - md.k0;
-      if (sample < 0 || sample >= md.capacity) continue;
-      double bsum = 0.0;
+    if (sh.cnt[0]) atomicAdd(&P.counters[CNT_SPIKES], sh.cnt[0]);
+    if (sh.cnt[1]) atomicAdd(&P.counters[CNT_WCROSS], sh.cnt[1]);
+    if (sh.cnt[2]) atomicAdd(&P.counters[CNT_NONFINITE], sh.cnt[2]);
+    if (MON) {
+      /* per-CTA partial sums of the reduced monitors; the CTA that finishes last adds them in CTA order, so the trace does
+       * not depend on the order in which CTAs finish (round 1 used one fp64 atomicAdd per CTA: run-to-run different bits) */
 #pragma unroll
-      for (int q = 0; q < NEURON_BLOCK / 32; ++q) bsum += red[m][q];
-      atomicAdd(&md.buf[sample], bsum);
+      for (int r = 0; r < MAX_RED; ++r) {
+        double bsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NEURON_WARPS; ++q) bsum += sh.red[r][q];
+        P.mon_part[(size_t)r * gridDim.x + blockIdx.x] = bsum;
+      }
     }
-    if (PIPE) {
+    if (closes) {
       __threadfence();
       sh.is_last = atomicAdd(P.pass_done, 1u) == gridDim.x - 1;
     }
   }
-  stamp(3);
-  if (PIPE) {          /* the last CTA to finish closes the step: every spike of step k is in the ring below *head */
-    __syncthreads();
-    if (sh.is_last) {
-      __threadfence();
-      const unsigned nz = *(volatile unsigned*)P.zcount;           /* spikes of this step whose row has zero-delay synapses (rare) */
-      for (unsigned q = tid; q < nz; q += NEURON_BLOCK) spike_local(P, ((volatile int*)P.zlist)[q], k, t);
-      __syncthreads();
-      if (tid == 0) {
-        if (P.dbg_times) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); P.dbg_times[8 * 4096 + (k & 4095) * 2 + 1] = g; }
-        *P.zcount = 0u;
-        *P.pass_done = 0u;
-        *P.tile_ctr = 0u;
-        *P.stp_mark = P.step_end[((int)k + P.W - 1) % P.W];     /* ahead_phase of this pass applied p0..p6 up to here */
-        P.step_end[(int)k % P.W] = *(volatile unsigned long long*)P.head;
-      }
+  if (!closes) return;
+  __syncthreads();
+  if (!sh.is_last) return;
+  __threadfence();
+  if (MON) {
+    for (int m = warp; m < P.n_mon; m += NEURON_WARPS) {
+      const MonDesc& md = sh.mon[m];
+      if (!md.active || md.reduce == HHD_REDUCE_NONE) continue;
+      const long long sample = k - md.k0;
+      if (sample < 0 || sample >= md.capacity) continue;
+      /* fixed order: lane l adds CTAs l, l + 32, ...; then the butterfly */
+      double acc = 0.0;
+      const volatile double* part = P.mon_part + (size_t)md.red_slot * gridDim.x;
+      for (unsigned b = lane; b < gridDim.x; b += 32) acc += part[b];
+      acc = warp_sum(acc);
+      if (lane == 0) md.buf[sample] = md.buf[sample] + acc;
     }
   }
+  if (P.n_ranks > 1 && P.peer_buf[P.rank]) push_spikes(P, k);     /* the exchange's send half (exchange over peer memory) */
+  if (tid == 0) *P.pass_done = 0u;
 }
 
 /*
  * METHOD: 0 euler, 1 rk2, 2 rk4, 3 adaptive rk2(3).  STEP = false: only finish the previous step (used once at the end of
  * hhd_run so that the state read back is the state after `resets`/`after_resets`).
  */
-template <int METHOD, bool STEP, bool TIMED = false, bool PIPE = false>
-__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ NeuronShared sh;
+template <int METHOD, bool STEP, bool TIMED = false, bool MON = false>
+__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? HHD_NEURON_MINBLOCKS_RK2 : HHD_NEURON_MINBLOCKS_RK4)) k_neuron(const __grid_constant__ Params P, const int step_offset) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ NeuronShared<MON> sh;
   pdl_wait();
-  neuron_shared_init(P, sh);
-  unsigned bar_parity = 0;
-  neuron_phase<METHOD, STEP, TIMED, PIPE>(P, *P.base_step + step_offset, reinterpret_cast<NeuronStage*>(smem_raw), sh, bar_parity);
+  neuron_phase<METHOD, STEP, TIMED, MON>(P, *P.base_step + step_offset, smem_raw, sh);
   pdl_trigger();     /* at the END: a dependent launched earlier would take the SM resources this grid's own CTAs still need */
 }
+
 
 /* buffer that collects the deliveries of slot k */
 __device__ __forceinline__ long long* pend_of_slot(const Params& P, long long k) {
@@ -737,9 +691,9 @@ __device__ __forceinline__ void add_increment(const Params& P, long long* pout, 
   /* summed per (channel, target) for this step; the target's next state-update pass adds the sum to g_on and g_off */
   if (P.accum == HHD_ACCUM_FIXED) {
     const long long q = __double2ll_rn(inc * 1099511627776.0);
-    atomicAdd((unsigned long long*)&pout[(size_t)c * P.n_pad + tgt], (unsigned long long)q);
+    atomicAdd((unsigned long long*)&pout[pend_index(c, tgt)], (unsigned long long)q);
   } else {
-    atomicAdd(reinterpret_cast<double*>(&pout[(size_t)c * P.n_pad + tgt]), inc);
+    atomicAdd(reinterpret_cast<double*>(&pout[pend_index(c, tgt)]), inc);
   }
 }
 
@@ -768,36 +722,9 @@ __device__ __forceinline__ unsigned deliver_row_due(const Params& P, long long* 
   return n;
 }
 
-
-/* ---- pipelined schedule -------------------------------------------------------------------------------------------
- * Legal while max_delay < refractory steps (a neuron never has a new spike and an undelivered older one) on a
- * single rank.  What pass k+1 must see of the spikes of step k is only last_spike (p5) and the zero-delay deliveries —
- * spike_local, by the detecting thread.  Everything else of slot k+1 depends on spikes of steps <= k only, so pass k+1
- * computes it itself while it integrates (ahead_phase) and pass k+2 consumes it. */
-/* zero-delay synapses of neuron j, which spiked in step k (time t): p0..p6 and delivery for those synapses only */
-__device__ __forceinline__ void spike_local(const Params& P, int j, long long k, double t) {
-  const double last = ((volatile double*)P.prev_spike)[j];
-  const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-  long long* const pout = pend_of_slot(P, k);
-  unsigned long long n = 0;
-  for (long long r = r0; r < r1; ++r) {
-    const SynHot sh = P.hot[r];
-    if (sh.delay != 0) break;
-    SynStp sy = P.stp[r];
-    const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t, last,
-                                      P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)k);
-    P.stp[r].u = sy.u;
-    P.stp[r].R = sy.R;
-    P.hot[r].amp = amp;
-    ++n;
-    if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
-  }
-  atomicAdd(&P.del_slots[j & (CNT_SLOTS - 1)], n);
-}
-
 /* Lane-per-spike delivery.  due_segment: the synapses of the spike in ring entry sp that are due in slot k, as a segment
  * (first record, count) of its delay-sorted row, straight from the row's per-delay offsets.  skip_respiked: leave out
- * neurons that spiked again in step k (serial schedule with long delays: k_spike_new delivers for them). */
+ * neurons that spiked again in step k (long delays: the spike-time half delivers for them). */
 __device__ __forceinline__ void due_segment(const Params& P, const long long k, const unsigned long long sp, const bool skip_respiked,
                                             long long& ra, unsigned& cnt) {
   const unsigned pos = (unsigned)sp & P.cap_mask;
@@ -850,177 +777,51 @@ __device__ __forceinline__ void deliver_flat(const Params& P, long long* const p
   }
 }
 
-/* p0..p6 for ONE synapse of a spike of step ks (spike time ts, previous spike of the neuron `last`); slot >= 0: deliver
- * it too if it is due in that slot.  Zero-delay synapses were handled by spike_local at the spike's own step. */
-__device__ __forceinline__ void stp_apply(const Params& P, const long long slot, long long* const pout, const long long r,
-                                          const SynHot& sh, SynStp sy, const long long ks, const double ts, const double last,
-                                          unsigned long long& delivered) {
-  if (sh.delay == 0) return;
-  const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, ts, last,
-                                    P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)ks);
-  P.stp[r].u = sy.u;
-  P.stp[r].R = sy.R;
-  P.hot[r].amp = amp;
-  if (slot >= 0 && (long long)sh.delay == slot - ks) {
-    ++delivered;
-    if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
-  }
-}
-
-/* p0..p6 for the ring entries [lo, hi) (spikes whose rows were not processed yet).  A task is one block of NEURON_BLOCK
- * consecutive synapses of one spike's row, stp_chunks tasks per spike (rows longer than that wrap around; the chunk count
- * follows the mean row); CTA `part` of `nparts` takes the tasks first_task, first_task + nparts, ... */
-__device__ __forceinline__ void stp_range(const Params& P, const long long slot, const unsigned long long lo,
-                                          const unsigned long long hi, const unsigned first_task, const unsigned nparts,
-                                          unsigned long long& delivered) {
-  long long* const pout = pend_of_slot(P, slot);
-  const unsigned chunks = (unsigned)P.stp_chunks;
-  const unsigned ntasks = (unsigned)(hi - lo) * chunks;                 /* far below 2^32: one spike per neuron and step at most */
-  for (unsigned task = first_task; task < ntasks; task += nparts) {
-    const unsigned chunk = task % chunks;
-    const unsigned pos = (unsigned)(lo + task / chunks) & P.cap_mask;
-    const int j = P.spk_neuron[pos];
-    const long long ks = (long long)P.spk_step[pos];
-    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-    if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
-    const double ts = (double)ks * P.dt;
-    const double last = P.prev_spike[j];
-    for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x)
-      stp_apply(P, slot, pout, r, P.hot[r], P.stp[r], ks, ts, last, delivered);
-  }
-}
-
 __device__ __forceinline__ void ext_events(const Params& P, const long long k, long long* const pout, const unsigned gtid, const unsigned gthreads);
 
-/* This CTA's share of slot k in the pipelined schedule:
- *  - p0..p6 of the spikes of step k-1 (and the delivery of their delay-1 synapses): one task per CTA, usually;
- *  - the due synapses of every older active spike: the active spikes are spread evenly over every warp of the share
- *    (spw per warp); each lane looks up the due segment of ITS spike in the row's per-delay offsets, then the warp walks
- *    the concatenation of its lanes' segments 32 synapses at a time (the segments are very uneven, 0..~100);
- *  - the SpikeGeneratorGroup events of step k.
- * Both chains are three dependent loads deep into 23 GB of synapse data (TLB misses included), and that latency is all
- * this costs: the loads of the CTA's first STP task and of each warp's first group are issued level by level together,
- * before anything is stored. */
-__device__ __forceinline__ void ahead_phase(const Params& P, const long long k, const unsigned part, const unsigned nparts) {
-  const unsigned lane = threadIdx.x & 31;
-  long long* const pout = pend_of_slot(P, k);
-  const unsigned long long lo = P.step_end[((int)k + 1) % P.W];        /* head at the end of step k - max_delay - 1 */
-  const unsigned long long hi = P.step_end[((int)k + P.W - 1) % P.W];  /* head at the end of step k - 1 */
-  const unsigned long long mark = *P.stp_mark;
-  const unsigned gthreads = nparts * blockDim.x;
-  const unsigned chunks = (unsigned)P.stp_chunks;
-  const unsigned ntasks = (unsigned)(hi - mark) * chunks;
-  const unsigned nact = (unsigned)(mark - lo);
-  const unsigned warps = gthreads >> 5;
-  const unsigned spw = min(32u, (nact + warps - 1) / warps);
-  /* the warps are walked from the far end of the share for the deliveries and the CTAs from the near end for the STP
-   * tasks: nobody gets both unless there is more work than CTAs */
-  const unsigned wid = (nparts - 1 - part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const unsigned long long first0 = lo + (unsigned long long)wid * spw;
-
-  /* ---- level 1: ring entries ---- */
-  const bool stp0 = part < ntasks;
-  int sj = 0;
-  long long sks = 0;
-  if (stp0) {
-    const unsigned pos = (unsigned)(mark + part / chunks) & P.cap_mask;
-    sj = P.spk_neuron[pos];
-    sks = (long long)P.spk_step[pos];
-  }
-  /* ---- levels 1-2 of the warp's first group, level 2 of the STP task: rows ---- */
-  long long dra = 0;
-  unsigned dcnt = 0;
-  if (spw && lane < spw && first0 + lane < mark) due_segment(P, k, first0 + lane, false, dra, dcnt);
-  long long sr0 = 0, sr1 = 0;
-  double slast = 0.0;
-  if (stp0) { sr0 = P.row_ptr[sj]; sr1 = P.row_ptr[sj + 1]; slast = P.prev_spike[sj]; }
-  /* ---- level 3: synapse records ---- */
-  const unsigned schunk = part % chunks;
-  const long long sr = sr0 + (long long)schunk * blockDim.x + threadIdx.x;
-  const bool sval = stp0 && sr < sr1;
-  SynHot ssh;
-  SynStp ssy;
-  if (sval) { ssh = P.hot[sr]; ssy = P.stp[sr]; }
-
-  unsigned long long delivered = 0;
-  for (unsigned long long first = first0; first < mark && spw; first += (unsigned long long)warps * spw) {
-    long long ra = dra;
-    unsigned cnt = dcnt;
-    if (first != first0) {               /* further groups of this warp (only when there are more than 32 spikes per warp) */
-      ra = 0;
-      cnt = 0;
-      if (lane < spw && first + lane < mark) due_segment(P, k, first + lane, false, ra, cnt);
-    }
-    deliver_flat(P, pout, ra, cnt, lane, delivered);
-  }
-  delivered = (unsigned long long)warp_sum((double)delivered);
-  if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
-
-  /* ---- p0..p6: the prefetched task, the rest of its row if it is longer than stp_chunks blocks, further tasks ---- */
-  unsigned long long sdel = 0;
-  if (stp0) {
-    const double ts = (double)sks * P.dt;
-    if (schunk == 0 && threadIdx.x == 0 && sr1 > sr0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(sr1 - sr0));
-    if (sval) stp_apply(P, k, pout, sr, ssh, ssy, sks, ts, slast, sdel);
-    for (long long r = sr + (long long)chunks * blockDim.x; r < sr1; r += (long long)chunks * blockDim.x)
-      stp_apply(P, k, pout, r, P.hot[r], P.stp[r], sks, ts, slast, sdel);
-    stp_range(P, k, mark, hi, part + nparts, nparts, sdel);
-  }
-  sdel = (unsigned long long)warp_sum((double)sdel);
-  if (lane == 0 && sdel) atomicAdd(&P.del_slots[(part * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], sdel);
-  ext_events(P, k, pout, part * blockDim.x + threadIdx.x, gthreads);
-}
-
-/* End of a run in the pipelined schedule: p0..p6 of the spikes of the last step, so that the synaptic state read back
- * (and the amplitudes the next run delivers) are complete; the next pass finds nothing below the mark left to do. */
-__global__ void __launch_bounds__(STP_BLOCK) k_stp_flush(const __grid_constant__ Params P) {
-  unsigned long long none = 0;
-  stp_range(P, -1, *P.stp_mark, *P.head, blockIdx.x, gridDim.x, none);
-}
-__global__ void k_set_mark(const __grid_constant__ Params P) { *P.stp_mark = *P.head; }
-
 /*
- * The serial schedule (delays that can outlast the refractory period, partitioned networks, the cooperative plan): after
- * the state update of step k, two concurrent launches make slot k.
+ * Slot `synapses` of step k is ONE launch (k_synapse) whose CTAs split into two roles.
  *
- * k_spike_new: pathways p0..p6 (`u`, `R`, `a_syn`, failure draw at the presynaptic spike, codes/CortexNetwork.py:351-366)
- * for the spikes of THIS step plus their zero-delay deliveries.  A task is one block of STP_BLOCK consecutive synapses of
- * one spike's row, stp_chunks tasks per spike, so a spike's row is rewritten by several CTAs at once; the previous spike
- * time it needs was saved by note_spike.
+ * Spike-time half (CTAs [0, stp_blocks)): pathways p0..p6 (`u`, `R`, `a_syn`, failure draw at the presynaptic spike,
+ * codes/CortexNetwork.py:351-366) for the spikes of THIS step plus their zero-delay deliveries.  A task is one block of
+ * STP_BLOCK consecutive synapses of one spike's row, stp_chunks tasks per spike, so a spike's row is rewritten by several
+ * CTAs at once; the previous spike time it needs was saved by note_spike.
  * LONG = true (some delay >= refractory steps): the neuron may still have older spikes in flight whose deliveries must
  * use the amplitudes just rewritten.  Their steps are in the neuron's history; every thread checks ITS synapse
- * against them and delivers it if one of them is due now, while k_deliver<DELIVER_MAIN> skips every neuron that spiked in
+ * against them and delivers it if one of them is due now, while the delivery half skips every neuron that spiked in
  * this step.
  */
 template <bool LONG>
-__device__ __forceinline__ void spike_new_phase(const Params& P, const long long k) {
+__device__ __forceinline__ void spike_new_phase(const Params& P, const long long k, const unsigned bid, const unsigned nblk) {
+  __shared__ int older_sh[17];
   const double t = (double)k * P.dt;
   const unsigned lane = threadIdx.x & 31;
   long long* const pout = pend_of_slot(P, k);
   const unsigned long long lo_new = P.step_end[((int)k + P.W - 1) % P.W];
   const unsigned long long hi = *P.head;
-  if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[(int)k % P.W] = hi;
+  if (bid == 0 && threadIdx.x == 0) P.step_end[(int)k % P.W] = hi;
   unsigned long long delivered = 0;
   const unsigned chunks = (unsigned)P.stp_chunks;
   const unsigned ntasks = (unsigned)(hi - lo_new) * chunks;
-  for (unsigned task = blockIdx.x; task < ntasks; task += gridDim.x) {
+  for (unsigned task = bid; task < ntasks; task += nblk) {
     const unsigned chunk = task % chunks;
     const int j = P.spk_neuron[(unsigned)(lo_new + task / chunks) & P.cap_mask];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
     const double last = P.prev_spike[j];
     if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
-    int older[17];                                             /* ages of the neuron's older spikes that can still deliver, else -1 */
+    /* ages of the neuron's older spikes that can still deliver (else -1): the same for every thread of the task, so they
+     * are worked out once per task into shared memory */
     if (LONG) {
-      const int* hist = P.spk_hist + (size_t)j * P.hist_depth;
-      const int maxd = P.row_maxd[j];
-#pragma unroll
-      for (int q = 0; q < 17; ++q) {
-        older[q] = -1;
-        if (q < P.hist_depth) {
-          const int age = (int)(k - (long long)hist[q]);
-          if (age > 0 && age <= maxd) older[q] = age;
+      __syncthreads();                                         /* the previous task's readers are done */
+      if (threadIdx.x < 17) {
+        int a = -1;
+        if ((int)threadIdx.x < P.hist_depth) {
+          const int age = (int)(k - (long long)P.spk_hist[(size_t)j * P.hist_depth + threadIdx.x]);
+          if (age > 0 && age <= (int)P.row_maxd[j]) a = age;
         }
+        older_sh[threadIdx.x] = a;
       }
+      __syncthreads();
     }
     for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x) {
       const SynHot sh = P.hot[r];
@@ -1032,8 +833,7 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
       P.hot[r].amp = amp;
       bool due = sh.delay == 0;
       if (LONG) {
-#pragma unroll
-        for (int q = 0; q < 17; ++q) if ((int)sh.delay == older[q]) due = true;
+        for (int q = 0; q < P.hist_depth; ++q) if ((int)sh.delay == older_sh[q]) due = true;
       }
       if (due) {
         ++delivered;
@@ -1042,30 +842,20 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
     }
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
-  if (lane == 0 && delivered) atomicAdd(&P.del_slots[(blockIdx.x * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], delivered);
+  if (lane == 0 && delivered) atomicAdd(&P.del_slots[(bid * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], delivered);
 }
 
+/* Delivery half (CTAs [stp_blocks, grid)): one LANE per ACTIVE spike of an EARLIER step; with delays beyond the
+ * refractory period (LONG) a neuron that spiked again in this step is skipped here — its amplitudes are being rewritten,
+ * the spike-time half delivers for it.  Also the SpikeGeneratorGroup events of the step. */
 template <bool LONG>
-__global__ void __launch_bounds__(STP_BLOCK) k_spike_new(const __grid_constant__ Params P, const int step_offset) {
-  pdl_wait();
-  spike_new_phase<LONG>(P, *P.base_step + step_offset);
-  pdl_trigger();
-}
-
-/* MODE: DELIVER_FUSED (max_delay < refractory steps) or DELIVER_MAIN (longer delays).  Either way this launch delivers
- * for the spikes of EARLIER steps and runs concurrently with k_spike_new on the second stream; with longer delays a
- * neuron that spiked again in this step is skipped here — its amplitudes are being rewritten, k_spike_new<true> delivers
- * for it. */
-enum { DELIVER_FUSED = 1, DELIVER_MAIN = 2 };
-
-template <int MODE>
-__device__ __forceinline__ void deliver_phase(const Params& P, const long long k) {
+__device__ __forceinline__ void deliver_phase(const Params& P, const long long k, const unsigned bid, const unsigned nblk) {
   const unsigned lane = threadIdx.x & 31;
   long long* const pout = pend_of_slot(P, k);
   const unsigned long long lo = P.step_end[(k + 1) % P.W];             /* head at the end of step k - max_delay - 1 */
   const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];   /* first spike of this step */
-  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
-  const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned warps = (nblk * blockDim.x) >> 5;
+  const unsigned wid = (bid * blockDim.x + threadIdx.x) >> 5;
   unsigned long long delivered = 0;
   if (P.row_doff) {                    /* one LANE per spike of an earlier step, spread evenly over the warps of the grid */
     const unsigned nact = (unsigned)(lo_new - lo);
@@ -1073,7 +863,7 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
     for (unsigned long long first = lo + (unsigned long long)wid * spw; first < lo_new && spw; first += (unsigned long long)warps * spw) {
       long long ra = 0;
       unsigned cnt = 0;
-      if (lane < spw && first + lane < lo_new) due_segment(P, k, first + lane, MODE == DELIVER_MAIN, ra, cnt);
+      if (lane < spw && first + lane < lo_new) due_segment(P, k, first + lane, LONG, ra, cnt);
       deliver_flat(P, pout, ra, cnt, lane, delivered);
     }
   } else
@@ -1082,13 +872,13 @@ __device__ __forceinline__ void deliver_phase(const Params& P, const long long k
     const int j = P.spk_neuron[pos];
     const int age = (int)(k - (long long)P.spk_step[pos]);
     if (age > (int)P.row_maxd[j]) continue;                             /* nothing of this neuron can be due any more */
-    if (MODE == DELIVER_MAIN && P.spk_last[j] == (int)k) continue;      /* spiked again now: k_spike_new<true> */
+    if (LONG && P.spk_last[j] == (int)k) continue;                      /* spiked again now: the spike-time half */
     delivered += deliver_row_due(P, pout, j, age, lane);
   }
   delivered = (unsigned long long)warp_sum((double)delivered);
   if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
 
-  ext_events(P, k, pout, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  ext_events(P, k, pout, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
 }
 
 /* SpikeGeneratorGroup events of step k: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
@@ -1107,46 +897,49 @@ __device__ __forceinline__ void ext_events(const Params& P, const long long k, l
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(DELIVER_BLOCK) k_deliver(const __grid_constant__ Params P, const int step_offset) {
-  pdl_wait();
-  deliver_phase<MODE>(P, *P.base_step + step_offset);
-  pdl_trigger();
-}
-
 /* ================================================================================================================== *
- * Whole-run cooperative plan (HHD_PLAN_PERSISTENT): ONE launch runs a whole segment of time steps on the whole chip.
- * The grid is the persistent state-update grid (every CTA resident, 5 per SM); a step is neuron_phase, grid barrier,
- * spike_new_phase + deliver_phase by the same CTAs, grid barrier.  It removes the three launches and two dependency
- * edges per step of the graph plan (~10 us of a 66 us step at 1M neurons).  Same phase functions, same results.
- * Requires max_delay < refractory steps and a single rank.
+ * Spike exchange of a partitioned network over peer memory (CUDA IPC over NVLink), split over the two launches of a step
+ * so that it costs no launch of its own:
+ *   push_spikes   the CTA of k_neuron that finishes LAST writes this rank's (count, ids...) list of step k into slot
+ *                 [k & 1][rank] of EVERY rank's receive buffer — one warp per peer —, fences at system scope and raises
+ *                 its flag (k + 1) on every rank;
+ *   recv_spikes   CTA 0 of k_synapse waits until every rank's flag in its own buffer has reached k + 1, appends all lists
+ *                 to the spike ring in rank order (note_spike for local and remote neurons) and releases the other CTAs
+ *                 of the launch, which spin on a device flag meanwhile.
+ * Two parities suffice: a rank can only write step k + 2 after it has consumed everybody's step k + 1, which a peer only
+ * sends after it has consumed step k.  A peer that does not arrive within 20 s (it died) is reported through CNT_TIMEOUT
+ * instead of hanging the device.  If the buffers cannot be mapped the engine falls back to ncclAllGather + k_append.
+ * HHD_DEBUG_TIMES: %globaltimer stamps per step — 0 k_neuron's first CTA starts, 1 its last CTA is done, 2 push done,
+ * 3 k_synapse's CTA 0 starts, 4 all flags seen, 5 append done, 6 CTA 0 of k_synapse done.
  * ================================================================================================================== */
-/*
- * The exchange of a partitioned network as ONE launch over peer memory instead of ncclAllGather + k_append (the all-gather
- * costs 18-20 us per step for half a kilobyte of spikes; this is a store over NVLink and a flag).  The block writes this
- * rank's (count, ids...) list of step k into slot [k & 1][rank] of EVERY rank's receive buffer, fences, raises its flag
- * (k + 1) on every rank, waits until every rank's flag in its own buffer has reached k + 1, and appends all lists to the
- * ring in rank order exactly as k_append does.  Two parities suffice: a rank can only write step k + 2 after it has
- * consumed everybody's step k + 1, which a peer only sends after it has consumed step k.  A peer that does not arrive
- * within 20 s (it died) is reported through CNT_TIMEOUT instead of hanging the device.
- */
-/* (one CTA; also called by block 0 of the cooperative whole-run kernel) */
-__device__ __forceinline__ void exchange_phase(const Params& P, const long long k) {
+/* whole CTA (the last one of k_neuron to finish) */
+__device__ __forceinline__ void push_spikes(const Params& P, const long long k) {
   const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
   const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
-  __shared__ unsigned long long base_sh[MAX_RANKS + 1];
-  const int n_mine = min(P.xchg_send[0], P.xchg_cap);
-  /* one warp per peer, all peers at once: list, system-scope fence by every writing lane, then the flag */
+  const int n_mine = min(__ldcg(P.xchg_send), P.xchg_cap);
   const int lane = tid & 31, warp = tid >> 5, n_warps = (int)blockDim.x >> 5;
+  if (tid == 0) dbg_stamp(P, k, 1);
   for (int r = warp; r < P.n_ranks; r += n_warps) {
     int* dst = P.peer_buf[r] + ((size_t)par * P.n_ranks + me) * slot;
-    for (int q = lane; q < n_mine; q += 32) dst[1 + q] = P.xchg_send[1 + q];
+    for (int q = lane; q < n_mine; q += 32) dst[1 + q] = __ldcg(P.xchg_send + 1 + q);
     if (lane == 0) dst[0] = n_mine;
     __threadfence_system();
     __syncwarp();
     if (lane == 0) *(volatile int*)(P.peer_buf[r] + flags_off + me) = (int)(k + 1);
   }
   __syncthreads();
+  if (tid == 0) {
+    P.xchg_send[0] = 0;
+    dbg_stamp(P, k, 2);
+  }
+}
+
+/* CTA 0 of k_synapse */
+__device__ __forceinline__ void recv_spikes(const Params& P, const long long k) {
+  const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
+  const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
+  __shared__ unsigned long long base_sh[MAX_RANKS + 1];
+  if (tid == 0) dbg_stamp(P, k, 3);
   if (tid < P.n_ranks) {
     volatile int* mine = P.peer_buf[me] + flags_off + tid;
     if (!*(volatile unsigned int*)P.xchg_dead) {
@@ -1166,6 +959,7 @@ __device__ __forceinline__ void exchange_phase(const Params& P, const long long 
   __syncthreads();
   const int* recv = P.peer_buf[me] + (size_t)par * P.n_ranks * slot;
   if (tid == 0) {
+    dbg_stamp(P, k, 4);
     unsigned long long b = *P.head;
     for (int r = 0; r < P.n_ranks; ++r) {
       base_sh[r] = b;
@@ -1188,62 +982,41 @@ __device__ __forceinline__ void exchange_phase(const Params& P, const long long 
   __syncthreads();
   if (tid == 0) {
     *P.head = base_sh[P.n_ranks];
-    P.xchg_send[0] = 0;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Params P, const int step_offset) {
-  exchange_phase(P, *P.base_step + step_offset);
-}
-
-/* Grid-wide barrier for a cooperative launch (every CTA resident): one release-add per CTA on a monotone counter, one
- * thread per CTA spins with acquire loads.  The gpu-scope fences also invalidate the SM's L1 (CCTL.IVALL), so data other
- * SMs wrote before the barrier is re-read from L2 afterwards.  Measured ~4x cheaper than cooperative_groups' grid.sync()
- * on 740 CTAs (profiles/r1_notes.md). */
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(counter, 1ull);
-    unsigned long long seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
-    __threadfence();
+    const unsigned long long v = (unsigned long long)(k + 1);
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.xchg_done), "l"(v) : "memory");
+    dbg_stamp(P, k, 5);
   }
   __syncthreads();
 }
 
-template <int METHOD, bool TIMED = false>
-__global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLOCKS_EULER : METHOD == 1 ? 4 : 3)) k_grid(const __grid_constant__ Params P, const int n_steps) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ NeuronShared sh;
-  NeuronStage* st = reinterpret_cast<NeuronStage*>(smem_raw);
-  neuron_shared_init(P, sh);
-  unsigned bar_parity = 0;
-  const long long k0 = *P.base_step;
-  unsigned long long arrived = *P.grid_bar;      /* a multiple of gridDim.x: every earlier launch completed its barriers */
-  for (int s = 0; s < n_steps; ++s) {
-    const long long k = k0 + s;
-    neuron_phase<METHOD, true, TIMED, false>(P, k, st, sh, bar_parity);
-    arrived += gridDim.x;
-    grid_barrier(P.grid_bar, arrived);
-    if (P.n_ranks > 1) {                 /* partitioned network: block 0 exchanges the step's spikes over peer memory */
-      if (blockIdx.x == 0) exchange_phase(P, k);
-      arrived += gridDim.x;
-      grid_barrier(P.grid_bar, arrived);
-    }
-    if (P.max_delay < P.refr_steps) {
-      spike_new_phase<false>(P, k);
-      deliver_phase<DELIVER_FUSED>(P, k);
+#ifndef HHD_SYNAPSE_MINBLOCKS
+#define HHD_SYNAPSE_MINBLOCKS 8    /* 64 registers: the kernel is a chain of dependent loads, it lives on resident warps */
+#endif
+template <bool LONG>
+__global__ void __launch_bounds__(STP_BLOCK, HHD_SYNAPSE_MINBLOCKS) k_synapse(const __grid_constant__ Params P, const int step_offset, const int stp_blocks) {
+  pdl_wait();
+  const long long k = *P.base_step + step_offset;
+  if (P.n_ranks > 1 && P.peer_buf[P.rank]) {
+    if (blockIdx.x == 0) {
+      recv_spikes(P, k);
     } else {
-      spike_new_phase<true>(P, k);
-      deliver_phase<DELIVER_MAIN>(P, k);
+      if (threadIdx.x == 0) {
+        unsigned long long seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.xchg_done) : "memory");
+        } while (seen < (unsigned long long)(k + 1) && !*(volatile unsigned int*)P.xchg_dead);
+      }
+      __syncthreads();
     }
-    arrived += gridDim.x;
-    grid_barrier(P.grid_bar, arrived);
   }
-  neuron_phase<METHOD, false, TIMED, false>(P, k0 + n_steps, st, sh, bar_parity);
+  if (stp_blocks <= 0) {            /* one wave of CTAs, each does its share of both halves: spike-time tasks first */
+    spike_new_phase<LONG>(P, k, blockIdx.x, gridDim.x);
+    deliver_phase<LONG>(P, k, blockIdx.x, gridDim.x);
+  } else if ((int)blockIdx.x < stp_blocks) spike_new_phase<LONG>(P, k, blockIdx.x, (unsigned)stp_blocks);
+  else deliver_phase<LONG>(P, k, blockIdx.x - (unsigned)stp_blocks, gridDim.x - (unsigned)stp_blocks);
+  if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P, k, 6);
+  pdl_trigger();
 }
 
 
@@ -1266,7 +1039,7 @@ struct ResList {                 /* lives in the shared memory of CTA 0 of the c
 template <int METHOD>
 __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant__ Params P, const int n_steps) {
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   /* layout: pend[3][128] (8 B each) | MonDesc[MAX_MON] | ResList | end[W] | neuron[cap] | step[cap] */
   unsigned long long* pend_sh = reinterpret_cast<unsigned long long*>(smem_raw);
   MonDesc* mon_sh = reinterpret_cast<MonDesc*>(pend_sh + 3 * RES_BLOCK);
@@ -1310,7 +1083,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
   bool has_out = false;
   if (live) {
 #pragma unroll
-    for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
+    for (int v = 0; v < 8; ++v) x[v] = P.nb[nb_index(v, i)];
     p = load_par(P, i);
     ls = P.last_spike[P.off + i];
     meta = P.meta[i];
@@ -1494,7 +1267,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
   /* ---------------- write back ---------------------------------------------------------------------------------------- */
   if (live) {
 #pragma unroll
-    for (int v = 0; v < 8; ++v) P.x[v][i] = x[v];
+    for (int v = 0; v < 8; ++v) P.nb[nb_index(v, i)] = x[v];
     P.meta[i] = meta;
     if (METHOD == 3) P.hstep[i] = hcar;
   }
@@ -1557,9 +1330,15 @@ __global__ void k_read_var(const __grid_constant__ Params P, int var, double* ou
   if (i >= P.N) return;
   double x[8];
 #pragma unroll
-  for (int v = 0; v < 8; ++v) x[v] = P.x[v][i];
+  for (int v = 0; v < 8; ++v) x[v] = P.nb[nb_index(v, i)];
   const NeuronPar p = load_par(P, i);
   out[i] = hhd_var_value(P.cc, p, x, var, P.last_spike[P.off + i], P.iac_table ? iac_at(P, P.iac_col[i], *P.base_step) : 0.0);
+}
+
+/* one field (0..7 state, 8.. parameters) of the neuron blocks from / to a plain [N] array */
+__global__ void k_scatter_field(const __grid_constant__ Params P, int field, const double* in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.N) P.nb[nb_index(field, i)] = in[i];
 }
 
 /* ================================================== host side =================================================== */
@@ -1585,8 +1364,7 @@ struct hhd_engine {
   std::string err;
   int N = 0, NG = 0;
   long long step = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Params P;
   bool neurons_set = false, channels_set = false, started = false, graph_dirty = true, ext_dirty = false;
@@ -1599,6 +1377,7 @@ struct hhd_engine {
   long long ext_syn_total = 0;
   void *d_ext_ptr = nullptr, *d_ext_tgt = nullptr, *d_ext_mask = nullptr, *d_ext_gmax = nullptr, *d_ext_pfail = nullptr, *d_ext_id = nullptr;
   MonDesc* d_mon = nullptr;
+  double* d_stage = nullptr;        /* [N] staging buffer of scatter_field */
   long long* d_base_step = nullptr;
   unsigned long long* d_counters = nullptr;
   unsigned long long ring_cap = 0;
@@ -1617,7 +1396,7 @@ struct hhd_engine {
   cudaGraphExec_t graph_exec = nullptr;
   hhd_counters cnt;
   int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
-  bool pipelined = false;
+  bool mon_variant = false;         /* some state monitor is active: the k_neuron variant that samples them is launched */
   bool p2p = false;                 /* spike exchange over mapped peer memory (k_exchange) instead of NCCL */
   void* peer_mapped[MAX_RANKS] = {};/* cudaIpcOpenMemHandle results, closed in hhd_destroy */
 #ifdef HHD_WITH_NCCL
@@ -1626,10 +1405,9 @@ struct hhd_engine {
   bool comm_ready = false;
   bool cross_instance = false; /* some synapse joins two instances: the resident plan is not applicable */
   bool resident = false;       /* HHD_PLAN_RESIDENT chosen */
-  bool gridplan = false;       /* HHD_PLAN_PERSISTENT chosen: one cooperative launch per segment */
   int res_smem = 0;
   bool pdl = false;            /* programmatic dependent launch between the kernels of the main stream */
-  bool fused = false;          /* spike-time STP runs inside k_deliver (max_delay < refractory steps) */
+  bool fused = false;          /* max_delay < refractory steps: no neuron has a new spike and an undelivered older one */
   int kernels_per_step = 3;
 };
 
@@ -1701,41 +1479,43 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   h->NG = h->cfg.n_global;
   if (h->cfg.global_offset < 0 || h->cfg.global_offset + h->N > h->NG) { delete h; return fail(nullptr, HHD_E_ARG, "partition out of range"); }
   h->sm_count = prop.multiProcessorCount;
+  {
+    /* L2 set-aside for lines loaded / stored with the evict_last priority (the state rows, k_neuron): the size of the
+     * state rows, as far as the device allows (measured on 1 003 000 neurons: 0 MB 65.2, 64 MB 63.2, the maximum of
+     * 79 MB 64.0 us per step), or HHD_L2_PERSIST_MB */
+    const size_t n_pad0 = (size_t)((cfg->n_neurons + 31) / 32) * 32;
+    size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, n_pad0 * (size_t)(8 * 8));
+    if (const char* env = getenv("HHD_L2_PERSIST_MB")) want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)atoll(env) << 20);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] L2 %d MB, persisting set-aside %zu MB (max %d MB)\n", prop.l2CacheSize >> 20, want >> 20, prop.persistingL2CacheMaxSize >> 20);
+  }
   memset(&h->cnt, 0, sizeof h->cnt);
   memset(&h->P, 0, sizeof h->P);
   h->record_spikes = cfg->record_spikes != 0;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, HHD_E_CUDA, "cudaStreamCreate failed"); }
-  cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_seg[0], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_seg[1], cudaEventDisableTiming);
   cudaMallocHost(&h->pin_head, 16);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
-  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   Params& P = h->P;
   P.N = h->N; P.NG = h->NG; P.off = h->cfg.global_offset; P.dt = cfg->dt_ms; P.accum = cfg->accum; P.seed = cfg->seed;
   P.refr_steps = (int)hhd_timestep(cfg->refractory_ms, cfg->dt_ms);
   P.cc.window_ms = cfg->block_window_ms;
   int rc = 0;
-  const size_t n_pad = (size_t)((h->N + NEURON_BLOCK - 1) / NEURON_BLOCK) * NEURON_BLOCK;   /* whole tiles for the bulk copies */
-  for (int p = 0; p < HHD_N_PARAMS && !rc; ++p) rc = dev_alloc(h, &P.par[p], n_pad);
-  for (int v = 0; v < 8 && !rc; ++v) rc = dev_alloc(h, &P.x[v], n_pad);
+  const size_t n_pad = (size_t)((h->N + NB_LANES - 1) / NB_LANES) * NB_LANES;   /* whole 32-neuron blocks for the bulk copies */
+  rc = dev_alloc(h, &P.nb, n_pad * NB_FIELDS);
   if (!rc) rc = dev_alloc(h, &P.last_spike, h->NG, false);
   if (!rc && cfg->method == HHD_RK23_ADAPTIVE) rc = dev_alloc(h, &P.hstep, n_pad, false);
-  if (!rc) rc = dev_alloc(h, &P.meta, h->N, false);
+  if (!rc) rc = dev_alloc(h, &P.meta, n_pad, false);
   unsigned char* ho = nullptr;
   if (!rc) rc = dev_alloc(h, &ho, h->NG);
   P.has_out = ho;
   P.n_pad = (long long)n_pad;
   if (!rc) rc = dev_alloc(h, &P.pend, (size_t)6 * n_pad);
   if (!rc) rc = dev_alloc(h, &P.prev_spike, h->NG);
-  if (!rc) rc = dev_alloc(h, &P.stp_mark, 1);
   if (!rc) rc = dev_alloc(h, &P.pass_done, 1);
-  if (!rc) rc = dev_alloc(h, &P.tile_ctr, 1);
-  if (!rc) rc = dev_alloc(h, &P.zcount, 1);
-  if (!rc) rc = dev_alloc(h, &P.zlist, h->N);
   long long* rp = nullptr;
   if (!rc) rc = dev_alloc(h, &rp, (size_t)h->NG + 1);
   P.row_ptr = rp;
@@ -1743,13 +1523,12 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (!rc) rc = dev_alloc(h, &h->d_base_step, 1);
   if (!rc) rc = dev_alloc(h, &h->d_counters, CNT_N);
   if (!rc) rc = dev_alloc(h, &P.del_slots, CNT_SLOTS);
-  if (!rc) rc = dev_alloc(h, &P.grid_bar, 1);
   if (!rc) rc = dev_alloc(h, &h->d_mon, MAX_MON);
   if (rc) { std::string m = h->err; hhd_destroy(h); g_create_err = m; return rc; }
   P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
   {
     std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms);
-    std::vector<int> lk((size_t)h->N, -(1 << 30));   /* lastspike = -2^26 steps, no flags */
+    std::vector<int> lk(n_pad, -(1 << 30));          /* lastspike = -2^26 steps, no flags */
     cudaMemcpyAsync(P.last_spike, ls.data(), ls.size() * 8, cudaMemcpyHostToDevice, h->stream);
     if (P.hstep) {
       std::vector<double> h0(n_pad, cfg->dt_ms);
@@ -1773,18 +1552,25 @@ extern "C" void hhd_destroy(hhd_handle h) {
 #endif
   for (int r = 0; r < MAX_RANKS; ++r) if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
   for (int q = 0; q < 2; ++q) if (h->ev_seg[q]) cudaEventDestroy(h->ev_seg[q]);
   if (h->pin_head) cudaFreeHost(h->pin_head);
   if (h->pin_nb) cudaFreeHost(h->pin_nb);
   if (h->pin_sb) cudaFreeHost(h->pin_sb);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+/* host array [N] -> one field of the neuron blocks (staged through a device buffer kept for the next call) */
+static int scatter_field(hhd_handle h, int field, const double* in) {
+  if (!h->d_stage) { int rc = dev_alloc(h, &h->d_stage, (size_t)h->N, false); if (rc) return rc; }
+  CU(cudaMemcpyAsync(h->d_stage, in, (size_t)h->N * 8, cudaMemcpyHostToDevice, h->stream));
+  k_scatter_field<<<(h->N + 255) / 256, 256, 0, h->stream>>>(h->P, field, h->d_stage);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));   /* caller owns `in` */
+  return 0;
 }
 
 extern "C" int hhd_set_neurons(hhd_handle h, const double* const* params, const double* V0, const double* w0) {
@@ -1795,9 +1581,18 @@ extern "C" int hhd_set_neurons(hhd_handle h, const double* const* params, const 
   for (int i = 0; i < h->N; ++i)
     if (!(params[HHD_P_C][i] > 0) || !(params[HHD_P_GL][i] > 0) || !(params[HHD_P_DELTAT][i] > 0) || !(params[HHD_P_TAUW][i] > 0))
       return fail(h, HHD_E_ARG, "neuron %d: C, g_L, delta_T and tau_w must be positive", i);
-  for (int p = 0; p < HHD_N_PARAMS; ++p) { int rc = upload(h, h->P.par[p], params[p], (size_t)h->N); if (rc) return rc; }
-  int rc = upload(h, h->P.x[0], V0, (size_t)h->N);
-  if (!rc) rc = upload(h, h->P.x[1], w0, (size_t)h->N);
+  /* blocked layout (nb_index); the padding lanes of the last block get parameters with a stable fixed point at V = w = 0
+   * (no exponential current, leak towards 0, a threshold that is never reached) so that they compute harmlessly */
+  const size_t n_pad = (size_t)h->P.n_pad;
+  std::vector<double> blk(n_pad * NB_FIELDS, 0.0);
+  const double pad_par[HHD_N_PARAMS] = {1.0, 1.0, 0.0, 1.0, 1e300, 1.0, 0.0, 0.0, 1000.0, 1e300, 0.0, 0.0};   /* C gL EL dT Vup tauw b Vr VT Iref Vdep IDC */
+  for (size_t i = 0; i < n_pad; ++i) {
+    const bool live = i < (size_t)h->N;
+    for (int p = 0; p < HHD_N_PARAMS; ++p) blk[nb_index(NB_STATE + p, (long long)i)] = live ? params[p][i] : pad_par[p];
+    blk[nb_index(0, (long long)i)] = live ? V0[i] : 0.0;
+    blk[nb_index(1, (long long)i)] = live ? w0[i] : 0.0;
+  }
+  int rc = upload(h, h->P.nb, blk.data(), blk.size());
   if (rc) return rc;
   h->neurons_set = true;
   return HHD_OK;
@@ -1807,7 +1602,7 @@ extern "C" int hhd_set_idc(hhd_handle h, const double* idc) {
   if (!h || !idc) return fail(h, HHD_E_ARG, "null argument");
   if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
   cudaSetDevice(h->cfg.device);
-  return upload(h, h->P.par[HHD_P_IDC], idc, (size_t)h->N);
+  return scatter_field(h, NB_STATE + HHD_P_IDC, idc);
 }
 
 extern "C" int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const double* table, const int32_t* col_of_neuron) {
@@ -2047,7 +1842,7 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
   P.row_doff = nullptr;
   {
     /* an STP task is one block of a spiking neuron's row: as many tasks per spike as 1.25 mean rows need.  Needed by
-     * k_spike_new whichever delivery index is built below. */
+     * the spike-time half of k_synapse whichever delivery index is built below. */
     const double mean_row = (double)nsyn / std::max(1, h->NG);
     P.stp_chunks = std::max(1, (int)std::ceil(1.25 * mean_row / NEURON_BLOCK));
   }
@@ -2300,19 +2095,20 @@ extern "C" int hhd_clear_monitor(hhd_handle h, int32_t mon_id) {
 }
 
 /* ---- run --------------------------------------------------------------------------------------------------------- */
-/* The TimedArray and pipelined variants are separate instantiations: no cost when unused. */
+/* The TimedArray and monitor-sampling variants are separate instantiations: no cost when unused.  The pass that only
+ * finishes the last step (STEP = false) samples nothing. */
 template <int M, bool STEP>
-static const void* neuron_fn(bool timed, bool pipe) {
-  if (timed) return pipe ? (const void*)k_neuron<M, STEP, true, STEP> : (const void*)k_neuron<M, STEP, true, false>;
-  return pipe ? (const void*)k_neuron<M, STEP, false, STEP> : (const void*)k_neuron<M, STEP, false, false>;
+static const void* neuron_fn(bool timed, bool mon) {
+  if (timed) return (mon && STEP) ? (const void*)k_neuron<M, STEP, true, STEP> : (const void*)k_neuron<M, STEP, true, false>;
+  return (mon && STEP) ? (const void*)k_neuron<M, STEP, false, STEP> : (const void*)k_neuron<M, STEP, false, false>;
 }
 template <bool STEP>
-static const void* neuron_fn_of(int method, bool timed, bool pipe) {
+static const void* neuron_fn_of(int method, bool timed, bool mon) {
   switch (method) {
-    case HHD_EULER: return neuron_fn<0, STEP>(timed, pipe);
-    case HHD_RK2: return neuron_fn<1, STEP>(timed, pipe);
-    case HHD_RK4: return neuron_fn<2, STEP>(timed, pipe);
-    default: return neuron_fn<3, STEP>(timed, pipe);
+    case HHD_EULER: return neuron_fn<0, STEP>(timed, mon);
+    case HHD_RK2: return neuron_fn<1, STEP>(timed, mon);
+    case HHD_RK4: return neuron_fn<2, STEP>(timed, mon);
+    default: return neuron_fn<3, STEP>(timed, mon);
   }
 }
 
@@ -2320,7 +2116,7 @@ static unsigned long long next_pow2(unsigned long long v) { unsigned long long p
 
 #ifdef HHD_WITH_NCCL
 /* Map every rank's receive buffer into this process (CUDA IPC; the handles travel through the NCCL communicator) so that
- * k_exchange can write spike lists and flags straight into peer memory.  Collective: every rank calls it from its first
+ * push_spikes can write spike lists and flags straight into peer memory.  Collective: every rank calls it from its first
  * hhd_run.  Any failure on any rank (no peer access, IPC not permitted in this container, HHD_NO_P2P set) leaves all ranks
  * on the NCCL all-gather. */
 static int setup_p2p(hhd_handle h) {
@@ -2364,7 +2160,7 @@ static int setup_p2p(hhd_handle h) {
   CU(cudaStreamSynchronize(h->stream));
   dev_free(h, d_mine); dev_free(h, d_all); dev_free(h, d_ok);
   h->p2p = all_ok != 0;
-  if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] rank %d: spike exchange over %s\n", P.rank, h->p2p ? "peer memory (k_exchange)" : "NCCL all-gather");
+  if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] rank %d: spike exchange over %s\n", P.rank, h->p2p ? "peer memory (push_spikes / recv_spikes)" : "NCCL all-gather");
   if (!h->p2p) {
     for (int r = 0; r < R; ++r) {
       if (h->peer_mapped[r]) { cudaIpcCloseMemHandle(h->peer_mapped[r]); h->peer_mapped[r] = nullptr; }
@@ -2420,6 +2216,7 @@ static int finalize_setup(hhd_handle h) {
     rc = dev_alloc(h, &P.xchg_send, (size_t)1 + P.xchg_cap, true);
     if (!rc) rc = dev_alloc(h, &P.xchg_recv, (size_t)P.n_ranks * (1 + P.xchg_cap), true);
     if (!rc) rc = dev_alloc(h, &P.xchg_dead, 1, true);
+    if (!rc) rc = dev_alloc(h, &P.xchg_done, 1, true);
     if (rc) return rc;
     P.rank = h->cfg.rank;
 #ifdef HHD_WITH_NCCL
@@ -2427,28 +2224,33 @@ static int finalize_setup(hhd_handle h) {
 #endif
   }
   {
-    /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than tiles */
+    /* persistent state-update grid: as many CTAs as fit at once (shared-memory and register limited), never more than
+     * there are warp tiles */
     int occ = 1 << 30;
     for (int v = 0; v < 8; ++v) {           /* every variant of this method may be launched: opt in to the shared memory */
-      const bool timed = v & 1, pipe = v & 2, step = v & 4;
-      const void* fn = step ? neuron_fn_of<true>(h->cfg.method, timed, pipe) : neuron_fn_of<false>(h->cfg.method, timed, pipe);
+      const bool timed = v & 1, mon = v & 2, step = v & 4;
+      const void* fn = step ? neuron_fn_of<true>(h->cfg.method, timed, mon) : neuron_fn_of<false>(h->cfg.method, timed, mon);
       CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
       int q = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, NEURON_BLOCK, NEURON_SMEM));
       if (timed == (P.iac_table != nullptr || P.noise_sigma != nullptr)) occ = std::min(occ, q);
     }
-    const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
+    const int ctas = (int)((P.n_pad / NB_LANES + NEURON_WARPS - 1) / NEURON_WARPS);
     const char* env = getenv("HHD_NEURON_CTAS_PER_SM");
     int cps = std::max(1, occ);
     if (env && atoi(env) > 0) cps = std::min(cps, atoi(env));
-    h->neuron_grid = std::max(1, std::min(tiles, h->sm_count * cps));
-    if (!HHD_NEURON_PREFETCH && !getenv("HHD_NEURON_PERSISTENT")) h->neuron_grid = tiles;
+    h->neuron_grid = std::max(1, std::min(ctas, h->sm_count * cps));
+    rc = dev_alloc(h, &P.mon_part, (size_t)MAX_RED * h->neuron_grid, true);
+    if (rc) return rc;
+    if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] k_neuron: %d CTAs per SM, grid %d, %d bytes of dynamic shared memory per CTA\n", cps, h->neuron_grid, NEURON_SMEM);
   }
+  /* k_synapse: spike-time CTAs + delivery CTAs in one launch; on a partitioned network every CTA must be resident while
+   * CTA 0 receives the peers' spikes (the others spin), which the occupancy of the kernel bounds */
   h->stp_grid = h->sm_count * 4;
-  h->deliver_grid = h->sm_count * 16;          /* 16 CTAs x 128 threads = one full wave; >= 1 warp per active spike at 1M neurons */
+  h->deliver_grid = h->sm_count * 8;
   if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
   if (getenv("HHD_DELIVER_CTAS_PER_SM") && atoi(getenv("HHD_DELIVER_CTAS_PER_SM")) > 0) h->deliver_grid = h->sm_count * atoi(getenv("HHD_DELIVER_CTAS_PER_SM"));
-  if (getenv("HHD_STP_CTAS_PER_SM") && atoi(getenv("HHD_STP_CTAS_PER_SM")) > 0) h->stp_grid = h->sm_count * atoi(getenv("HHD_STP_CTAS_PER_SM"));
+  if (getenv("HHD_STP_CTAS_PER_SM") && atoi(getenv("HHD_STP_CTAS_PER_SM")) >= 0) h->stp_grid = h->sm_count * atoi(getenv("HHD_STP_CTAS_PER_SM"));
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
     unsigned short* rmax = nullptr;
@@ -2466,15 +2268,18 @@ static int finalize_setup(hhd_handle h) {
     P.stp_chunks = 1;
   }
   if (P.stp_chunks < 1) return fail(h, HHD_E_STATE, "internal: stp_chunks not set");
-  h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");
-  h->kernels_per_step = 3;
-  /* pipelined schedule: graph plan, single rank, no neuron with a new spike and an undelivered older one */
+  h->fused = P.max_delay < P.refr_steps && !getenv("HHD_NO_FUSE");      /* no delay outlasts the refractory period (k_synapse<false>) */
+  h->kernels_per_step = 2;
+  if (h->cfg.plan == HHD_PLAN_PERSISTENT || h->cfg.plan == HHD_PLAN_PIPELINED)
+    return fail(h, HHD_E_ARG, "plan %d was removed in round 2 (measured slower than the graph plan, profiles/r1_notes.md): use auto, graph or resident", h->cfg.plan);
   {
-    const bool can = h->fused && h->cfg.n_ranks == 1 && P.row_doff && HHD_NEURON_PREFETCH == 2;
-    if (h->cfg.plan == HHD_PLAN_PIPELINED && !can)
-      return fail(h, HHD_E_ARG, "HHD_PLAN_PIPELINED needs max delay < refractory period and a single rank");
-    /* opt-in: measured 61.1 vs 59.6 us per step against the serial schedule on 1M neurons (profiles/r1_notes.md) */
-    h->pipelined = can && (h->cfg.plan == HHD_PLAN_PIPELINED || (h->cfg.plan == HHD_PLAN_AUTO && getenv("HHD_PIPELINE") && atoi(getenv("HHD_PIPELINE"))));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->fused ? (const void*)k_synapse<false> : (const void*)k_synapse<true>, STP_BLOCK, 0));
+    const int cap = std::max(1, per_sm) * h->sm_count;
+    if (h->cfg.n_ranks > 1 && h->stp_grid + h->deliver_grid > cap) {
+      h->stp_grid = std::max(1, std::min(h->stp_grid, cap / 3));
+      h->deliver_grid = std::max(1, cap - h->stp_grid);
+    }
   }
   h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
   {
@@ -2490,24 +2295,6 @@ static int finalize_setup(hhd_handle h) {
     while (cs0 * RES_BLOCK < inst) cs0 <<= 1;
     const bool one_wave = (long long)(h->N / inst) * cs0 <= (long long)h->sm_count;
     h->resident = can && (h->cfg.plan == HHD_PLAN_RESIDENT || (h->cfg.plan == HHD_PLAN_AUTO && one_wave && !getenv("HHD_NO_RESIDENT")));
-    {
-      /* whole-run cooperative plan: needs every CTA of the state-update grid resident at once (it is sized that way)
-       * and smem opt-in for k_grid */
-      const void* gfn[8] = {(const void*)k_grid<0>, (const void*)k_grid<1>, (const void*)k_grid<2>, (const void*)k_grid<3>,
-                            (const void*)k_grid<0, true>, (const void*)k_grid<1, true>, (const void*)k_grid<2, true>, (const void*)k_grid<3, true>};
-      const int gm = h->cfg.method + ((P.iac_table || P.noise_sigma) ? 4 : 0);
-      int per_sm = 0;
-      CU(cudaFuncSetAttribute(gfn[gm], cudaFuncAttributeMaxDynamicSharedMemorySize, NEURON_SMEM));
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfn[gm], NEURON_BLOCK, NEURON_SMEM));
-      const bool gcan = HHD_NEURON_PREFETCH >= 2 && per_sm > 0 && (h->cfg.n_ranks == 1 ? h->NG == h->N : h->p2p);
-      if (h->cfg.plan == HHD_PLAN_PERSISTENT && !gcan)
-        return fail(h, HHD_E_ARG, "HHD_PLAN_PERSISTENT: a partitioned network needs the peer-memory spike exchange");
-      const int tiles = (h->N + NEURON_BLOCK - 1) / NEURON_BLOCK;
-      const int ggrid = std::max(1, std::min(tiles, h->sm_count * per_sm));
-      h->gridplan = !h->resident && gcan &&
-                    (h->cfg.plan == HHD_PLAN_PERSISTENT || (h->cfg.plan == HHD_PLAN_AUTO && getenv("HHD_GRIDPLAN") && atoi(getenv("HHD_GRIDPLAN"))));
-      if (h->gridplan) h->neuron_grid = std::min(h->neuron_grid, ggrid);
-    }
     if (h->resident) {
       P.inst_size = inst;
       P.n_inst = h->N / inst;
@@ -2525,44 +2312,10 @@ static int finalize_setup(hhd_handle h) {
       }
     }
   }
-  if (getenv("HHD_DEBUG_TIMES")) { rc = dev_alloc(h, &P.dbg_times, (size_t)16 * 4096, true); if (rc) return rc; }
-  if (h->resident || h->gridplan) h->pipelined = false;
+  if (getenv("HHD_DEBUG_TIMES")) { rc = dev_alloc(h, &P.dbg_times, (size_t)8 * 4096, true); if (rc) return rc; }
   k_mark_flags<<<(h->NG + 255) / 256, 256, 0, h->stream>>>(h->NG, h->N, P.off, P.row_ptr, P.hot, const_cast<unsigned char*>(P.has_out), P.meta);
   CU(cudaGetLastError());
-  if (h->pipelined) {
-    h->kernels_per_step = 1;
-    const char* env = getenv("HHD_AHEAD_CTAS");
-    /* dyn_tiles: static iterations given up for the drawn tail (0 = all static) */
-    P.dyn_tiles = getenv("HHD_DYN_TILES") ? atoi(getenv("HHD_DYN_TILES")) : 2;
-    P.ahead_ctas = std::max(1, std::min(h->neuron_grid, env && atoi(env) > 0 ? atoi(env) : h->neuron_grid));
-  }
   h->started = true;
-  return 0;
-}
-
-static int launch_grid(hhd_handle h, int n_steps) {
-  cudaLaunchConfig_t lc;
-  memset(&lc, 0, sizeof lc);
-  lc.gridDim = dim3((unsigned)h->neuron_grid);
-  lc.blockDim = dim3(NEURON_BLOCK);
-  lc.dynamicSmemBytes = (size_t)NEURON_SMEM;
-  lc.stream = h->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;
-  at[0].val.cooperative = 1;
-  lc.attrs = at;
-  lc.numAttrs = 1;
-  const bool timed = h->P.iac_table != nullptr || h->P.noise_sigma != nullptr;
-  cudaError_t e;
-  switch (h->cfg.method) {
-    case HHD_EULER: e = timed ? cudaLaunchKernelEx(&lc, k_grid<0, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<0, false>, h->P, n_steps); break;
-    case HHD_RK2: e = timed ? cudaLaunchKernelEx(&lc, k_grid<1, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<1, false>, h->P, n_steps); break;
-    case HHD_RK4: e = timed ? cudaLaunchKernelEx(&lc, k_grid<2, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<2, false>, h->P, n_steps); break;
-    default: e = timed ? cudaLaunchKernelEx(&lc, k_grid<3, true>, h->P, n_steps) : cudaLaunchKernelEx(&lc, k_grid<3, false>, h->P, n_steps); break;
-  }
-  if (e != cudaSuccess) return fail(h, HHD_E_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
-  k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, n_steps);
-  h->cnt.kernel_launches += 2;
   return 0;
 }
 
@@ -2612,50 +2365,37 @@ static void launch_pdl(hhd_handle h, K kernel, int grid, int block, size_t smem,
 template <bool STEP>
 static void launch_neuron(hhd_handle h, int offset) {
   typedef void (*kern_t)(const Params, const int);
-  const kern_t fn = (kern_t)neuron_fn_of<STEP>(h->cfg.method, h->P.iac_table != nullptr || h->P.noise_sigma != nullptr, STEP && h->pipelined);
+  const kern_t fn = (kern_t)neuron_fn_of<STEP>(h->cfg.method, h->P.iac_table != nullptr || h->P.noise_sigma != nullptr, h->mon_variant);
   launch_pdl(h, fn, h->neuron_grid, NEURON_BLOCK, NEURON_SMEM, h->stream, offset);
 }
 
+static void launch_synapse(hhd_handle h, int offset) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof lc);
+  lc.gridDim = dim3((unsigned)(h->stp_grid + h->deliver_grid));      /* stp_grid = 0: every CTA does both halves */
+  lc.blockDim = dim3(STP_BLOCK);
+  lc.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = h->pdl ? 1 : 0;
+  if (h->fused) cudaLaunchKernelEx(&lc, k_synapse<false>, h->P, offset, h->stp_grid);
+  else cudaLaunchKernelEx(&lc, k_synapse<true>, h->P, offset, h->stp_grid);
+}
+
+/* One time step: k_neuron, k_synapse.  On a partitioned network the step's spike indices travel every rank to every rank
+ * in between — inside those two launches over peer memory (push_spikes / recv_spikes), or as ncclAllGather + k_append when
+ * the peers' buffers could not be mapped. */
+static void launch_step(hhd_handle h, int offset) {
+  launch_neuron<true>(h, offset);
 #ifdef HHD_WITH_NCCL
-/* This step's spike indices, every rank to every rank: one launch over peer memory, or NCCL when the buffers could not be mapped */
-static void launch_exchange(hhd_handle h, int offset) {
-  if (h->p2p) {
-    k_exchange<<<1, 256, 0, h->stream>>>(h->P, offset);
-  } else {
+  if (h->cfg.n_ranks > 1 && !h->p2p) {
     ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
     k_append<<<1, 256, 0, h->stream>>>(h->P, offset);
   }
-}
 #endif
-
-static void launch_step(hhd_handle h, int offset) {
-  if (h->pipelined) {            /* one launch per step: state update + the synaptic work that is one step ahead */
-    launch_neuron<true>(h, offset);
-    return;
-  }
-  launch_neuron<true>(h, offset);
-#ifdef HHD_WITH_NCCL
-  if (h->cfg.n_ranks > 1) {   /* the one real exchange of the path: this step's spike indices, every rank to every rank */
-    launch_exchange(h, offset);
-  }
-#endif
-  if (h->fused) {
-    cudaEventRecord(h->ev_fork, h->stream);
-    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    k_spike_new<false><<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
-    cudaEventRecord(h->ev_join, h->stream2);
-    launch_pdl(h, k_deliver<DELIVER_FUSED>, h->deliver_grid, DELIVER_BLOCK, 0, h->stream, offset);
-    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-  } else {
-    /* delays beyond the refractory period: same two concurrent kernels; k_spike_new<true> also delivers what is due from
-     * older spikes of the neurons that spiked now, k_deliver<DELIVER_MAIN> skips those neurons */
-    cudaEventRecord(h->ev_fork, h->stream);
-    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    k_spike_new<true><<<h->stp_grid, STP_BLOCK, 0, h->stream2>>>(h->P, offset);
-    cudaEventRecord(h->ev_join, h->stream2);
-    launch_pdl(h, k_deliver<DELIVER_MAIN>, h->deliver_grid, DELIVER_BLOCK, 0, h->stream, offset);
-    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-  }
+  launch_synapse(h, offset);
 }
 
 static int build_graph(hhd_handle h) {
@@ -2786,6 +2526,9 @@ static int push_monitor_descs(hhd_handle h) {
   CU(cudaMemcpyAsync(h->d_mon, d, sizeof d, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->P.n_mon = (int)h->mons.size();
+  bool any = false;
+  for (const Monitor& m : h->mons) any = any || m.active;
+  if (any != h->mon_variant) { h->mon_variant = any; h->graph_dirty = true; }
   return 0;
 }
 
@@ -2803,7 +2546,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   if (prev_n_mon != h->P.n_mon) h->graph_dirty = true;
   for (Monitor& m : h->mons) if (m.active && m.first_step < 0) m.first_step = h->step;
   CU(cudaMemcpyAsync(h->d_base_step, &h->step, 8, cudaMemcpyHostToDevice, h->stream));
-  if (!h->resident && !h->gridplan && h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
+  if (!h->resident && h->graph_dirty && n_steps >= STEPS_PER_GRAPH && (rc = build_graph(h))) return rc;
 
   CU(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
@@ -2817,8 +2560,8 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   };
   while (done < n_steps) {
     const long long seg = std::min<long long>(h->seg_steps, n_steps - done);
-    if (h->resident || h->gridplan) {
-      if ((rc = h->resident ? launch_resident(h, (int)seg) : launch_grid(h, (int)seg))) return rc;
+    if (h->resident) {
+      if ((rc = launch_resident(h, (int)seg))) return rc;
       done += seg;
       CU(cudaGetLastError());
       if ((rc = segment_done())) return rc;
@@ -2827,7 +2570,7 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
     long long s = 0;
     while (seg - s >= STEPS_PER_GRAPH && h->graph_exec && !h->graph_dirty) {
       CU(cudaGraphLaunch(h->graph_exec, h->stream));
-      h->cnt.kernel_launches += (h->kernels_per_step + (h->cfg.n_ranks > 1 ? 1 : 0)) * STEPS_PER_GRAPH + 1;
+      h->cnt.kernel_launches += (h->kernels_per_step + (h->cfg.n_ranks > 1 && !h->p2p ? 2 : 0)) * STEPS_PER_GRAPH + 1;
       s += STEPS_PER_GRAPH;
     }
     const int rem = (int)(seg - s);
@@ -2835,11 +2578,6 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
     if (rem) { k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, rem); h->cnt.kernel_launches += h->kernels_per_step * rem + 1; }
     done += seg;
     if (done == n_steps) {
-      if (h->pipelined) {          /* p0..p6 of the last step's spikes */
-        k_stp_flush<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P);
-        k_set_mark<<<1, 1, 0, h->stream>>>(h->P);
-        h->cnt.kernel_launches += 2;
-      }
       launch_neuron<false>(h, 0);
       h->cnt.kernel_launches += 1;
     }
@@ -2920,28 +2658,17 @@ extern "C" int hhd_profile_kernels(hhd_handle h, int64_t n_steps, double us[3]) 
   for (int64_t s = 0; s < n_steps; ++s) {
     launch_neuron<true>(h, (int)s);
     CU(cudaEventRecord(ev[3 * s + 1], h->stream));
-    if (h->pipelined) {            /* the step is that one launch */
-      CU(cudaEventRecord(ev[3 * s + 2], h->stream));
-      CU(cudaEventRecord(ev[3 * s + 3], h->stream));
-      continue;
-    }
 #ifdef HHD_WITH_NCCL
-    if (h->cfg.n_ranks > 1) {   /* the exchange is accounted to slot 1 */
-      launch_exchange(h, (int)s);
+    if (h->cfg.n_ranks > 1 && !h->p2p) {   /* slot 1: the NCCL fallback of the exchange (over peer memory it is inside the two kernels) */
+      ncclAllGather(h->P.xchg_send, h->P.xchg_recv, (size_t)1 + h->P.xchg_cap, ncclInt32, h->comm, h->stream);
+      k_append<<<1, 256, 0, h->stream>>>(h->P, (int)s);
     }
 #endif
-    if (!h->fused) k_spike_new<true><<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
-    else k_spike_new<false><<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P, (int)s);
     CU(cudaEventRecord(ev[3 * s + 2], h->stream));
-    if (h->fused) k_deliver<DELIVER_FUSED><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
-    else k_deliver<DELIVER_MAIN><<<h->deliver_grid, DELIVER_BLOCK, 0, h->stream>>>(h->P, (int)s);
+    launch_synapse(h, (int)s);
     CU(cudaEventRecord(ev[3 * s + 3], h->stream));
   }
   k_advance<<<1, 1, 0, h->stream>>>(h->d_base_step, (int)n_steps);
-  if (h->pipelined) {
-    k_stp_flush<<<h->stp_grid, STP_BLOCK, 0, h->stream>>>(h->P);
-    k_set_mark<<<1, 1, 0, h->stream>>>(h->P);
-  }
   launch_neuron<false>(h, 0);
   h->cnt.kernel_launches += h->kernels_per_step * n_steps + 2;
   CU(cudaGetLastError());
@@ -2996,7 +2723,7 @@ extern "C" int hhd_read_state(hhd_handle h, int32_t var, double* out) {
 extern "C" int hhd_write_state(hhd_handle h, int32_t var, const double* in) {
   if (!h || !in) return fail(h, HHD_E_ARG, "null argument");
   cudaSetDevice(h->cfg.device);
-  if (var >= 0 && var < 8) return upload(h, h->P.x[var], in, (size_t)h->N);
+  if (var >= 0 && var < 8) return scatter_field(h, var, in);
   if (var == HHD_LAST_SPIKE) return upload(h, h->P.last_spike + h->cfg.global_offset, in, (size_t)h->N);
   return fail(h, HHD_E_ARG, "variable %d is not writable", var);
 }

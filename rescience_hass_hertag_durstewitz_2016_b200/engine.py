@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HHD_LIB") or os.path.join(_HERE, "csrc", "libhhd.so")
 ABI_VERSION = 1
 METHODS = {"euler": 0, "rk2": 1, "rk4": 2, "rk23": 3, "gsl_rk2": 3}
 ACCUM = {"fp64": 0, "fixed": 1}
-PLANS = {"auto": 0, "graph": 1, "resident": 2, "persistent": 3, "pipelined": 4}
+PLANS = {"auto": 0, "graph": 1, "resident": 2}
 REDUCE = {"none": 0, "sum": 1, "mean": 2}
 PARAM_ROWS = ["C", "g_L", "E_L", "delta_T", "V_up", "tau_w", "b", "V_r", "V_T", "I_ref", "V_dep", "I_DC"]
 VARS = ["V", "w", "g_AMPA_on", "g_AMPA_off", "g_GABA_on", "g_GABA_off", "g_NMDA_on", "g_NMDA_off",
@@ -271,10 +271,11 @@ class Engine:
         self._check(self._fn("run")(self._h, C.c_int64(int(n_steps))))
 
     def profile_kernels(self, n_steps):
-        """Run n_steps with a CUDA event between kernels -> mean microseconds per launch (neuron, stp, deliver)."""
+        """Run n_steps with a CUDA event between kernels -> mean microseconds per launch: k_neuron, the exchange (only when
+        it is the NCCL all-gather fallback; over peer memory it happens inside the two kernels), k_synapse."""
         us = (C.c_double * 3)()
         self._check(self._fn("profile_kernels")(self._h, C.c_int64(int(n_steps)), us))
-        return {"k_neuron": us[0], "k_stp": us[1], "k_deliver": us[2]}
+        return {"k_neuron": us[0], "exchange": us[1], "k_synapse": us[2]}
 
     def spike_count(self):
         n = C.c_int64(0)

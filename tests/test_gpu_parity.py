@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 STATE = ["V", "w", "g_AMPA_on", "g_AMPA_off", "g_GABA_on", "g_GABA_off", "g_NMDA_on", "g_NMDA_off"]
 
 
-PLANS = ["graph", "resident", "persistent", "pipelined"]   # CUDA graphs of grid-wide kernels / one cluster per instance / one cooperative launch / one launch per step
+PLANS = ["graph", "resident"]   # CUDA graphs of the two grid-wide kernels / one thread-block cluster per instance
 
 
 def gpu_cpu(g, plan, **kw):
@@ -62,7 +62,7 @@ def test_network_fixed_accumulation_bit_exact(method, plan):
         assert gc[k] == cc[k], k
 
 
-@pytest.mark.parametrize("plan", ["auto", "persistent"])
+@pytest.mark.parametrize("plan", ["auto", "graph"])
 def test_multicolumn_long_delays_fixed_bit_exact(plan):
     """5 columns: inter-column delays exceed the refractory period, so a second spike can change the amplitude of a
     delivery still in flight — both engines must agree on that too."""
