@@ -91,7 +91,9 @@ def test_group_helpers():
     gab = c.group_name_to_GABAsynapses_idc([["all", "all", "PC", 0]])
     assert len(a) == len(n) > 0 and len(gab) == 0
     k = int(syn[0])
-    assert c.get_connections_count(int(c.target_arr[k])) == np.sum(c.target_arr == c.target_arr[k])
+    q = int(c.target_arr[k])        # incoming + outgoing, as the reference counts them (codes/CortexNetwork.py:838-842)
+    assert c.get_connections_count(q) == np.sum(c.target_arr == q) + np.sum(c.source_arr == q)
+    assert np.array_equal(c.get_source_from_target(np.array([q, q + 1])), c.source_arr[np.isin(c.target_arr, [q, q + 1])])
 
 
 def test_scales2_rescales_gmax():
