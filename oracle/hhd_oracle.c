@@ -115,7 +115,7 @@ struct hhd_engine {
   /* neurons */
   double* par[HHD_N_PARAMS];
   double* x[8];
-  double* last_spike;       /* [NG], ms, the model's custom variable (written by pathway p5) */
+  double* last_spike;       /* [NG], SECONDS (k * dt_s, as Brian holds it): the model's custom variable, written by pathway p5 */
   double* noise_sigma;      /* [N] nS/sqrt(ms), NULL = no conductance noise */
   double* hstep;            /* [N] adaptive integrator: step size carried from one dt to the next (use_last_timestep) */
   int64_t* lastspike_step;  /* [N], Brian's internal `lastspike` as a step index */
@@ -186,7 +186,7 @@ int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   h->has_out = (uint8_t*)calloc((size_t)h->NG, 1);
   h->cur_spikes = (int32_t*)malloc((size_t)h->N * sizeof(int32_t));
   h->cur_wcross = (int32_t*)malloc((size_t)h->N * sizeof(int32_t));
-  for (int i = 0; i < h->NG; ++i) h->last_spike[i] = cfg->last_spike0_ms;   /* codes/CortexNetwork.py:320 */
+  for (int i = 0; i < h->NG; ++i) h->last_spike[i] = cfg->last_spike0_ms * 1e-3;   /* codes/CortexNetwork.py:320 */
   for (int i = 0; i < h->N; ++i) h->lastspike_step[i] = INT64_MIN / 4;       /* Brian: lastspike = -inf */
   h->spikes_active = cfg->record_spikes;
   h->row_ptr = (int64_t*)calloc((size_t)h->NG + 1, sizeof(int64_t));
@@ -311,7 +311,7 @@ int hhd_set_synapses(hhd_handle h, int64_t nsyn, const int32_t* src, const int32
   h->failure = (uint8_t*)calloc(n, 1); h->touched = (uint8_t*)calloc(n, 1); h->row_syn = (int64_t*)malloc(n * 8);
   for (int64_t k = 0; k < nsyn; ++k) {
     h->src[k] = src[k]; h->tgt[k] = tgt[k]; h->chan[k] = chan[k]; h->gmax[k] = g_max[k]; h->U[k] = U[k];
-    h->tau_rec[k] = tau_rec[k]; h->tau_fac[k] = tau_fac[k]; h->pfail[k] = p_fail[k];
+    h->tau_rec[k] = tau_rec[k] * 1e-3; h->tau_fac[k] = tau_fac[k] * 1e-3; h->pfail[k] = p_fail[k];   /* tau in seconds, see hhd_time_s */
     h->delay_steps[k] = hhd_delay_steps(delay_ms[k], h->cfg.dt_ms);
     h->u[k] = U[k]; h->R[k] = 1.0; h->a_syn[k] = U[k];     /* codes/CortexNetwork.py:421-426 */
     h->row_ptr[src[k] + 1]++;
@@ -421,12 +421,14 @@ static void subexpressions(const hhd_handle h, const npar* p, const double x[8],
   s->dD0 = p->C * (s->ex - 1.0);                                                /* :249 */
 }
 
-/* Right-hand sides, codes/CortexNetwork.py:251-263.  t = stage time, ls = this neuron's last_spike. */
-static void deriv(const hhd_handle h, const npar* p, const double x[8], double t, double ls, double iac, double d[8]) {
+/* Right-hand sides, codes/CortexNetwork.py:251-263.  ts = stage time and ls = this neuron's last_spike, both in SECONDS:
+ * `int(t - last_spike < 5*ms)` is evaluated on Brian's SI values (t = k * dt with dt = 0.05 * 0.001) — on millisecond values the
+ * comparison falls on the other side for one spike step in ten (k*0.05 - k0*0.05 vs 5.0 at k - k0 = 100). */
+static void deriv(const hhd_handle h, const npar* p, const double x[8], double ts, double ls, double iac, double d[8]) {
   subexpr s;
   subexpressions(h, p, x, iac, &s);
   const double V = x[HHD_V], w = x[HHD_W];
-  const double a = ((s.I_tot >= p->Iref) ? 1.0 : 0.0) * ((t - ls < h->cfg.block_window_ms) ? 1.0 : 0.0);
+  const double a = ((s.I_tot >= p->Iref) ? 1.0 : 0.0) * ((ts - ls < h->cfg.block_window_ms * 1e-3) ? 1.0 : 0.0);
   const double dV = (a * (-p->gL / p->C)) * (V - p->Vdep) + ((1.0 - a) * (s.w_V - w)) / p->C;      /* :251 */
   const double gate = ((w > s.w_V - s.D0 / p->tauw) ? 1.0 : 0.0) * ((w < s.w_V + s.D0 / p->tauw) ? 1.0 : 0.0) *
                       ((V <= p->VT) ? 1.0 : 0.0) * ((s.I_tot < p->Iref) ? 1.0 : 0.0);
@@ -439,27 +441,27 @@ static void deriv(const hhd_handle h, const npar* p, const double x[8], double t
 }
 
 /* Brian 2 ExplicitStateUpdater definitions: euler, rk2 (midpoint), rk4. */
-static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], double t, double ls, double iac0, double iac1) {
-  const double dt = h->cfg.dt_ms;
+static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], double ts, double ls, double iac0, double iac1) {
+  const double dt = h->cfg.dt_ms, dts = hhd_dt_s(h->cfg.dt_ms);
   double k1[8], k2[8], k3[8], k4[8], y[8];
-  deriv(h, p, x, t, ls, iac0, k1);
+  deriv(h, p, x, ts, ls, iac0, k1);
   for (int v = 0; v < 8; ++v) k1[v] = dt * k1[v];
   if (h->cfg.method == HHD_EULER) {
     for (int v = 0; v < 8; ++v) x[v] = x[v] + k1[v];
     return;
   }
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k1[v] * 0.5;
-  deriv(h, p, y, t + dt * 0.5, ls, iac0, k2);
+  deriv(h, p, y, ts + dts * 0.5, ls, iac0, k2);
   for (int v = 0; v < 8; ++v) k2[v] = dt * k2[v];
   if (h->cfg.method == HHD_RK2) {
     for (int v = 0; v < 8; ++v) x[v] = x[v] + k2[v];
     return;
   }
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k2[v] * 0.5;
-  deriv(h, p, y, t + dt * 0.5, ls, iac0, k3);
+  deriv(h, p, y, ts + dts * 0.5, ls, iac0, k3);
   for (int v = 0; v < 8; ++v) k3[v] = dt * k3[v];
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k3[v];
-  deriv(h, p, y, t + dt, ls, iac1, k4);      /* TimedArray read at t + dt: the next row */
+  deriv(h, p, y, ts + dts, ls, iac1, k4);      /* TimedArray read at t + dt: the next row */
   for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
   for (int v = 0; v < 8; ++v) x[v] = x[v] + (((k1[v] + 2.0 * k2[v]) + 2.0 * k3[v]) + k4[v]) / 6.0;
 }
@@ -475,6 +477,7 @@ static void integrate_fixed(const hhd_handle h, const npar* p, double x[8], doub
  * reproduces it bit for bit (the growth exponent is -1/4 instead of GSL's -1/3 for that reason).
  */
 #define RK23_MAX_SUBSTEPS 4096
+#define OMP_MIN_NEURONS 8192   /* below this a parallel region costs more than the loop it splits */
 /*
  * `gsl_rk2`: what Brian 2's GSL state updater runs per neuron and dt —
  *   stepper   gsl_odeiv2_step_rk2: k1 = f(y), k2 = f(y + h/2 k1), k3 = f(y + h(-k1 + 2 k2)), y+ = y + h (k1 + 4 k2 + k3)/6,
@@ -496,11 +499,11 @@ static void integrate_rk23(const hhd_handle h, const npar* p, double x[8], doubl
     int final_step = 0;
     if (hs > dt - t) { hs = dt - t; final_step = 1; }     /* evolve.c: if (h0 > t1 - t) { h0 = t1 - t; final_step = 1; } */
     double k1[8], k2[8], k3[8], y[8], ynew[8];
-    deriv(h, p, x, t0 + t, ls, iac0, k1);
+    deriv(h, p, x, t0 + t * 1e-3, ls, iac0, k1);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
-    deriv(h, p, y, t0 + (t + 0.5 * hs), ls, iac0, k2);
+    deriv(h, p, y, t0 + (t + 0.5 * hs) * 1e-3, ls, iac0, k2);
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    deriv(h, p, y, t0 + (t + hs), ls, final_step ? iac1 : iac0, k3);
+    deriv(h, p, y, t0 + (t + hs) * 1e-3, ls, final_step ? iac1 : iac0, k3);
     double rmax = 0.0;
     for (int v = 0; v < 8; ++v) {
       ynew[v] = x[v] + hs * (((k1[v] + 4.0 * k2[v]) + k3[v]) / 6.0);
@@ -543,7 +546,7 @@ static double monitor_value(const hhd_handle h, int var, int i) {
   double x[8];
   for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
   if (var < 8) return x[var];
-  if (var == HHD_LAST_SPIKE) return h->last_spike[h->cfg.global_offset + i];
+  if (var == HHD_LAST_SPIKE) return h->last_spike[h->cfg.global_offset + i] * 1e3;
   npar p = load_par(h, i);
   subexpr s;
   subexpressions(h, &p, x, iac_at(h, i, h->step), &s);
@@ -583,7 +586,7 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
   int rc = check_ready(h);
   if (rc) return rc;
   const int64_t k = h->step;
-  const double dt = h->cfg.dt_ms, t = (double)k * dt;
+  const double ts = hhd_time_s(k, h->cfg.dt_ms);
   const int off = h->cfg.global_offset;
 
   /* slot `start`: StateMonitors sample the state before the update (codes/CortexNetwork.py:510) */
@@ -604,15 +607,15 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
   /* slot `groups`: state update of all 8 variables (codes/CortexNetwork.py:308-309) */
   int64_t bad = 0;
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static) reduction(+ : bad)
+#pragma omp parallel for schedule(static) reduction(+ : bad) if (h->N >= OMP_MIN_NEURONS)
 #endif
   for (int i = 0; i < h->N; ++i) {
     npar p = load_par(h, i);
     double x[8];
     for (int v = 0; v < 8; ++v) x[v] = h->x[v][i];
     const double iac0 = iac_at(h, i, k), iac1 = iac_at(h, i, k + 1);
-    if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, t, h->last_spike[off + i], iac0, iac1, &h->hstep[i]);
-    else integrate_fixed(h, &p, x, t, h->last_spike[off + i], iac0, iac1);
+    if (h->cfg.method == HHD_RK23_ADAPTIVE) integrate_rk23(h, &p, x, ts, h->last_spike[off + i], iac0, iac1, &h->hstep[i]);
+    else integrate_fixed(h, &p, x, ts, h->last_spike[off + i], iac0, iac1);
     if (h->noise_sigma && h->noise_sigma[i] != 0.0) {
       /* Euler-Maruyama term of Brian's stochastic `euler` updater: x + dt f(x) + xi sigma, xi = sqrt(dt) N(0,1) */
       const double sg = h->noise_sigma[i] * sqrt(h->cfg.dt_ms);
@@ -633,7 +636,7 @@ int hhdo_step_begin(hhd_handle h, int32_t* local_spikes_global_ids, int32_t* n_s
   h->n_cur_wcross = 0;
   if (!h->flag_scratch) h->flag_scratch = (uint8_t*)malloc((size_t)h->N);
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (h->N >= OMP_MIN_NEURONS)
 #endif
   for (int i = 0; i < h->N; ++i) {
     const int not_refractory = (k - h->lastspike_step[i]) >= h->refr_steps;
@@ -685,7 +688,7 @@ int hhdo_step_end(hhd_handle h, const int32_t* all_spikes, int32_t n_all) {
   if (!h) return HHD_E_ARG;
   if (!h->step_open) return fail(h, HHD_E_STATE, "no open step");
   const int64_t k = h->step;
-  const double dt = h->cfg.dt_ms, t = (double)k * dt;
+  const double t = hhd_time_s(k, h->cfg.dt_ms);      /* seconds: t, last_spike_pre and the STP time constants as Brian holds them */
   const int off = h->cfg.global_offset;
 
   /* slot `synapses`, pathways p0..p6 (order 0..6, no delay) for every synapse of every spiking neuron (:360-366) */
@@ -736,6 +739,9 @@ int hhdo_step_end(hhd_handle h, const int32_t* all_spikes, int32_t n_all) {
   }
   if (h->cfg.accum != HHD_ACCUM_FIXED) {
     for (int c = 0; c < 3; ++c)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (h->N >= OMP_MIN_NEURONS)
+#endif
       for (int i = 0; i < h->N; ++i) {
         const double inc = h->pendd[(size_t)c * h->N + i];
         if (inc != 0.0) {
@@ -747,6 +753,9 @@ int hhdo_step_end(hhd_handle h, const int32_t* all_spikes, int32_t n_all) {
   }
   if (h->cfg.accum == HHD_ACCUM_FIXED) {
     for (int c = 0; c < 3; ++c)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (h->N >= OMP_MIN_NEURONS)
+#endif
       for (int i = 0; i < h->N; ++i) {
         const int64_t q = h->pend[0][(size_t)c * h->N + i];
         if (q) {
@@ -886,7 +895,7 @@ int hhd_read_state(hhd_handle h, int32_t var, double* out) {
 int hhd_write_state(hhd_handle h, int32_t var, const double* in) {
   if (!h || !in) return fail(h, HHD_E_ARG, "null argument");
   if (var >= 0 && var < 8) memcpy(h->x[var], in, (size_t)h->N * 8);
-  else if (var == HHD_LAST_SPIKE) memcpy(h->last_spike + h->cfg.global_offset, in, (size_t)h->N * 8);
+  else if (var == HHD_LAST_SPIKE) for (int i = 0; i < h->N; ++i) h->last_spike[h->cfg.global_offset + i] = in[i] * 1e-3;
   else return fail(h, HHD_E_ARG, "variable %d is not writable", var);
   return HHD_OK;
 }

@@ -100,11 +100,11 @@ struct __align__(16) SynStp {   /* read and written once per presynaptic spike (
 
 struct Params {
   int N, NG, off, refr_steps, accum, n_mon, max_delay, W;
-  double dt;
+  double dt, dt_s;             /* ms (integration) and seconds (Brian's clock: t, last_spike, the STP decays — hhd_time_s) */
   unsigned long long seed;
   ChannelConst cc;
   double* nb;                  /* [n_pad / 32][NB_FIELDS][32] neuron blocks: 8 state rows + 12 parameter rows (nb_index) */
-  double* last_spike;          /* [NG] */
+  double* last_spike;          /* [NG] seconds */
   double* hstep;               /* [n_pad] adaptive method: the step size a neuron carries from one dt to the next */
   int* meta;                   /* [n_pad] lastspike_step << META_SHIFT | flags (of the previous step; FLAG_OUT, FLAG_ZERO static) */
   const unsigned char* has_out;/* [NG] */
@@ -363,7 +363,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
   const int warp = tid >> 5;
-  const double t = (double)k * P.dt;
+  const double t = (double)k * P.dt_s;
   const int nblocks = (int)(P.n_pad >> 5);
   if (STEP && blockIdx.x == 0 && tid == 0) dbg_stamp(P, k, 0);
   if (tid < 3) sh.cnt[tid] = 0ull;
@@ -794,7 +794,7 @@ __device__ __forceinline__ void ext_events(const Params& P, const long long k, l
 template <bool LONG>
 __device__ __forceinline__ void spike_new_phase(const Params& P, const long long k, const unsigned bid, const unsigned nblk) {
   __shared__ int older_sh[17];
-  const double t = (double)k * P.dt;
+  const double t = (double)k * P.dt_s;
   const unsigned lane = threadIdx.x & 31;
   long long* const pout = pend_of_slot(P, k);
   const unsigned long long lo_new = P.step_end[((int)k + P.W - 1) % P.W];
@@ -976,7 +976,7 @@ __device__ __forceinline__ void recv_spikes(const Params& P, const long long k) 
       const int j = __ldcg(src + 1 + q);             /* written by another GPU: not through this SM's L1 */
       P.spk_neuron[pos] = j;
       P.spk_step[pos] = (int)k;
-      note_spike(P, j, (int)k, (double)k * P.dt);
+      note_spike(P, j, (int)k, (double)k * P.dt_s);
     }
   }
   __syncthreads();
@@ -1096,7 +1096,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
 
   for (int s = 0; s <= n_steps; ++s) {
     const long long k = k0 + s;
-    const double t = (double)k * P.dt;
+    const double t = (double)k * P.dt_s;
     /* ---------------- phase 1: finish step k-1, then (if s < n_steps) slots start / groups / thresholds of step k ------ */
     if (live) {
 #pragma unroll
@@ -1113,7 +1113,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
         x[0] = p.Vr;
         x[1] += p.b;
         if (has_out) {                                   /* p5: last_spike_pre = t of the spike's step */
-          ls = (double)(k - 1) * P.dt;
+          ls = (double)(k - 1) * P.dt_s;
           P.last_spike[P.off + i] = ls;
         }
       }
@@ -1313,7 +1313,7 @@ __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P
       const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
       P.spk_neuron[pos] = src[1 + q];
       P.spk_step[pos] = (int)k;
-      note_spike(P, src[1 + q], (int)k, (double)k * P.dt);
+      note_spike(P, src[1 + q], (int)k, (double)k * P.dt_s);
     }
   }
   __syncthreads();
@@ -1500,9 +1500,9 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   Params& P = h->P;
-  P.N = h->N; P.NG = h->NG; P.off = h->cfg.global_offset; P.dt = cfg->dt_ms; P.accum = cfg->accum; P.seed = cfg->seed;
+  P.N = h->N; P.NG = h->NG; P.off = h->cfg.global_offset; P.dt = cfg->dt_ms; P.dt_s = hhd_dt_s(cfg->dt_ms); P.accum = cfg->accum; P.seed = cfg->seed;
   P.refr_steps = (int)hhd_timestep(cfg->refractory_ms, cfg->dt_ms);
-  P.cc.window_ms = cfg->block_window_ms;
+  P.cc.window_s = cfg->block_window_ms * 1e-3;
   int rc = 0;
   const size_t n_pad = (size_t)((h->N + NB_LANES - 1) / NB_LANES) * NB_LANES;   /* whole 32-neuron blocks for the bulk copies */
   rc = dev_alloc(h, &P.nb, n_pad * NB_FIELDS);
@@ -1527,7 +1527,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (rc) { std::string m = h->err; hhd_destroy(h); g_create_err = m; return rc; }
   P.base_step = h->d_base_step; P.counters = h->d_counters; P.mon = h->d_mon;
   {
-    std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms);
+    std::vector<double> ls((size_t)h->NG, cfg->last_spike0_ms * 1e-3);     /* seconds */
     std::vector<int> lk(n_pad, -(1 << 30));          /* lastspike = -2^26 steps, no flags */
     cudaMemcpyAsync(P.last_spike, ls.data(), ls.size() * 8, cudaMemcpyHostToDevice, h->stream);
     if (P.hstep) {
@@ -1700,7 +1700,7 @@ __global__ void k_syn_gather(long long nsyn, const unsigned long long* keys, con
   h.amp = 0.0;
   hot[r] = h;
   SynStp y;
-  y.U = U[o]; y.tau_rec = tau_rec[o]; y.tau_fac = tau_fac[o]; y.gmax = gmax[o]; y.pfail = pfail[o];
+  y.U = U[o]; y.tau_rec = tau_rec[o] * 1e-3; y.tau_fac = tau_fac[o] * 1e-3;   /* seconds (hhd_time_s) */ y.gmax = gmax[o]; y.pfail = pfail[o];
   y.u = y.U;       /* u = U   (codes/CortexNetwork.py:422) */
   y.R = 1.0;       /* R = 1   (:424) */
   y.orig = o; y.pad = 0;
@@ -2724,7 +2724,11 @@ extern "C" int hhd_write_state(hhd_handle h, int32_t var, const double* in) {
   if (!h || !in) return fail(h, HHD_E_ARG, "null argument");
   cudaSetDevice(h->cfg.device);
   if (var >= 0 && var < 8) return scatter_field(h, var, in);
-  if (var == HHD_LAST_SPIKE) return upload(h, h->P.last_spike + h->cfg.global_offset, in, (size_t)h->N);
+  if (var == HHD_LAST_SPIKE) {       /* given in ms, held in seconds */
+    std::vector<double> ls((size_t)h->N);
+    for (int i = 0; i < h->N; ++i) ls[i] = in[i] * 1e-3;
+    return upload(h, h->P.last_spike + h->cfg.global_offset, ls.data(), (size_t)h->N);
+  }
   return fail(h, HHD_E_ARG, "variable %d is not writable", var);
 }
 

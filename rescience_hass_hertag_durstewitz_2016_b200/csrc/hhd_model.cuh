@@ -1,6 +1,6 @@
 /*
  * hhd_model.cuh — device-side arithmetic of the simplified-AdEx neuron and its synapses, shared by the grid-wide
- * (hhd_engine.cu) and cluster-resident (hhd_resident.cu) kernels.
+ * (k_neuron / k_synapse) and cluster-resident (k_resident) kernels of hhd_engine.cu.
  *
  * Every expression keeps the operand order of the reference's equation strings (codes/CortexNetwork.py:233-302 for the
  * neuron, :360-372 for the synapse pathways) and is compiled with -fmad=false, so a neuron's trajectory is bit-identical
@@ -15,7 +15,7 @@ struct ChannelConst {
   double inv_tau_on[3], inv_tau_off[3];   /* 1/tau (codes/CortexNetwork.py:256-263 write -(1/tau)*g) */
   double E[3], gsyn[3];
   double mg_fac, mg_slope, mg_half;
-  double window_ms;                        /* `t - last_spike < 5*ms` (:251) */
+  double window_s;                         /* `t - last_spike < 5*ms` (:251), in seconds like t and last_spike (hhd_time_s) */
 };
 
 struct NeuronPar {
@@ -66,10 +66,11 @@ __device__ __forceinline__ void hhd_subexpr_new_g(const ChannelConst& cc, const 
 }
 
 /* Right-hand sides at state x given the subexpressions `s` of that state. */
-__device__ __forceinline__ void hhd_rhs(const ChannelConst& cc, const NeuronPar& p, const double x[8], double t, double ls,
+/* ts = stage time, ls = the neuron's last_spike, both in SECONDS (Brian's SI values, see hhd_time_s in hhd_math.h). */
+__device__ __forceinline__ void hhd_rhs(const ChannelConst& cc, const NeuronPar& p, const double x[8], double ts, double ls,
                                         const SubExpr& s, double d[8]) {
   const double V = x[0], w = x[1];
-  const double a = ((s.I_tot >= p.Iref) ? 1.0 : 0.0) * ((t - ls < cc.window_ms) ? 1.0 : 0.0);
+  const double a = ((s.I_tot >= p.Iref) ? 1.0 : 0.0) * ((ts - ls < cc.window_s) ? 1.0 : 0.0);
   const double dV = (a * hhd_div(-p.gL, p.C)) * (V - p.Vdep) + hhd_div((1.0 - a) * (s.w_V - w), p.C);
   const double band = hhd_div(s.D0, p.tauw);
   const double gate = ((w > s.w_V - band) ? 1.0 : 0.0) * ((w < s.w_V + band) ? 1.0 : 0.0) *
@@ -93,12 +94,13 @@ __device__ __forceinline__ void hhd_deriv(const ChannelConst& cc, const NeuronPa
 /* Brian 2's ExplicitStateUpdaters: METHOD 0 euler, 1 rk2 (midpoint), 2 rk4.  `s1` = subexpressions of the state x on entry
  * (the caller has them already: they also decide the deferred w_crossing test and feed the monitors). */
 template <int METHOD>
-__device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t,
-                                              double ls, double dt, const SubExpr& s1, const double iac0 = 0.0,
+__device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const NeuronPar& p, double x[8], double t /* s */,
+                                              double ls /* s */, double dt /* ms */, const SubExpr& s1, const double iac0 = 0.0,
                                               const double iac1 = 0.0,     /* I_AC of this step / of the next (stage at t+dt) */
                                               double* hcar = nullptr) {    /* adaptive method only: the carried step size */
   double k1[8], y[8];
   SubExpr sk;
+  const double dts = hhd_dt_s(dt);
   hhd_rhs(cc, p, x, t, ls, s1, k1);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k1[v] = dt * k1[v];
@@ -110,7 +112,7 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   double k2[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k1[v] * 0.5;
-  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k2, sk, iac0);
+  hhd_deriv(cc, p, y, t + dts * 0.5, ls, k2, sk, iac0);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k2[v] = dt * k2[v];
   if (METHOD == 1) {
@@ -121,12 +123,12 @@ __device__ __forceinline__ void hhd_integrate(const ChannelConst& cc, const Neur
   double k3[8], k4[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k2[v] * 0.5;
-  hhd_deriv(cc, p, y, t + dt * 0.5, ls, k3, sk, iac0);
+  hhd_deriv(cc, p, y, t + dts * 0.5, ls, k3, sk, iac0);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k3[v] = dt * k3[v];
 #pragma unroll
   for (int v = 0; v < 8; ++v) y[v] = x[v] + k3[v];
-  hhd_deriv(cc, p, y, t + dt, ls, k4, sk, iac1);
+  hhd_deriv(cc, p, y, t + dts, ls, k4, sk, iac1);
 #pragma unroll
   for (int v = 0; v < 8; ++v) k4[v] = dt * k4[v];
 #pragma unroll
@@ -149,15 +151,15 @@ __device__ __forceinline__ void hhd_integrate<3>(const ChannelConst& cc, const N
     if (hs > dt - t) { hs = dt - t; final_step = true; }
     double k1[8], k2[8], k3[8], y[8], ynew[8];
     SubExpr sk;
-    if (first) hhd_rhs(cc, p, x, t0 + t, ls, s1, k1);
-    else hhd_deriv(cc, p, x, t0 + t, ls, k1, sk, iac0);
+    if (first) hhd_rhs(cc, p, x, t0 + t * 1e-3, ls, s1, k1);
+    else hhd_deriv(cc, p, x, t0 + t * 1e-3, ls, k1, sk, iac0);
     first = false;
 #pragma unroll
     for (int v = 0; v < 8; ++v) y[v] = x[v] + (0.5 * hs) * k1[v];
-    hhd_deriv(cc, p, y, t0 + (t + 0.5 * hs), ls, k2, sk, iac0);
+    hhd_deriv(cc, p, y, t0 + (t + 0.5 * hs) * 1e-3, ls, k2, sk, iac0);
 #pragma unroll
     for (int v = 0; v < 8; ++v) y[v] = x[v] + hs * (2.0 * k2[v] - k1[v]);
-    hhd_deriv(cc, p, y, t0 + (t + hs), ls, k3, sk, final_step ? iac1 : iac0);
+    hhd_deriv(cc, p, y, t0 + (t + hs) * 1e-3, ls, k3, sk, final_step ? iac1 : iac0);
     double rmax = 0.0;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
@@ -222,7 +224,7 @@ __device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const Ne
     case 5: return x[5];
     case 6: return x[6];
     case 7: return x[7];
-    case 20: return last_spike;
+    case 20: return last_spike * 1e3;      /* held in seconds, reported in ms */
   }
   SubExpr s;
   hhd_subexpr(cc, p, x, s, iac);
@@ -243,7 +245,8 @@ __device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const Ne
   return 0.0;
 }
 
-/* Pathways p0..p6 for one synapse at presynaptic spike time t (codes/CortexNetwork.py:360-366); returns the amplitude
+/* Pathways p0..p6 for one synapse at presynaptic spike time t (codes/CortexNetwork.py:360-366; t, last, tau_rec, tau_fac in
+ * seconds); returns the amplitude
  * ((g_max*a_syn)*(1-failure))*Gsyn that the order-7 pathways add when the delay has elapsed (:367-372). */
 __device__ __forceinline__ double hhd_stp_update(double& u, double& R, double U, double tau_rec, double tau_fac,
                                                  double gmax, double gsyn, double pfail, double t, double last,

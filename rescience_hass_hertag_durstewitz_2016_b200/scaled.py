@@ -96,28 +96,49 @@ def _clipped(torch, draw, lo, hi, gen, device):
     return torch.where(bad, lo + (hi - lo) * torch.rand(draw.shape, generator=gen, device=device, dtype=torch.float64), draw)
 
 
+def column_chunk(n_columns):
+    """Columns per random-number chunk of `inter_column_synapses_device`: the draws of a chunk depend only on (seed, chunk
+    index), so every partition whose boundaries are multiples of the chunk builds the SAME network (1000 or 4000 columns on
+    1, 2, 4 or 8 GPUs: chunks of 25)."""
+    return 25 if n_columns % 200 == 0 else (5 if n_columns % 40 == 0 else 1)
+
+
 def inter_column_synapses_device(groups, n_per_column, n_columns, device, col_lo=0, col_hi=None, seed=0):
     """Inter-column synapses of a ring of `n_columns` identical columns, for the TARGET columns [col_lo, col_hi), drawn on
-    the GPU with the reference's rules (codes/ParamSetup.py:575-587, codes/NetworkSetup.py:267-321): PC_L23 -> PC_L23 at
+    `device` (a CUDA device, or "cpu" for the CPU arm of bench.py) with the reference's rules (codes/ParamSetup.py:575-587,
+    codes/NetworkSetup.py:267-321): PC_L23 -> PC_L23 at
     +-2 and +-4 columns, IN_CC_L5 -> PC_L5 and IN_F_L5 -> PC_L5 at +-1, connection probability and peak conductance
     falling off as exp(-d/0.909), delay mean and spread growing linearly with d (up to ~15 ms, i.e. beyond the refractory
     period), AMPA synapses with an NMDA twin of the same delay, STP classes mixed as within a column.
     `groups[g]` = template-local neuron ids of cell group g.  Pairs are drawn WITH replacement (< 1 % duplicates), which
     the reference's own blocks also contain; this is the synthetic stand-in for SURVEY §8f-1, not a bit-exact port.
-    -> (src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms) as torch CUDA tensors, ids global."""
+    The random stream is restarted per chunk of `column_chunk(n_columns)` target columns, so the network does not depend on
+    how it is partitioned (round 1 seeded by col_lo: 1 GPU and 8 GPUs simulated different networks).
+    -> (src, tgt, chan, g_max, U, tau_rec, tau_fac, p_fail, delay_ms) as torch tensors on `device`, ids global."""
     import contextlib
     import io
     import torch
     from .codes.ParamSetup import ParamSetup
     with contextlib.redirect_stdout(io.StringIO()):
         ps = ParamSetup(1000, 1, ([1, 1, 1, 1], [1, 1, 1, 1], np.ones((10, 14))))
+    col_hi = n_columns if col_hi is None else col_hi
+    chunk = column_chunk(n_columns)
+    if col_lo % chunk or col_hi % chunk:
+        raise ValueError("partition boundaries must be multiples of %d columns for a %d-column ring" % (chunk, n_columns))
+    parts = [_inter_column_chunk(torch, ps, groups, n_per_column, n_columns, device, c, c + chunk, seed) for c in range(col_lo, col_hi, chunk)]
+    parts = [p for p in parts if p is not None]
+    if not parts:
+        return None
+    return tuple(torch.cat([p[q] for p in parts]).contiguous() for q in range(9))
+
+
+def _inter_column_chunk(torch, ps, groups, n_per_column, n_columns, device, col_lo, col_hi, seed):
     SynTypes, Syngmax, Syndelay, STSP_prob, STSP_types, pCon, S_sig = ps[8], ps[9], ps[10], ps[12], ps[13], ps[14], ps[16]
     STSP_setup, get_SynType, get_STSP_prob, get_STSP_types = ps[26], ps[27], ps[28], ps[29]
     rules, coef, offsets = ps[31]
-    col_hi = n_columns if col_hi is None else col_hi
     ncol = col_hi - col_lo
     gen = torch.Generator(device=device)
-    gen.manual_seed(int(seed) * 7919 + 17 * col_lo + 1)
+    gen.manual_seed(int(seed) * 1000003 + 7919 * (col_lo // column_chunk(n_columns)) + 1)
     cols = torch.arange(col_lo, col_hi, device=device, dtype=torch.int64)[:, None]
     out = [[] for _ in range(9)]
     f64 = dict(generator=gen, device=device, dtype=torch.float64)
