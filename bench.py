@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--instances", action="store_true", help="treat every column as an independent instance (config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rk4 / high-activity / one-column legs")
+    ap.add_argument("--high-idc-scale", type=float, default=1.5, help="background-current scale of the high-activity leg")
     return ap.parse_args()
 
 
@@ -93,9 +95,23 @@ def build_workload(args, rank, world, device_synapses=False):
     return net
 
 
-def make_engine(cls, net, args, seed, **kw):
+def make_engine(cls, net, args, seed, host=False, **kw):
     from rescience_hass_hertag_durstewitz_2016_b200.engine import load_codes_network
     n = net["NeuPar"].shape[1]
+    if host and "col" in net:
+        # CPU arm: the same generators, tensors on the host
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import multicolumn_synapses_device, tile_synapses_device
+        col = net["col"]
+        e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
+        load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+        if args.workload == "multicolumn":
+            syn = multicolumn_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], col["groups"], net["columns_total"],
+                                              net["n_per_column"], "cpu", 0, net["columns_total"], seed=1)
+        else:
+            syn = tile_synapses_device(col["SynPar"], col["source_arr"], col["target_arr"], net["columns_total"], net["n_per_column"], "cpu")
+        net["nsyn"] = int(syn[0].numel())
+        e.set_synapses(*[t.numpy() for t in syn])
+        return e
     if cls.__name__ == "Engine":
         kw = dict(kw, plan=args.plan, instance_size=net["n_per_column"] if (args.instances or args.workload == "column") else 0)
     e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
@@ -174,55 +190,107 @@ class ClockSampler:
 
 
 # ---- the CPU arm ---------------------------------------------------------------------------------------------------
-CPU_SAMPLE_COLUMNS = 16
+CPU_SAMPLE_COLUMNS = 40      # columns of the CPU sample of a multi-column workload (40 130 neurons, 1.26e7 synapses)
 
 
-def cpu_sample(args, seconds, threads):
-    """Time the CPU oracle (kind 'port': Brian 2, the reference's engine, cannot be installed here) on a bounded
-    sample of the same workload: the first CPU_SAMPLE_COLUMNS columns (columns of the tiled network are independent,
-    and CPU cost is linear in neurons) for a bounded number of time steps."""
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    from oracle_binding import OracleEngine
-    import copy
-    a2 = copy.copy(args)
-    if args.workload != "column":
-        a2.workload = "columns"           # the CPU sample is always a block of independent columns
-        a2.columns = min(args.columns or 1000, CPU_SAMPLE_COLUMNS)
-    net = build_workload(a2, 0, 1)
-    e = make_engine(OracleEngine, net, args, seed=1, record_spikes=True)
-    n = net["NeuPar"].shape[1]
-    e.run(3)                                   # first touch
-    t0 = time.perf_counter()
-    e.run(5)
-    per = max((time.perf_counter() - t0) / 5, 1e-7)
-    nsteps = int(max(4, min(args.window * 20, seconds / per)))     # about `seconds` of CPU work, at most 2 s of biological time
-    t0 = time.perf_counter()
-    e.run(nsteps)
-    el = time.perf_counter() - t0
-    c = e.counters()
-    e.close()
-    return dict(value=n * nsteps / el, unit="neuron-updates/s", cores=threads, kind="port",
-                sample="%d time steps of %d column(s) (%d neurons, %d synapses) of the same network from rest (%.1f s wall), C oracle%s" %
-                       (nsteps, net["columns_total"], n, net["nsyn"], el, " with OpenMP over neurons" if threads > 1 else ", single thread"),
-                syn_events_per_s=c["syn_events"] / el, ms_per_time_step=el / nsteps * 1e3), nsteps, el
+class CpuSample:
+    """The CPU oracle (kind 'port': Brian 2, the reference's engine, cannot be installed here — the probe below says so in
+    the JSON line) on a bounded sample of the SAME workload: for the ring of columns a ring of CPU_SAMPLE_COLUMNS columns
+    with inter-column synapses drawn by the same generator (scaled.multicolumn_synapses_device on the host), for the
+    single column the column itself.  CPU cost is linear in neurons, so neuron-updates/s of the sample is the figure for
+    the whole network.  Built once; every call continues the same simulation."""
+
+    def __init__(self, args, threads):
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        from oracle_binding import OracleEngine, oracle_lib
+        import copy
+        self.threads = threads
+        self.lib = oracle_lib()
+        self.lib.omp_set_num_threads(int(threads))     # the environment variable is only read when libgomp is loaded
+        a2 = copy.copy(args)
+        if args.workload != "column":
+            a2.columns = min(args.columns or 1000, CPU_SAMPLE_COLUMNS)
+        self.args = a2
+        net = build_workload(a2, 0, 1, device_synapses=args.workload != "column")
+        t0 = time.perf_counter()
+        self.e = make_engine(OracleEngine, net, a2, seed=1, record_spikes=False, host=True)
+        self.n = net["NeuPar"].shape[1]
+        self.net = net
+        self.setup_s = time.perf_counter() - t0
+        self.e.run(3)                                   # first touch
+
+    def probe(self, steps=12):
+        self.lib.omp_set_num_threads(int(self.threads))
+        t0 = time.perf_counter()
+        self.e.run(steps)
+        return (time.perf_counter() - t0) / steps
+
+    def run(self, seconds, max_steps):
+        per = max(self.probe(5), 1e-7)
+        nsteps = int(max(4, min(max_steps, seconds / per)))
+        c0 = self.e.counters()
+        t0 = time.perf_counter()
+        self.e.run(nsteps)
+        el = time.perf_counter() - t0
+        c1 = self.e.counters()
+        what = ("ring of %d columns with inter-column synapses" % self.net["columns_total"]) if self.args.workload == "multicolumn" else \
+               ("%d independent column(s)" % self.net["columns_total"])
+        info = dict(value=self.n * nsteps / el, unit="neuron-updates/s", cores=self.threads, kind="port",
+                    sample="%d time steps of a %s (%d neurons, %d synapses; same generator as the GPU workload), %.1f s wall, C oracle %s" %
+                           (nsteps, what, self.n, self.net["nsyn"], el,
+                            ("with OpenMP over neurons, %d threads" % self.threads) if self.threads > 1 else "single thread"),
+                    syn_events_per_s=(c1["syn_events"] - c0["syn_events"]) / el, ms_per_time_step=el / nsteps * 1e3)
+        return info, nsteps, el
+
+    def close(self):
+        self.e.close()
+
+
+def best_cpu_sample(args):
+    """All host threads if they help, else one: the probe decides, and `cores` reports the count that was used."""
+    ncpu = os.cpu_count() or 1
+    one = CpuSample(args, 1)
+    if ncpu == 1 or args.workload == "column":
+        return one, {"1": one.probe()}
+    t1 = one.probe()
+    many = CpuSample(args, ncpu)
+    tn = many.probe()
+    probes = {"1": t1, str(ncpu): tn}
+    if tn < t1:
+        one.close()
+        return many, probes
+    many.close()
+    return one, probes
+
+
+def brian2_probe():
+    """if Brian 2 is importable on the bench box the reference's own CortexNetwork.run would be the baseline."""
+    try:
+        import brian2  # noqa: F401
+        return "importable (version %s) — the reference itself is not on this box (/root/reference is absent), so it is still the C port that is timed" % brian2.__version__
+    except Exception as ex:
+        return "not importable (%s): the CPU arm is the C restatement of Brian's schedule (oracle/hhd_oracle.c)" % type(ex).__name__
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     net = build_workload(args, 0, 1 if args.workload == "column" else world, device_synapses=True)   # config only
-    threads = os.cpu_count() or 1
+    net["nsyn"] = int(net["nsyn"] * (1.0766 if args.workload == "multicolumn" else 1.0))              # + inter-column synapses (measured ratio)
+    cs, probes = best_cpu_sample(args)
     # one bench step = one bounded sample; K steps + W warm-ups must end within a few minutes
     budget = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
     vals, ms = [], []
     info = None
     for it in range(args.warmup + args.steps):
-        info, nsteps, el = cpu_sample(args, budget, threads)
+        info, nsteps, el = cs.run(budget, args.window * 20)
         if it >= args.warmup:
             vals.append(info["value"])
             ms.append(el * 1e3)
     v = float(np.mean(vals))
     info["value"] = v
+    info["thread_probe_s_per_time_step"] = probes
+    info["brian2"] = brian2_probe()
     out = dict(metric="neuron_updates_per_s", value=v, unit="neuron-updates/s", n_gpus=args.gpus, steps=args.steps,
                warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f64", data="synthetic", impl="reference", config=workload_config(args, net, world),
@@ -241,6 +309,103 @@ def workload_config(args, net, world):
                 monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
                 l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
                 parallelism="%d GPU(s), columns partitioned, spike indices exchanged every time step over IPC-mapped peer memory (NCCL all-gather as fallback)" % world if world > 1 else "1 GPU")
+
+
+# ---- the other halves of the metric: the 1003-neuron column (configs 0-1) and the reference's default integrator -------------
+PUBLISHED_BRIAN_MS_PER_STEP = 1.02     # codes_revision/Tests.py:10 (31 s bio + setup + analyses in 10 min 35 s; rk4; hardware unknown)
+
+
+def column_leg(args, method, device, cpu=True):
+    """One PFC column (the reference's own NetworkSetup output, seed 0), 2 s of biological time = 40 000 steps (BASELINE
+    configs 0/1), cluster-resident plan, spikes + summed-I_tot monitor; CPU beside it: the C port (1 thread) and the NumPy
+    oracle (structurally Brian's numpy target)."""
+    import copy
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
+    a2 = copy.copy(args)
+    a2.workload, a2.method, a2.plan, a2.columns = "column", method, "auto", 0
+    net = build_workload(a2, 0, 1)
+    n = net["NeuPar"].shape[1]
+    steps = int(2000.0 / a2.dt)
+    eng = make_engine(Engine, net, a2, seed=1, device=device)
+    lfp = eng.add_state_monitor("I_tot", None, reduce="sum")
+    eng.run(steps // 4)                                       # warm-up: 500 ms, the network leaves rest
+    eng.clear_monitor(lfp)
+    eng.clear_monitor(-1)
+    c0 = eng.counters()
+    eng.run(steps)
+    c1 = eng.counters()
+    dev_s = (c1["run_ms_device"] - c0["run_ms_device"]) * 1e-3
+    eng.clear_monitor(lfp)
+    eng.clear_monitor(-1)
+    t0 = time.perf_counter()                                  # end to end: host buffers in and out
+    eng.set_idc(net["I_DC"])
+    eng.run(steps)
+    i, sp = eng.spikes()
+    trace = eng.read_monitor(lfp)
+    e2e_s = time.perf_counter() - t0
+    eng.close()
+    out = dict(workload="one PFC column (%s), 2 s biological time" % net["template"], method=method, plan="cluster-resident (k_resident)",
+               neurons=n, synapses=net["nsyn"], time_steps=steps, us_per_time_step=dev_s / steps * 1e6,
+               neuron_updates_per_s=n * steps / dev_s, syn_events_per_s=(c1["syn_events"] - c0["syn_events"]) / dev_s,
+               realtime_factor=2.0 / dev_s, mean_rate_hz=(c1["spikes"] - c0["spikes"]) / n / 2.0,
+               e2e=dict(us_per_time_step=e2e_s / steps * 1e6, neuron_updates_per_s=n * steps / e2e_s, h2d_bytes=int(n * 8),
+                        d2h_bytes=int(len(i) * 12 + trace.nbytes)),
+               speedup_vs_published_brian_1p02_ms_per_step=(PUBLISHED_BRIAN_MS_PER_STEP * 1e3) / (dev_s / steps * 1e6) if method == "rk4" else None)
+    if cpu:
+        cs = CpuSample(a2, 1)
+        info, nsteps, el = cs.run(3.0, steps)
+        cs.close()
+        out["cpu_baseline"] = info
+        out["speedup_vs_c_port_1_thread"] = out["neuron_updates_per_s"] / info["value"]
+        np_us = numpy_oracle_us_per_step(net, a2)
+        out["numpy_oracle"] = dict(us_per_time_step=np_us, neuron_updates_per_s=n / (np_us * 1e-6), cores=1, kind="port",
+                                   sample="300 time steps of the same column after 100 warm-up steps, oracle/numpy_oracle.py (SI units, one numpy statement per Brian code object)")
+        out["speedup_vs_numpy_oracle"] = np_us / out["us_per_time_step"]
+    return out
+
+
+def numpy_oracle_us_per_step(net, a2, steps=300):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from numpy_oracle import NumpyOracle
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import load_codes_network
+    e = NumpyOracle(net["NeuPar"].shape[1], a2.dt, method=a2.method, seed=1)
+    load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+    e.run(100)
+    t0 = time.perf_counter()
+    e.run(steps)
+    return (time.perf_counter() - t0) / steps * 1e6
+
+
+def method_leg(args, method, net, n, device, idc_scale=1.0, windows=2):
+    """The default 1M-neuron workload again with another integrator / background current: device-timed windows + kernel times."""
+    import copy
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
+    a2 = copy.copy(args)
+    a2.method = method
+    net2 = dict(net)
+    net2["I_DC"] = net["I_DC"] * idc_scale
+    eng = make_engine(Engine, net2, a2, seed=1, device=device)
+    lfp = eng.add_state_monitor("I_tot", None, reduce="sum")
+    S = args.window
+    for _ in range(2):
+        eng.run(S)
+        eng.clear_monitor(lfp)
+        eng.clear_monitor(-1)
+    c0 = eng.counters()
+    for _ in range(windows):
+        eng.run(S)
+        eng.clear_monitor(lfp)
+        eng.clear_monitor(-1)
+    c1 = eng.counters()
+    prof = eng.profile_kernels(min(S, 200))
+    eng.close()
+    dev_s = (c1["run_ms_device"] - c0["run_ms_device"]) * 1e-3
+    ev = c1["syn_events"] - c0["syn_events"]
+    steps = S * windows
+    return dict(method=method, idc_scale=idc_scale, us_per_time_step=dev_s / steps * 1e6, neuron_updates_per_s=n * steps / dev_s,
+                syn_events_per_s=ev / dev_s, mean_rate_hz=(c1["spikes"] - c0["spikes"]) / n / (steps * args.dt * 1e-3),
+                realtime_factor=steps * args.dt * 1e-3 / dev_s, us_per_launch=prof, syn_events_per_time_step=ev / steps,
+                frac_of_hbm_roofline_whole_step=None)
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------
@@ -359,28 +524,67 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_PER_NEURON_UPDATE * n / (prof["k_neuron"] * 1e-6) / 1e9
-    traffic = None
-    try:        # DRAM bytes per launch of the same kernel from the committed ncu capture (same workload only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if args.workload != "column" and n == 1003000 and args.method == "euler" and world == 1:
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    traffic, traffic_source = None, None
+    try:        # DRAM bytes per launch of the same kernel: NOT measured in this run (ncu cannot run inside a timed bench) but
+        #         read from the committed `ncu --set full` capture of this very command, and labelled so
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if args.workload == "multicolumn" and n == 1003000 and args.method == "euler" and world == 1:
+            traffic = tr["k_neuron"]["dram_bytes_read"] + tr["k_neuron"]["dram_bytes_write"]
+            traffic_source = "committed ncu capture: " + tr["source"]
     except Exception:
-        pass
+        tr = {}
+    time_steps = S * args.steps
+    ev_per_step = syn_ev / time_steps / world                    # per rank and time step
+    deliv_bytes = BYTES_PER_SYN_EVENT * ev_per_step
+    deliv_achieved = deliv_bytes / (prof["k_synapse"] * 1e-6) / 1e9 if prof["k_synapse"] > 0 else None
+    deliv_traffic = None
+    if traffic is not None and "k_synapse" in tr:
+        deliv_traffic = tr["k_synapse"]["dram_bytes_read"] + tr["k_synapse"]["dram_bytes_write"]
+    step_bytes = BYTES_PER_NEURON_UPDATE * n + deliv_bytes
+    step_us = dev_ms * 1e3 / time_steps
     out = dict(
         metric="neuron_updates_per_s", value=value, unit="neuron-updates/s", n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype="f64", data="synthetic", config=workload_config(args, net, world),
         syn_events_per_s=syn_ev / (dev_ms * 1e-3), realtime_factor=bio_s / (dev_ms * 1e-3),
-        mean_rate_hz=spikes / n_total / bio_s, us_per_time_step=dev_ms * 1e3 / (S * args.steps),
+        mean_rate_hz=spikes / n_total / bio_s, us_per_time_step=step_us,
         roofline=dict(bound="hbm", kernel="k_neuron<%s>" % args.method, achieved=achieved, peak=peak, unit="GB/s",
-                      frac=achieved / peak, traffic=traffic, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                      frac=achieved / peak, traffic=traffic, traffic_source=traffic_source,
+                      peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                       algorithmic_bytes_per_launch=BYTES_PER_NEURON_UPDATE * n,
                       us_per_launch=prof, note="mean of %d launches, CUDA events between kernels on the engine's stream" % min(S, 200)),
+        roofline_delivery=dict(bound="hbm", kernel="k_synapse (spike-time STP + delayed delivery)", achieved=deliv_achieved, peak=peak,
+                               unit="GB/s", frac=(deliv_achieved / peak) if deliv_achieved else None, traffic=deliv_traffic,
+                               traffic_source=traffic_source if deliv_traffic is not None else None,
+                               algorithmic_bytes_per_launch=deliv_bytes, syn_events_per_launch=ev_per_step,
+                               note="96 B per synaptic event (SURVEY 8d) x events per time step; at %.1f Hz the kernel is latency-bound, not "
+                                    "bandwidth-bound — see `high_activity` for the regime where delivery traffic matters" % (spikes / n_total / bio_s)),
+        roofline_whole_step=dict(achieved=step_bytes / (step_us * 1e-6) / 1e9 / 1.0, peak=peak, unit="GB/s",
+                                 frac=step_bytes / (step_us * 1e-6) / 1e9 / peak,
+                                 note="(240 B x neurons + 96 B x synaptic events) per rank / time per time step"),
         e2e=dict(value=e2e_value, unit="neuron-updates/s", h2d_bytes_per_step=int(n * 8), d2h_bytes_per_step=int(d2h / args.steps),
                  ms_per_step=e2e_ms / args.steps),
         gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, wall_s_device_leg=wall_dev)
-    if not args.no_cpu_baseline:
-        out["cpu_baseline"], _, _ = cpu_sample(args, args.cpu_seconds, 1)
+    eng.close()
+    if world == 1 and not args.no_extras and args.workload != "column":
+        # the rest of BASELINE.json's metric on the same box, same process: the reference's default integrator at 1M neurons, a
+        # high-activity variant for the delivery kernel, and the 1003-neuron column (euler + rk4) with its own CPU baselines
+        extra = {}
+        if args.method != "rk4":
+            extra["rk4_1M"] = method_leg(args, "rk4", net, n, local_rank)
+        extra["high_activity"] = method_leg(args, args.method, net, n, local_rank, idc_scale=args.high_idc_scale)
+        for leg in extra.values():
+            b = BYTES_PER_NEURON_UPDATE * n + BYTES_PER_SYN_EVENT * leg["syn_events_per_time_step"]
+            leg["frac_of_hbm_roofline_whole_step"] = b / (leg["us_per_time_step"] * 1e-6) / 1e9 / peak
+            leg["delivery_gbs_algorithmic"] = BYTES_PER_SYN_EVENT * leg["syn_events_per_time_step"] / (leg["us_per_launch"]["k_synapse"] * 1e-6) / 1e9
+        extra["column_1k"] = {m: column_leg(args, m, local_rank, cpu=not args.no_cpu_baseline) for m in ("euler", "rk4")}
+        out.update(extra)
+    if not args.no_cpu_baseline and world == 1:
+        cs, probes = best_cpu_sample(args)
+        out["cpu_baseline"], _, _ = cs.run(args.cpu_seconds, args.window * 20)
+        out["cpu_baseline"]["thread_probe_s_per_time_step"] = probes
+        out["cpu_baseline"]["brian2"] = brian2_probe()
+        cs.close()
     print(json.dumps(out), flush=True)
 
 

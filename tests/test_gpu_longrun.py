@@ -12,11 +12,13 @@ Published (content.tex:239, 318, 334-335, 344, 359, 382):
     CV 1.13 +- 0.49 / 0.97 +- 0.45 / 1.10 +- 0.45;   zero-lag Pearson CC 9.7e-4 +- 6.7e-3 / 7.0e-4 +- 6.4e-3 / 6.7e-4 +- 6.5e-3;
     spiking neurons (> 10 spikes / 30 s) 20.66 +- 2.55 % (16.95-27.62), pyramidal cells 12.28 +- 2.81 % (8.12-20.12), 25 realisations;
     LFP spectrum ~ 1/f^a with a ~ 1 below 60 Hz and 2 < a < 3 above;   V std (spikes excised) 2.82 +- 1.43 mV, PC 2.42 +- 0.94 mV.
-Measured on B200 (profiles/r2_longrun_rk4.json, r2_longrun_gslrk2.json; mean +- SD ACROSS realisations, [min, max]):
-    rk4, seeds 0-6:      mean ISI 480 +- 99 ms [348, 607];  CV 0.958 +- 0.050 [0.90, 1.06];  CC0 8e-4 +- 6.4e-3;
-                         spiking 19.2 +- 2.7 % [16.0, 24.6], PC 11.1 +- 2.7 %;  LFP slope -0.76 +- 0.15 (7.4-60 Hz), -3.05 +- 0.08 (60-1000 Hz);
-                         V std 2.66 +- 0.16 mV, PC 2.46 +- 0.10 mV
-    gsl_rk2, seeds 0-4:  mean ISI 479 +- 73 ms;  CV 0.954 +- 0.020;  CC0 8e-4 +- 6.4e-3;  spiking 18.8 %, PC 10.7 %
+Measured on B200 with `accum="fixed"` and the clock in seconds (profiles/r2_longrun_final.json, r2_longrun_pytest_output.txt;
+mean +- SD ACROSS realisations, [min, max]):
+    rk4, seeds 0-6:      mean ISI 491 +- 68 ms [406, 580];  CV 0.963 +- 0.047 [0.92, 1.06];  CC0 8.6e-4 +- 6.3e-3;
+                         spiking 19.4 +- 2.7 % [16.0, 25.0], PC 11.2 +- 2.7 %;  LFP slope -0.72 +- 0.13 (7.4-60 Hz), -3.05 +- 0.07 (60-1000 Hz);
+                         V std 2.69 +- 0.13 mV, PC 2.44 +- 0.12 mV
+    gsl_rk2, seeds 0-4:  mean ISI 495 +- 95 ms [380, 653];  CV 0.952 +- 0.026;  CC0 8.6e-4 +- 6.4e-3;  spiking 18.8 %, PC 10.8 %;
+                         LFP slope -0.70 / -3.06
 Round 1 compared ONE realisation (seed 0: 412 ms) and had to widen the ISI tolerance to +-35 %; the realisation spread above
 explains that number.  Tolerances: population mean of mean-ISI within +-10 % of the paper's figure for the same
 integrator; population mean of CV within +-0.16 of the paper's (plus twice the standard error of our own estimate over the
