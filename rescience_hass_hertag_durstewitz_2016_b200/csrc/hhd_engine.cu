@@ -103,14 +103,18 @@ struct Params {
   double dt, dt_s;             /* ms (integration) and seconds (Brian's clock: t, last_spike, the STP decays — hhd_time_s) */
   unsigned long long seed;
   ChannelConst cc;
-  double* nb;                  /* [n_pad / 32][NB_FIELDS][32] neuron blocks: 8 state rows + 12 parameter rows (nb_index) */
+  double* nb;                  /* [n_pad / 32][NB_FIELDS][32] neuron blocks: 8 state rows + 9 streamed parameter rows (nb_index) */
+  const double* rare;          /* [N_RARE][n_pad] b, V_r, V_dep: fetched only by the lanes that need them */
   double* last_spike;          /* [NG] seconds */
   double* hstep;               /* [n_pad] adaptive method: the step size a neuron carries from one dt to the next */
   int* meta;                   /* [n_pad] lastspike_step << META_SHIFT | flags (of the previous step; FLAG_OUT, FLAG_ZERO static) */
   const unsigned char* has_out;/* [NG] */
-  long long* pend;             /* [2][n_pad / 32][3][32] (pend_index) synaptic increments summed per (channel, target): fp64
-                                  bits (HHD_ACCUM_FP64) or int64 multiples of 2^-40 nS (HHD_ACCUM_FIXED).  The deliveries of
-                                  slot k go to buffer (k+1)&1; the state-update pass of step k+1 consumes and clears it. */
+  long long* pend;             /* [n_slots][n_pad / 32][3][32] (pend_index): the per-delay circular conductance buffer.  Slot
+                                  (s mod n_slots) sums, per (channel, target), the synaptic increments that Brian's `synapses`
+                                  slot of step s delivers: fp64 bits (HHD_ACCUM_FP64) or int64 multiples of 2^-40 nS
+                                  (HHD_ACCUM_FIXED).  A presynaptic spike of step k adds its synapses' amplitudes to slots
+                                  k + delay right away (k_synapse); the state-update pass of step s + 1 consumes and clears slot s. */
+  int n_slots;                 /* max_delay + 1 */
   long long n_pad;             /* neurons rounded up to whole 32-neuron blocks */
   /* synapses, CSR by global presynaptic neuron, rows sorted by (delay, original index) */
   const long long* row_ptr;    /* [NG+1] */
@@ -275,8 +279,24 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
  */
 #define NB_LANES 32
 #define NB_STATE 8
-#define NB_FIELDS (NB_STATE + HHD_N_PARAMS)                 /* 20 */
-#define NB_BYTES (NB_FIELDS * NB_LANES * 8)                 /* 5120 */
+#define NB_PARAMS 9                                         /* parameter rows that are streamed every step */
+#define NB_FIELDS (NB_STATE + NB_PARAMS)                    /* 17 */
+#define NB_BYTES (NB_FIELDS * NB_LANES * 8)                 /* 4352 */
+/* Three of the twelve parameters are needed by almost no neuron-step and are NOT streamed: b and V_r only by the reset of a
+ * neuron that spiked (0.015 % of the neuron-steps at 3 Hz), V_dep only while the depolarisation-block window of 5 ms after a
+ * spike is open (1.5 %).  They live in a plain side array (P.rare) and are fetched by the lanes that need them — 24 of the
+ * 240 algorithmic bytes per neuron-update are not moved at all. */
+enum { ROW_C = 0, ROW_GL, ROW_EL, ROW_DELTAT, ROW_VUP, ROW_TAUW, ROW_VT, ROW_IREF, ROW_IDC };
+enum { RARE_B = 0, RARE_VR, RARE_VDEP, N_RARE };
+__device__ __host__ __forceinline__ int param_row(int p) {      /* HHD_P_* -> streamed row (>= 0) or -1 - rare row */
+  switch (p) {
+    case HHD_P_C: return ROW_C;          case HHD_P_GL: return ROW_GL;      case HHD_P_EL: return ROW_EL;
+    case HHD_P_DELTAT: return ROW_DELTAT; case HHD_P_VUP: return ROW_VUP;    case HHD_P_TAUW: return ROW_TAUW;
+    case HHD_P_VT: return ROW_VT;        case HHD_P_IREF: return ROW_IREF;  case HHD_P_IDC: return ROW_IDC;
+    case HHD_P_B: return -1 - RARE_B;    case HHD_P_VR: return -1 - RARE_VR;
+  }
+  return -1 - RARE_VDEP;
+}
 #define PEND_BYTES (3 * NB_LANES * 8)                       /* 768 */
 #define META_BYTES (NB_LANES * 4)                           /* 128 */
 
@@ -290,10 +310,11 @@ __device__ __host__ __forceinline__ size_t pend_index(int c, long long i) {
 __device__ __forceinline__ NeuronPar load_par(const Params& P, int i) {
   NeuronPar p;
   const double* b = P.nb + nb_index(NB_STATE, i);
-  p.C = __ldg(b + HHD_P_C * NB_LANES); p.gL = __ldg(b + HHD_P_GL * NB_LANES); p.EL = __ldg(b + HHD_P_EL * NB_LANES);
-  p.dT = __ldg(b + HHD_P_DELTAT * NB_LANES); p.Vup = __ldg(b + HHD_P_VUP * NB_LANES); p.tauw = __ldg(b + HHD_P_TAUW * NB_LANES);
-  p.b = __ldg(b + HHD_P_B * NB_LANES); p.Vr = __ldg(b + HHD_P_VR * NB_LANES); p.VT = __ldg(b + HHD_P_VT * NB_LANES);
-  p.Iref = __ldg(b + HHD_P_IREF * NB_LANES); p.Vdep = __ldg(b + HHD_P_VDEP * NB_LANES); p.IDC = __ldg(b + HHD_P_IDC * NB_LANES);
+  p.C = __ldg(b + ROW_C * NB_LANES); p.gL = __ldg(b + ROW_GL * NB_LANES); p.EL = __ldg(b + ROW_EL * NB_LANES);
+  p.dT = __ldg(b + ROW_DELTAT * NB_LANES); p.Vup = __ldg(b + ROW_VUP * NB_LANES); p.tauw = __ldg(b + ROW_TAUW * NB_LANES);
+  p.VT = __ldg(b + ROW_VT * NB_LANES); p.Iref = __ldg(b + ROW_IREF * NB_LANES); p.IDC = __ldg(b + ROW_IDC * NB_LANES);
+  p.b = __ldg(P.rare + (size_t)RARE_B * P.n_pad + i); p.Vr = __ldg(P.rare + (size_t)RARE_VR * P.n_pad + i);
+  p.Vdep = __ldg(P.rare + (size_t)RARE_VDEP * P.n_pad + i);
   return p;
 }
 
@@ -378,7 +399,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   WarpStage* const st = reinterpret_cast<WarpStage*>(smem + (size_t)warp * NEURON_WARP_SMEM);
   WarpAux* const aux = reinterpret_cast<WarpAux*>(st + NEURON_STAGES);
   unsigned long long* const bar = sh.full_bar[warp];
-  long long* const pin = P.pend + (size_t)(k & 1) * 3 * (size_t)P.n_pad;     /* filled during slot k-1 */
+  long long* const pin = P.pend + (size_t)((k + P.n_slots - 1) % P.n_slots) * 3 * (size_t)P.n_pad;     /* slot k-1 */
   const int gwarp = blockIdx.x * NEURON_WARPS + warp, nwarps = gridDim.x * NEURON_WARPS;
 
 #if HHD_L2_HINTS
@@ -390,7 +411,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
 #if HHD_L2_HINTS
       const double* src = P.nb + (size_t)blk * (NB_FIELDS * NB_LANES);
       tma_load_1d_hint(&st[s].f[0][0], src, NB_STATE * NB_LANES * 8, &bar[s], pol_keep);
-      tma_load_1d_hint(&st[s].f[NB_STATE][0], src + NB_STATE * NB_LANES, HHD_N_PARAMS * NB_LANES * 8, &bar[s], pol_stream);
+      tma_load_1d_hint(&st[s].f[NB_STATE][0], src + NB_STATE * NB_LANES, NB_PARAMS * NB_LANES * 8, &bar[s], pol_stream);
 #else
       tma_load_1d(&st[s].f[0][0], P.nb + (size_t)blk * (NB_FIELDS * NB_LANES), NB_BYTES, &bar[s]);
 #endif
@@ -418,6 +439,8 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
   }
   /* last_spike lives per GLOBAL neuron (other ranks' neurons too) and is fetched one tile ahead into a register */
   double ls_next = (blk < nblocks && blk * NB_LANES + (int)lane < P.N) ? P.last_spike[P.off + blk * NB_LANES + lane] : 0.0;
+  double vdep_next = (blk < nblocks && blk * NB_LANES + (int)lane < P.N && (t - ls_next < P.cc.window_s))
+                         ? __ldg(P.rare + (size_t)RARE_VDEP * P.n_pad + blk * NB_LANES + lane) : 0.0;
   int col_next = -1;
   if (TIMED && P.iac_table && blk < nblocks && blk * NB_LANES + (int)lane < P.N) col_next = P.iac_col[blk * NB_LANES + lane];
 
@@ -432,16 +455,18 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     NeuronPar p;
 #pragma unroll
     for (int v = 0; v < 8; ++v) x[v] = st[s].f[v][lane];
-    p.C = st[s].f[NB_STATE + HHD_P_C][lane]; p.gL = st[s].f[NB_STATE + HHD_P_GL][lane]; p.EL = st[s].f[NB_STATE + HHD_P_EL][lane];
-    p.dT = st[s].f[NB_STATE + HHD_P_DELTAT][lane]; p.Vup = st[s].f[NB_STATE + HHD_P_VUP][lane]; p.tauw = st[s].f[NB_STATE + HHD_P_TAUW][lane];
-    p.b = st[s].f[NB_STATE + HHD_P_B][lane]; p.Vr = st[s].f[NB_STATE + HHD_P_VR][lane]; p.VT = st[s].f[NB_STATE + HHD_P_VT][lane];
-    p.Iref = st[s].f[NB_STATE + HHD_P_IREF][lane]; p.Vdep = st[s].f[NB_STATE + HHD_P_VDEP][lane]; p.IDC = st[s].f[NB_STATE + HHD_P_IDC][lane];
+    p.C = st[s].f[NB_STATE + ROW_C][lane]; p.gL = st[s].f[NB_STATE + ROW_GL][lane]; p.EL = st[s].f[NB_STATE + ROW_EL][lane];
+    p.dT = st[s].f[NB_STATE + ROW_DELTAT][lane]; p.Vup = st[s].f[NB_STATE + ROW_VUP][lane]; p.tauw = st[s].f[NB_STATE + ROW_TAUW][lane];
+    p.VT = st[s].f[NB_STATE + ROW_VT][lane]; p.Iref = st[s].f[NB_STATE + ROW_IREF][lane]; p.IDC = st[s].f[NB_STATE + ROW_IDC][lane];
+    p.b = 0.0; p.Vr = 0.0;            /* fetched by the reset below */
+    p.Vdep = vdep_next;               /* fetched one tile ahead for the lanes whose block window is open */
     long long pd[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) pd[c] = aux->pend[c][lane];
     const int meta = aux->meta[lane];
     const double ls = ls_next;
     const int col = col_next;
+    const int i_cur = i;
     /* the warp holds its tile in registers: hand the stage back and request the tile after next */
     __syncwarp();
     if (lane == 0) {
@@ -454,13 +479,15 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
       const bool nlive = blk + nwarps < nblocks && in < P.N;
       ls_next = nlive ? P.last_spike[P.off + in] : 0.0;
       if (TIMED && P.iac_table) col_next = nlive ? P.iac_col[in] : -1;
+      /* V_dep multiplies the gate int(t - last_spike < 5 ms), which is closed at every stage time if it is closed at t */
+      vdep_next = (nlive && (t - ls_next < P.cc.window_s)) ? __ldg(P.rare + (size_t)RARE_VDEP * P.n_pad + in) : 0.0;
     }
 
     SubExpr S;
     bool wcross = false;
     double iac0 = 0.0, iac1 = 0.0;
 #if HHD_EXPERIMENT & 4
-    S.I_tot = x[0] + p.C + p.gL + p.EL + p.dT + p.Vup + p.tauw + p.b + p.Vr + p.VT + p.Iref + p.Vdep + p.IDC + (double)pd[0] + (double)pd[1] + (double)pd[2];   /* timing experiment: data movement only */
+    S.I_tot = x[0] + p.C + p.gL + p.EL + p.dT + p.Vup + p.tauw + p.VT + p.Iref + p.Vdep + p.IDC + (double)pd[0] + (double)pd[1] + (double)pd[2];   /* timing experiment: data movement only */
     x[1] += S.I_tot * 1e-300;
 #else
     {
@@ -492,6 +519,8 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
         }
       }
       if (meta & FLAG_SPIKED) {        /* slot `resets`: V = V_r; w += b   (codes/CortexNetwork.py:305) */
+        p.Vr = __ldg(P.rare + (size_t)RARE_VR * P.n_pad + i_cur);
+        p.b = __ldg(P.rare + (size_t)RARE_B * P.n_pad + i_cur);
         x[0] = p.Vr;
         x[1] += p.b;
         hhd_subexpr(P.cc, p, x, S, iac_prev);
@@ -529,7 +558,7 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
         int slot = -1;
         if (live) slot = md.slot ? md.slot[i] : i;
         if (slot >= 0) {
-          const double v = hhd_var_is_derived(md.var) ? hhd_var_from_subexpr(S, md.var) : hhd_var_value(P.cc, p, x, md.var, ls);
+          const double v = hhd_var_is_derived(md.var) ? hhd_var_from_subexpr(S, md.var) : hhd_var_state(x, md.var, ls);
           if (md.reduce == HHD_REDUCE_NONE) md.buf[sample * md.n_idx + slot] = v;
           else {                 /* branch-free, so that the accumulators stay in registers (an indexed update put them in local memory) */
 #pragma unroll
@@ -683,9 +712,18 @@ __global__ void __launch_bounds__(NEURON_BLOCK, (METHOD == 0 ? HHD_NEURON_MINBLO
 }
 
 
-/* buffer that collects the deliveries of slot k */
-__device__ __forceinline__ long long* pend_of_slot(const Params& P, long long k) {
-  return P.pend + (size_t)((k + 1) & 1) * 3 * (size_t)P.n_pad;
+/* buffer that collects the deliveries of slot s (Brian's `synapses` slot of step s) */
+__device__ __forceinline__ long long* pend_of_slot(const Params& P, long long s) {
+  return P.pend + (size_t)(s % P.n_slots) * 3 * (size_t)P.n_pad;
+}
+/* an amplitude that replaces an earlier one in a slot that has not been consumed yet (see spike_new_phase) */
+__device__ __forceinline__ void add_correction(const Params& P, long long* pout, int c, int tgt, double amp_new, double amp_old) {
+  if (P.accum == HHD_ACCUM_FIXED) {
+    const long long q = __double2ll_rn(amp_new * 1099511627776.0) - __double2ll_rn(amp_old * 1099511627776.0);
+    if (q) atomicAdd((unsigned long long*)&pout[pend_index(c, tgt)], (unsigned long long)q);
+  } else if (amp_new != amp_old) {
+    atomicAdd(reinterpret_cast<double*>(&pout[pend_index(c, tgt)]), amp_new - amp_old);
+  }
 }
 __device__ __forceinline__ void add_increment(const Params& P, long long* pout, int c, int tgt, double inc) {
   /* summed per (channel, target) for this step; the target's next state-update pass adds the sum to g_on and g_off */
@@ -697,120 +735,43 @@ __device__ __forceinline__ void add_increment(const Params& P, long long* pout, 
   }
 }
 
-/* All synapses of neuron j whose delay equals `age` (whole warp): bucket index -> segment of the delay-sorted row ->
- * 16-byte records; returns the number of deliveries this lane made. */
-__device__ __forceinline__ unsigned deliver_row_due(const Params& P, long long* pout, const int j, const int age, const unsigned lane) {
-  unsigned n = 0;
-  const long long r0 = P.row_ptr[j];
-  const int b = age / P.bkt_width;
-  const long long s0 = r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b];
-  const long long s1 = b + 1 < DELAY_BUCKETS ? r0 + P.row_bkt[(size_t)j * DELAY_BUCKETS + b + 1] : P.row_ptr[j + 1];
-  for (long long rb = s0; rb < s1; rb += 32) {
-    const long long r = rb + lane;
-    int d = 0x7fffffff;
-    SynHot sh;
-    if (r < s1) {
-      sh = P.hot[r];                                           /* one 16-byte load: target, delay, channel, amplitude */
-      d = sh.delay;
-    }
-    if (d == age) {
-      ++n;
-      if (sh.amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, sh.amp);
-    }
-    if (__all_sync(0xffffffffu, d > age)) break;              /* rows are sorted by delay */
-  }
-  return n;
-}
-
-/* Lane-per-spike delivery.  due_segment: the synapses of the spike in ring entry sp that are due in slot k, as a segment
- * (first record, count) of its delay-sorted row, straight from the row's per-delay offsets.  skip_respiked: leave out
- * neurons that spiked again in step k (long delays: the spike-time half delivers for them). */
-__device__ __forceinline__ void due_segment(const Params& P, const long long k, const unsigned long long sp, const bool skip_respiked,
-                                            long long& ra, unsigned& cnt) {
-  const unsigned pos = (unsigned)sp & P.cap_mask;
-  const int j = P.spk_neuron[pos];
-  const int age = (int)(k - (long long)P.spk_step[pos]);
-  if (age > P.max_delay || age < 0) return;
-  if (skip_respiked && P.spk_last[j] == (int)k) return;
-  const unsigned short* o = P.row_doff + (size_t)j * P.doff_stride + age;
-  const unsigned a0 = o[0], a1 = o[1];
-  ra = P.row_ptr[j] + a0;
-  cnt = a1 - a0;
-}
-
-/* The warp walks the concatenation of its lanes' segments 32 synapses at a time, two rounds of loads in flight (the
- * segments are very uneven, 0..~100 synapses, so one thread per segment would wait for the longest). */
-__device__ __forceinline__ void deliver_flat(const Params& P, long long* const pout, const long long ra, const unsigned cnt,
-                                             const unsigned lane, unsigned long long& delivered) {
-  unsigned incl = cnt;                                   /* inclusive prefix sum of the segment lengths */
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((int)lane >= d) incl += v;
-  }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  const unsigned excl = incl - cnt;
-  for (unsigned base = 0; base < total; base += 64) {
-    SynHot q[2];
-    bool ok[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned idx = base + 32 * u + lane;
-      unsigned owner = 0;                                /* the last lane whose exclusive prefix is <= idx (binary search over the warp) */
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const unsigned probe = owner + step;
-        const unsigned e = __shfl_sync(0xffffffffu, excl, probe & 31);
-        if (probe < 32 && e <= idx) owner = probe;
-      }
-      const long long ra_o = __shfl_sync(0xffffffffu, ra, owner);
-      const unsigned ex_o = __shfl_sync(0xffffffffu, excl, owner);
-      ok[u] = idx < total;
-      if (ok[u]) q[u] = P.hot[ra_o + (idx - ex_o)];
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (ok[u]) {
-        ++delivered;
-        if (q[u].amp != 0.0) add_increment(P, pout, q[u].chan, q[u].tgt, q[u].amp);
-      }
-  }
-}
-
 __device__ __forceinline__ void ext_events(const Params& P, const long long k, long long* const pout, const unsigned gtid, const unsigned gthreads);
 
 /*
- * Slot `synapses` of step k is ONE launch (k_synapse) whose CTAs split into two roles.
- *
- * Spike-time half (CTAs [0, stp_blocks)): pathways p0..p6 (`u`, `R`, `a_syn`, failure draw at the presynaptic spike,
- * codes/CortexNetwork.py:351-366) for the spikes of THIS step plus their zero-delay deliveries.  A task is one block of
- * STP_BLOCK consecutive synapses of one spike's row, stp_chunks tasks per spike, so a spike's row is rewritten by several
- * CTAs at once; the previous spike time it needs was saved by note_spike.
- * LONG = true (some delay >= refractory steps): the neuron may still have older spikes in flight whose deliveries must
- * use the amplitudes just rewritten.  Their steps are in the neuron's history; every thread checks ITS synapse
- * against them and delivers it if one of them is due now, while the delivery half skips every neuron that spiked in
- * this step.
+ * Slot `synapses` of step k (k_synapse).  Pathways p0..p6 (`u`, `R`, `a_syn`, failure draw at the presynaptic spike,
+ * codes/CortexNetwork.py:351-366) for the spikes of THIS step, and the delayed pathways p7a..p9b (:367-372, `delay = dtax`
+ * :463-468) as a write into the per-delay circular conductance buffer: the synapse's amplitude is added to slot k + delay
+ * right away, so there is no delivery pass at all — an event costs one read of its two records (80 B), one write of
+ * (u, R, amplitude) and one atomic, the 96 B of SURVEY 8d.  A task is one block of STP_BLOCK consecutive synapses of one
+ * spike's row, stp_chunks tasks per spike, so a spike's row is rewritten by several CTAs at once; the previous spike time it
+ * needs was saved by note_spike.
+ * Brian reads `a_syn` and `failure` when the delayed pathway EXECUTES.  That only differs from the value at push
+ * time if the neuron spikes again while an older spike of it is still in flight, which needs a delay beyond the refractory
+ * period (LONG): the new spike then replaces, in every slot that has not been consumed yet, the amplitude the older spike
+ * put there (old amplitude = the record's current one; slots s = k_older + delay >= k).  In fixed-point accumulation that
+ * is exact; in fp64 accumulation the replacement is one rounded difference.
+ * Also the SpikeGeneratorGroup events of the step (no delay).
  */
 template <bool LONG>
 __device__ __forceinline__ void spike_new_phase(const Params& P, const long long k, const unsigned bid, const unsigned nblk) {
   __shared__ int older_sh[17];
   const double t = (double)k * P.dt_s;
   const unsigned lane = threadIdx.x & 31;
-  long long* const pout = pend_of_slot(P, k);
   const unsigned long long lo_new = P.step_end[((int)k + P.W - 1) % P.W];
   const unsigned long long hi = *P.head;
   if (bid == 0 && threadIdx.x == 0) P.step_end[(int)k % P.W] = hi;
-  unsigned long long delivered = 0;
+  unsigned long long pushed = 0;
   const unsigned chunks = (unsigned)P.stp_chunks;
   const unsigned ntasks = (unsigned)(hi - lo_new) * chunks;
+  const size_t slot_stride = (size_t)3 * (size_t)P.n_pad;
   for (unsigned task = bid; task < ntasks; task += nblk) {
     const unsigned chunk = task % chunks;
     const int j = P.spk_neuron[(unsigned)(lo_new + task / chunks) & P.cap_mask];
     const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
     const double last = P.prev_spike[j];
     if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
-    /* ages of the neuron's older spikes that can still deliver (else -1): the same for every thread of the task, so they
-     * are worked out once per task into shared memory */
+    /* ages of the neuron's older spikes that can still have deliveries in flight (else -1): the same for every thread of the
+     * task, so they are worked out once per task into shared memory */
     if (LONG) {
       __syncthreads();                                         /* the previous task's readers are done */
       if (threadIdx.x < 17) {
@@ -831,54 +792,38 @@ __device__ __forceinline__ void spike_new_phase(const Params& P, const long long
       P.stp[r].u = sy.u;
       P.stp[r].R = sy.R;
       P.hot[r].amp = amp;
-      bool due = sh.delay == 0;
+      const int d = (int)sh.delay;
+      ++pushed;
+      if (amp != 0.0) add_increment(P, P.pend + (size_t)((k + d) % P.n_slots) * slot_stride, sh.chan, sh.tgt, amp);
       if (LONG) {
-        for (int q = 0; q < P.hist_depth; ++q) if ((int)sh.delay == older_sh[q]) due = true;
-      }
-      if (due) {
-        ++delivered;
-        if (amp != 0.0) add_increment(P, pout, sh.chan, sh.tgt, amp);
+        for (int q = 0; q < P.hist_depth; ++q) {
+          const int a = older_sh[q];
+          if (a > 0 && a <= d)                     /* the older spike's delivery of this synapse is still to come: slot k - a + d */
+            add_correction(P, P.pend + (size_t)((k - a + d) % P.n_slots) * slot_stride, sh.chan, sh.tgt, amp, sh.amp);
+        }
       }
     }
   }
-  delivered = (unsigned long long)warp_sum((double)delivered);
-  if (lane == 0 && delivered) atomicAdd(&P.del_slots[(bid * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], delivered);
+  pushed = (unsigned long long)warp_sum((double)pushed);
+  if (lane == 0 && pushed) atomicAdd(&P.del_slots[(bid * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], pushed);
+  ext_events(P, k, pend_of_slot(P, k), bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
 }
 
-/* Delivery half (CTAs [stp_blocks, grid)): one LANE per ACTIVE spike of an EARLIER step; with delays beyond the
- * refractory period (LONG) a neuron that spiked again in this step is skipped here — its amplitudes are being rewritten,
- * the spike-time half delivers for it.  Also the SpikeGeneratorGroup events of the step. */
-template <bool LONG>
-__device__ __forceinline__ void deliver_phase(const Params& P, const long long k, const unsigned bid, const unsigned nblk) {
+/* Deliveries that were pushed into the conductance buffer but whose slot lies beyond the last completed step `last` (one warp
+ * per spike of the last max_delay steps): hhd_get_counters reports syn_deliveries as Brian counts them, at execution. */
+__global__ void k_inflight(const __grid_constant__ Params P, const long long last, const unsigned long long lo, const unsigned long long hi,
+                           unsigned long long* out) {
   const unsigned lane = threadIdx.x & 31;
-  long long* const pout = pend_of_slot(P, k);
-  const unsigned long long lo = P.step_end[(k + 1) % P.W];             /* head at the end of step k - max_delay - 1 */
-  const unsigned long long lo_new = P.step_end[(k + P.W - 1) % P.W];   /* first spike of this step */
-  const unsigned warps = (nblk * blockDim.x) >> 5;
-  const unsigned wid = (bid * blockDim.x + threadIdx.x) >> 5;
-  unsigned long long delivered = 0;
-  if (P.row_doff) {                    /* one LANE per spike of an earlier step, spread evenly over the warps of the grid */
-    const unsigned nact = (unsigned)(lo_new - lo);
-    const unsigned spw = min(32u, (nact + warps - 1) / warps);
-    for (unsigned long long first = lo + (unsigned long long)wid * spw; first < lo_new && spw; first += (unsigned long long)warps * spw) {
-      long long ra = 0;
-      unsigned cnt = 0;
-      if (lane < spw && first + lane < lo_new) due_segment(P, k, first + lane, LONG, ra, cnt);
-      deliver_flat(P, pout, ra, cnt, lane, delivered);
-    }
-  } else
-  for (unsigned long long sp = lo + wid; sp < lo_new; sp += warps) {     /* one warp per spike of an earlier step */
+  const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long n = 0;
+  for (unsigned long long sp = lo + (((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); sp < hi; sp += warps) {
     const unsigned pos = (unsigned)sp & P.cap_mask;
     const int j = P.spk_neuron[pos];
-    const int age = (int)(k - (long long)P.spk_step[pos]);
-    if (age > (int)P.row_maxd[j]) continue;                             /* nothing of this neuron can be due any more */
-    if (LONG && P.spk_last[j] == (int)k) continue;                      /* spiked again now: the spike-time half */
-    delivered += deliver_row_due(P, pout, j, age, lane);
+    const long long ks = P.spk_step[pos];
+    for (long long r = P.row_ptr[j] + lane; r < P.row_ptr[j + 1]; r += 32) n += (ks + (long long)P.hot[r].delay > last) ? 1ull : 0ull;
   }
-  delivered = (unsigned long long)warp_sum((double)delivered);
-  if (lane == 0 && delivered) atomicAdd(&P.del_slots[wid & (CNT_SLOTS - 1)], delivered);
-
-  ext_events(P, k, pout, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
+  n = (unsigned long long)warp_sum((double)n);
+  if (lane == 0 && n) atomicAdd(out, n);
 }
 
 /* SpikeGeneratorGroup events of step k: no STP, no delay, one failure draw per (spike, synapse) (:588-594) */
@@ -991,7 +936,7 @@ __device__ __forceinline__ void recv_spikes(const Params& P, const long long k) 
 }
 
 #ifndef HHD_SYNAPSE_MINBLOCKS
-#define HHD_SYNAPSE_MINBLOCKS 8    /* 64 registers: the kernel is a chain of dependent loads, it lives on resident warps */
+#define HHD_SYNAPSE_MINBLOCKS 4    /* one wave of 4 CTAs per SM does every spike-time task of a step */
 #endif
 template <bool LONG>
 __global__ void __launch_bounds__(STP_BLOCK, HHD_SYNAPSE_MINBLOCKS) k_synapse(const __grid_constant__ Params P, const int step_offset, const int stp_blocks) {
@@ -1010,11 +955,8 @@ __global__ void __launch_bounds__(STP_BLOCK, HHD_SYNAPSE_MINBLOCKS) k_synapse(co
       __syncthreads();
     }
   }
-  if (stp_blocks <= 0) {            /* one wave of CTAs, each does its share of both halves: spike-time tasks first */
-    spike_new_phase<LONG>(P, k, blockIdx.x, gridDim.x);
-    deliver_phase<LONG>(P, k, blockIdx.x, gridDim.x);
-  } else if ((int)blockIdx.x < stp_blocks) spike_new_phase<LONG>(P, k, blockIdx.x, (unsigned)stp_blocks);
-  else deliver_phase<LONG>(P, k, blockIdx.x - (unsigned)stp_blocks, gridDim.x - (unsigned)stp_blocks);
+  (void)stp_blocks;
+  spike_new_phase<LONG>(P, k, blockIdx.x, gridDim.x);
   if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P, k, 6);
   pdl_trigger();
 }
@@ -1506,6 +1448,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   int rc = 0;
   const size_t n_pad = (size_t)((h->N + NB_LANES - 1) / NB_LANES) * NB_LANES;   /* whole 32-neuron blocks for the bulk copies */
   rc = dev_alloc(h, &P.nb, n_pad * NB_FIELDS);
+  if (!rc) { double* r = nullptr; rc = dev_alloc(h, &r, n_pad * N_RARE); P.rare = r; }
   if (!rc) rc = dev_alloc(h, &P.last_spike, h->NG, false);
   if (!rc && cfg->method == HHD_RK23_ADAPTIVE) rc = dev_alloc(h, &P.hstep, n_pad, false);
   if (!rc) rc = dev_alloc(h, &P.meta, n_pad, false);
@@ -1513,7 +1456,7 @@ extern "C" int hhd_create(const hhd_config* cfg, hhd_handle* out) {
   if (!rc) rc = dev_alloc(h, &ho, h->NG);
   P.has_out = ho;
   P.n_pad = (long long)n_pad;
-  if (!rc) rc = dev_alloc(h, &P.pend, (size_t)6 * n_pad);
+  P.pend = nullptr;            /* the conductance buffer is sized in finalize_setup, when the largest delay is known */
   if (!rc) rc = dev_alloc(h, &P.prev_spike, h->NG);
   if (!rc) rc = dev_alloc(h, &P.pass_done, 1);
   long long* rp = nullptr;
@@ -1584,15 +1527,21 @@ extern "C" int hhd_set_neurons(hhd_handle h, const double* const* params, const 
   /* blocked layout (nb_index); the padding lanes of the last block get parameters with a stable fixed point at V = w = 0
    * (no exponential current, leak towards 0, a threshold that is never reached) so that they compute harmlessly */
   const size_t n_pad = (size_t)h->P.n_pad;
-  std::vector<double> blk(n_pad * NB_FIELDS, 0.0);
+  std::vector<double> blk(n_pad * NB_FIELDS, 0.0), rare(n_pad * N_RARE, 0.0);
   const double pad_par[HHD_N_PARAMS] = {1.0, 1.0, 0.0, 1.0, 1e300, 1.0, 0.0, 0.0, 1000.0, 1e300, 0.0, 0.0};   /* C gL EL dT Vup tauw b Vr VT Iref Vdep IDC */
   for (size_t i = 0; i < n_pad; ++i) {
     const bool live = i < (size_t)h->N;
-    for (int p = 0; p < HHD_N_PARAMS; ++p) blk[nb_index(NB_STATE + p, (long long)i)] = live ? params[p][i] : pad_par[p];
+    for (int p = 0; p < HHD_N_PARAMS; ++p) {
+      const int row = param_row(p);
+      const double v = live ? params[p][i] : pad_par[p];
+      if (row >= 0) blk[nb_index(NB_STATE + row, (long long)i)] = v;
+      else rare[(size_t)(-1 - row) * n_pad + i] = v;
+    }
     blk[nb_index(0, (long long)i)] = live ? V0[i] : 0.0;
     blk[nb_index(1, (long long)i)] = live ? w0[i] : 0.0;
   }
   int rc = upload(h, h->P.nb, blk.data(), blk.size());
+  if (!rc) rc = upload(h, const_cast<double*>(h->P.rare), rare.data(), rare.size());
   if (rc) return rc;
   h->neurons_set = true;
   return HHD_OK;
@@ -1602,7 +1551,7 @@ extern "C" int hhd_set_idc(hhd_handle h, const double* idc) {
   if (!h || !idc) return fail(h, HHD_E_ARG, "null argument");
   if (!h->neurons_set) return fail(h, HHD_E_STATE, "hhd_set_neurons has not been called");
   cudaSetDevice(h->cfg.device);
-  return scatter_field(h, NB_STATE + HHD_P_IDC, idc);
+  return scatter_field(h, NB_STATE + ROW_IDC, idc);
 }
 
 extern "C" int hhd_set_timed_current(hhd_handle h, int64_t n_steps, int32_t n_cols, const double* table, const int32_t* col_of_neuron) {
@@ -2184,6 +2133,9 @@ static int finalize_setup(hhd_handle h) {
   P.W = P.max_delay + 2;
   int rc = dev_alloc(h, &P.step_end, (size_t)P.W, true);
   if (rc) return rc;
+  P.n_slots = P.max_delay + 1;
+  if ((rc = dev_alloc(h, &P.pend, (size_t)P.n_slots * 3 * (size_t)P.n_pad, true)))      /* [n_slots][3][n_pad] x 8 B, zeroed */
+    return fail(h, HHD_E_NOMEM, "conductance buffer: %d delay slots x %lld neurons x 24 B do not fit", P.n_slots, (long long)P.n_pad);
   /* Spike ring: a neuron fires at most once per refractory period, so between two host drains (seg_steps apart) plus
    * the delivery window (max_delay) at most NG * per_neuron entries are live. */
   h->seg_steps = 2000;
@@ -2247,10 +2199,8 @@ static int finalize_setup(hhd_handle h) {
   /* k_synapse: spike-time CTAs + delivery CTAs in one launch; on a partitioned network every CTA must be resident while
    * CTA 0 receives the peers' spikes (the others spin), which the occupancy of the kernel bounds */
   h->stp_grid = h->sm_count * 4;
-  h->deliver_grid = h->sm_count * 8;
-  if (h->N < 50000) h->deliver_grid = h->sm_count * 2;
-  if (getenv("HHD_DELIVER_CTAS_PER_SM") && atoi(getenv("HHD_DELIVER_CTAS_PER_SM")) > 0) h->deliver_grid = h->sm_count * atoi(getenv("HHD_DELIVER_CTAS_PER_SM"));
-  if (getenv("HHD_STP_CTAS_PER_SM") && atoi(getenv("HHD_STP_CTAS_PER_SM")) >= 0) h->stp_grid = h->sm_count * atoi(getenv("HHD_STP_CTAS_PER_SM"));
+  h->deliver_grid = 0;                 /* no delivery pass: amplitudes go into the per-delay conductance buffer at spike time */
+  if (getenv("HHD_STP_CTAS_PER_SM") && atoi(getenv("HHD_STP_CTAS_PER_SM")) > 0) h->stp_grid = h->sm_count * atoi(getenv("HHD_STP_CTAS_PER_SM"));
   if (!P.row_bkt) {                            /* no synapses: a valid (all-zero) bucket index */
     unsigned int* bkt = nullptr;
     unsigned short* rmax = nullptr;
@@ -2372,7 +2322,7 @@ static void launch_neuron(hhd_handle h, int offset) {
 static void launch_synapse(hhd_handle h, int offset) {
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof lc);
-  lc.gridDim = dim3((unsigned)(h->stp_grid + h->deliver_grid));      /* stp_grid = 0: every CTA does both halves */
+  lc.gridDim = dim3((unsigned)std::max(1, h->stp_grid));
   lc.blockDim = dim3(STP_BLOCK);
   lc.stream = h->stream;
   cudaLaunchAttribute at[1];
@@ -2618,6 +2568,24 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
     unsigned long long slots[CNT_SLOTS];
     CU(cudaMemcpy(slots, h->P.del_slots, sizeof slots, cudaMemcpyDeviceToHost));
     for (int q = 0; q < CNT_SLOTS; ++q) c[CNT_DELIVERIES] += slots[q];
+  }
+  if (!h->resident && h->nsyn) {
+    /* the graph plan counts a delivery when it is pushed into the conductance buffer; Brian (and the oracle) count it when
+     * the delayed pathway executes: take off what is still in flight after the last completed step */
+    const long long last = h->step - 1, s0 = h->step - h->P.max_delay - 1;
+    std::vector<unsigned long long> ends((size_t)h->P.W);
+    unsigned long long head = 0, *d_n = nullptr, n_fly = 0;
+    CU(cudaMemcpy(ends.data(), h->P.step_end, ends.size() * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&head, h->P.head, 8, cudaMemcpyDeviceToHost));
+    const unsigned long long lo = s0 >= 0 ? ends[(size_t)(s0 % h->P.W)] : 0ull;      /* head at the end of step s0 */
+    if (head > lo) {
+      if ((rc = dev_alloc(h, &d_n, 1, true))) return rc;
+      k_inflight<<<(unsigned)std::min<unsigned long long>(1024, (head - lo + 3) / 4), 128, 0, h->stream>>>(h->P, last, lo, head, d_n);
+      CU(cudaMemcpyAsync(&n_fly, d_n, 8, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      dev_free(h, d_n);
+    }
+    c[CNT_DELIVERIES] -= std::min(n_fly, c[CNT_DELIVERIES]);
   }
   h->cnt.syn_events = (long long)c[CNT_SYN_EVENTS]; h->cnt.syn_deliveries = (long long)c[CNT_DELIVERIES];
   h->cnt.ext_events = (long long)c[CNT_EXT]; h->cnt.spikes = (long long)c[CNT_SPIKES];

@@ -212,6 +212,16 @@ __device__ __forceinline__ double hhd_var_from_subexpr(const SubExpr& s, int var
 }
 __device__ __forceinline__ bool hhd_var_is_derived(int var) { return var >= 8 && var != 20; }
 
+/* A state variable (id < 8) or last_spike (id 20) — no subexpression is evaluated.  (hhd_var_value below is side-effect free,
+ * so when both arms of `derived ? from_subexpr : var_value` are inlined the compiler evaluates its two exponentials and the
+ * division for every neuron and selects afterwards: 130 of the 800 instructions of a monitored Euler step.) */
+__device__ __forceinline__ double hhd_var_state(const double x[8], int var, double last_spike) {
+  double v = last_spike * 1e3;               /* held in seconds, reported in ms */
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v = (var == q) ? x[q] : v;
+  return v;
+}
+
 /* Value of a monitored / derived variable (ids of include/hhd.h) from the state. */
 __device__ __forceinline__ double hhd_var_value(const ChannelConst& cc, const NeuronPar& p, const double x[8], int var,
                                                 double last_spike, const double iac = 0.0) {
