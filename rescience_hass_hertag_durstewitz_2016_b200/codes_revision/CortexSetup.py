@@ -11,7 +11,7 @@ Engine-side simplifications that keep the caller-visible behaviour:
 """
 import numpy as np
 
-from ..engine import Engine, channels_from_STypPar
+from ..engine import Engine
 from ..monitors import SpikeMonitorView, StateMonitorView
 from .. import units
 from .NetworkSetup import CHANNEL_NAMES, Network, network_setup
@@ -63,9 +63,14 @@ class Cortex:
         return Cortex(network, constant_stimuli, method, dt, transient, fluctuant_stimuli, network.seed, **kw)
 
     def __init__(self, network, constant_stimuli, method, dt, transient=0, fluctuant_stimuli=None, seed=None,
-                 last_spike0_ms=-1000.0, mg_fac=None, accum="fp64", device=0, _engine_cls=None):
-        """last_spike0_ms = -1000 and (optionally) mg_fac = 1 are the revision's values (CortexSetup.py:254,
-        BasicsSetup.py:591); mg_fac=None keeps the network's own STypPar entry (0.33 in codes/)."""
+                 last_spike0_ms=None, mg_fac=None, reference_quirks=False, accum="fp64", device=0, _engine_cls=None):
+        """The model variant comes from the network (Network.channel_constants): a network drawn by the revision's generator
+        carries the revision's BasicsSetup tree — NMDA Mg factor 1 (BasicsSetup.py:591), last_spike = -1000 ms
+        (CortexSetup.py:254), block term relaxing to V_r (BasicsSetup.py:737); a network wrapped from codes/ arrays
+        (Network.from_codes) keeps the codes/ channel table (Mg factor 0.33).  `mg_fac` / `last_spike0_ms` override either.
+        reference_quirks=True additionally loads tau_fac from the tau_rec row, as BasicsSetup.py:447 makes the reference do.
+        Not reproduced: the revision sums I_syn = I_AMPA + I_GABA + I_NMDA (:727), the engine (I_AMPA + I_NMDA) + I_GABA as
+        codes/ does — a last-bit difference in I_tot."""
         if fluctuant_stimuli is not None and isinstance(fluctuant_stimuli[-1], (int, float)):
             fluctuant_stimuli = [fluctuant_stimuli]
         self.fluctuant_stimuli = fluctuant_stimuli
@@ -89,21 +94,26 @@ class Cortex:
                          P[7],                  # the revision's block term relaxes to V_r (BasicsSetup.py:737) = V_dep of codes/
                          I_DC])
         m = {"gsl_rk2": "rk23"}.get(method, method)
+        model = network.channel_constants()
+        ch = {k: model[k] for k in ("tau_on", "tau_off", "E_rev", "gsyn", "mg_fac", "mg_slope", "mg_half")}
+        if mg_fac is not None:
+            ch["mg_fac"] = float(mg_fac)
+        if last_spike0_ms is None:
+            last_spike0_ms = model["last_spike0_ms"]
+        self.reference_quirks = bool(reference_quirks)
         s = seed if seed is not None else int.from_bytes(__import__("os").urandom(8), "little")
         self.engine = (_engine_cls or Engine)(n, self.dt_ms, method=m, accum=accum, refractory_ms=5.0, block_window_ms=5.0,
                                               last_spike0_ms=last_spike0_ms, seed=s, device=device,
                                               record_spikes=not (transient > 0))
         self.engine.set_neurons(rows, P[2], np.zeros(n))                     # V = E_L, w = 0 (CortexSetup.py:256-258)
-        ch = channels_from_STypPar(network.STypPar)
-        if mg_fac is not None:
-            ch["mg_fac"] = float(mg_fac)
         self.engine.set_channels(**ch)
         self.gsyn_amp = dict(zip(CHANNEL_NAMES, ch["gsyn"]))
         sp = network.syn_params
         if network.syn_pairs.shape[1] > 0:
             self.engine.set_synapses(network.syn_pairs[1], network.syn_pairs[0], sp["channel"].values[0].astype(np.uint8),
                                      sp["spiking"].values[0], sp["STSP_params"].values[0], sp["STSP_params"].values[1],
-                                     sp["STSP_params"].values[2], sp["spiking"].values[1], sp["delay"].values[0])
+                                     sp["STSP_params"].values[1 if (reference_quirks and model["tau_fac_from"] == "tau_rec") else 2],
+                                     sp["spiking"].values[1], sp["delay"].values[0])
         # fluctuant_stimuli = [[target, function(t_ms) -> pA, start_ms, stop_ms], ...] -> TimedArray (CortexSetup.py:193-213).
         # As in the reference every entry re-creates the array, so only the LAST entry takes effect.
         self.fluctuant_array = None

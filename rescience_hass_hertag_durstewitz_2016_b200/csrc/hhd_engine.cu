@@ -437,10 +437,21 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     issue(blk, 0);
     issue(blk + nwarps, 1);
   }
-  /* last_spike lives per GLOBAL neuron (other ranks' neurons too) and is fetched one tile ahead into a register */
-  double ls_next = (blk < nblocks && blk * NB_LANES + (int)lane < P.N) ? P.last_spike[P.off + blk * NB_LANES + lane] : 0.0;
-  double vdep_next = (blk < nblocks && blk * NB_LANES + (int)lane < P.N && (t - ls_next < P.cc.window_s))
-                         ? __ldg(P.rare + (size_t)RARE_VDEP * P.n_pad + blk * NB_LANES + lane) : 0.0;
+  /* last_spike lives per GLOBAL neuron (other ranks' neurons too) and is fetched TWO tiles ahead into a register: the
+   * tile in between is the one whose V_dep is requested — only by the lanes whose block window is open — from the
+   * last_spike that arrived during the previous tile.  (One tile ahead, the gate `t - last_spike` waited for the load it
+   * had just issued: 19 % of the kernel's stall samples, profiles/r2_notes.md.) */
+  auto ls_load = [&](int b) -> double {
+    const int in = b * NB_LANES + (int)lane;
+    return (b < nblocks && in < P.N) ? P.last_spike[P.off + in] : 0.0;
+  };
+  auto vdep_load = [&](int b, double lsb) -> double {
+    const int in = b * NB_LANES + (int)lane;
+    return (b < nblocks && in < P.N && (t - lsb < P.cc.window_s)) ? __ldg(P.rare + (size_t)RARE_VDEP * P.n_pad + in) : 0.0;
+  };
+  double ls_next = ls_load(blk);
+  double ls_next2 = ls_load(blk + nwarps);
+  double vdep_next = vdep_load(blk, ls_next);
   int col_next = -1;
   if (TIMED && P.iac_table && blk < nblocks && blk * NB_LANES + (int)lane < P.N) col_next = P.iac_col[blk * NB_LANES + lane];
 
@@ -477,10 +488,11 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     {
       const int in = (blk + nwarps) * NB_LANES + (int)lane;
       const bool nlive = blk + nwarps < nblocks && in < P.N;
-      ls_next = nlive ? P.last_spike[P.off + in] : 0.0;
       if (TIMED && P.iac_table) col_next = nlive ? P.iac_col[in] : -1;
       /* V_dep multiplies the gate int(t - last_spike < 5 ms), which is closed at every stage time if it is closed at t */
-      vdep_next = (nlive && (t - ls_next < P.cc.window_s)) ? __ldg(P.rare + (size_t)RARE_VDEP * P.n_pad + in) : 0.0;
+      ls_next = ls_next2;                               /* requested one tile ago */
+      vdep_next = vdep_load(blk + nwarps, ls_next);
+      ls_next2 = ls_load(blk + 2 * nwarps);
     }
 
     SubExpr S;

@@ -91,7 +91,7 @@ def test_stimuli():
 
 
 def test_network_setup_draws_the_codes_network():
-    net = network_setup(200, 1, None, 0, workers=4)
+    net = network_setup(200, 1, None, 0, generator="codes", workers=4)
     g = load_golden("net_n200_s0")
     assert np.array_equal(net.syn_pairs[0], g["target_arr"]) and np.array_equal(net.syn_pairs[1], g["source_arr"])
     assert np.array_equal(net.membr_params.values[1], g["NeuPar"][1])
