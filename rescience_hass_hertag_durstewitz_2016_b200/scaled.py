@@ -39,16 +39,12 @@ def shift_stimuli(stimuli_list, factor):
     return [[a, b, c, d, e, t0 * factor, t0 * factor + (t1 - t0), tg] for a, b, c, d, e, t0, t1, tg in stimuli_list]
 
 
-def instances_with_stimuli(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, group_distr, n_instances, dt,
-                           poisson=None, regular=None, seed=0):
-    """BASELINE config 3: `n_instances` independent copies of one column in ONE engine (no synapse between copies), each
-    with its OWN draw of the Poisson / regular stimuli — instance q draws with np.random.seed(seed + q) exactly as a
-    separate run of codes/Main_poisson.py / Main_regular.py would (stimuli.draw_*).  Even instances get the Poisson
-    protocol, odd ones the regular protocol when both are given.
-    -> (network dict of tile_columns, stimulus dict for Engine.add_spike_source with global source / target ids)."""
+def draw_instance_stimuli(group_distr, n_instances, n_per_instance, dt, poisson=None, regular=None, seed=0):
+    """The external spike sources of BASELINE config 3 for `n_instances` independent copies of one column: instance q draws
+    with np.random.seed(seed + q) exactly as a separate run of codes/Main_poisson.py / Main_regular.py would (stimuli.draw_*).
+    Even instances get the Poisson protocol, odd ones the regular protocol when both are given.
+    -> stimulus dict for `attach_stimuli` (global source / target ids)."""
     from . import stimuli as st
-    net = tile_columns(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_instances)
-    n1 = net["n_per_column"]
     parts, n_src = [], 0
     state = np.random.get_state()
     try:
@@ -58,14 +54,23 @@ def instances_with_stimuli(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, gro
             s = st.draw_poisson_input(poisson, group_distr, dt) if use_poisson else st.draw_regular_input(regular, group_distr, dt)
             st.check_one_spike_per_step(s["spk_src"], s["spk_t"], dt)
             parts.append(dict(spk_src=s["spk_src"] + n_src, spk_t=s["spk_t"], syn_src=s["syn_src"] + n_src,
-                              syn_tgt=s["syn_tgt"] + q * n1, mask=st.channel_mask(s["syn_type"]), gmax=s["syn_gmax"],
+                              syn_tgt=s["syn_tgt"] + q * n_per_instance, mask=st.channel_mask(s["syn_type"]), gmax=s["syn_gmax"],
                               pfail=np.full(len(s["syn_src"]), s["pfail"])))
             n_src += s["n_sources"]
     finally:
         np.random.set_state(state)
     stim = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
     stim["n_sources"] = n_src
-    return net, stim
+    return stim
+
+
+def instances_with_stimuli(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, group_distr, n_instances, dt,
+                           poisson=None, regular=None, seed=0):
+    """BASELINE config 3: `n_instances` independent copies of one column in ONE engine (no synapse between copies), each
+    with its OWN draw of the Poisson / regular stimuli (draw_instance_stimuli).
+    -> (network dict of tile_columns, stimulus dict for Engine.add_spike_source with global source / target ids)."""
+    net = tile_columns(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_instances)
+    return net, draw_instance_stimuli(group_distr, n_instances, net["n_per_column"], dt, poisson, regular, seed)
 
 
 def attach_stimuli(engine, stim):
