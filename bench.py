@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the rk4 / high-activity / one-column legs")
+    ap.add_argument("--distinct", type=int, default=-1, help="distinct column draws in the scaled network (0: one template tiled; -1: default)")
+    ap.add_argument("--cache-dir", default=os.environ.get("HHD_COLUMN_CACHE", "/tmp/hhd_columns"), help="built columns are kept here between runs on one box")
+    ap.add_argument("--no-config3", action="store_true", help="skip the 256-instance / dt 0.01 ms / 4 s leg (BASELINE config 3, ~20 s)")
+    ap.add_argument("--config3-only", action="store_true", help="run only the config-3 leg and print its JSON")
     ap.add_argument("--high-idc-scale", type=float, default=1.5, help="background-current scale of the high-activity leg")
     return ap.parse_args()
 
@@ -72,10 +76,64 @@ def one_column(template):
                 name="%s: %d neurons, %d synapses" % (name, g["NeuPar"].shape[1], g["SynPar"].shape[1]))
 
 
-def build_workload(args, rank, world, device_synapses=False):
+_DRAWS = {}
+DEFAULT_DISTINCT = 1000      # column c of the scaled network is draw (c mod DISTINCT): with 1000 every column of the default workload is its own draw
+
+
+def distinct_draws(args):
+    if args.workload == "column" or args.instances or args.template != "n1000":
+        return 0
+    d = DEFAULT_DISTINCT if args.distinct < 0 else args.distinct
+    return min(d, args.columns or 1000)
+
+
+def prebuild_columns(args, rank, world, ncol=None):
+    """The distinct column draws this rank needs, built by forked workers BEFORE CUDA / NCCL exist in this process
+    (scaled.build_distinct_columns: the reference's generator per column, seed = f(column), fast per-neuron path)."""
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import build_distinct_columns
+    D = distinct_draws(args)
+    if not D:
+        return None
+    ncol = ncol or args.columns or 1000
+    per_rank = ncol // world
+    need = sorted({p % D for p in range(rank * per_rank, (rank + 1) * per_rank)})
+    t0 = time.perf_counter()
+    workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    runs, start = [], 0                                        # contiguous runs of draw indices -> one pool call each
+    while start < len(need):
+        end = start
+        while end + 1 < len(need) and need[end + 1] == need[end] + 1:
+            end += 1
+        runs.append((need[start], need[end] + 1))
+        start = end + 1
+    draws = {}
+    for lo, hi in runs:
+        if all(c in _DRAWS for c in range(lo, hi)):            # built earlier in this process (the CPU sample reuses the GPU arm's columns)
+            draws.update({c: _DRAWS[c] for c in range(lo, hi)})
+            continue
+        for c, col in zip(range(lo, hi), build_distinct_columns(1000, lo, hi, seed=0, workers=workers, cache_dir=args.cache_dir or None)):
+            draws[c] = col
+    _DRAWS.update(draws)
+    return dict(draws=draws, D=D, seconds=time.perf_counter() - t0, workers=workers)
+
+
+def build_workload(args, rank, world, device_synapses=False, prebuilt=None):
     from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_columns
     col = one_column(args.template)
     col["I_DC"] = col["I_DC"] * args.idc_scale
+    if prebuilt is not None and args.workload != "column":
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import distinct_columns_network
+        ncol = args.columns or 1000
+        per_rank = ncol // world
+        cols = [prebuilt["draws"][p % prebuilt["D"]] for p in range(rank * per_rank, (rank + 1) * per_rank)]
+        net = distinct_columns_network(cols)
+        net["I_DC"] = net["I_DC"] * args.idc_scale
+        net.update(SynPar=np.zeros((7, 0)), source_arr=[], target_arr=[], distinct_cols=cols, col=col, STypPar=col["STypPar"],
+                   nsyn=int(sum(len(c["src"]) for c in cols)), columns_total=per_rank * world, columns_rank=per_rank, first_column=rank * per_rank,
+                   template="%d distinct draws of the reference's 1003-neuron column, NetworkSetup(1000, 1) with one numpy seed per column"
+                            % min(prebuilt["D"], ncol),
+                   column_build=dict(seconds=prebuilt["seconds"], workers=prebuilt["workers"], columns_built=len(prebuilt["draws"])))
+        return net
     if args.workload == "column":
         ncol = 1
     else:
@@ -98,6 +156,14 @@ def build_workload(args, rank, world, device_synapses=False):
 def make_engine(cls, net, args, seed, host=False, **kw):
     from rescience_hass_hertag_durstewitz_2016_b200.engine import load_codes_network
     n = net["NeuPar"].shape[1]
+    if host and "distinct_cols" in net:
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import distinct_synapses_device
+        e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
+        load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+        syn = distinct_synapses_device(net["distinct_cols"], 0, net["columns_total"], "cpu", inter_column=args.workload == "multicolumn", seed=1)
+        net["nsyn"] = int(syn[0].numel())
+        e.set_synapses(*[t.numpy() for t in syn])
+        return e
     if host and "col" in net:
         # CPU arm: the same generators, tensors on the host
         from rescience_hass_hertag_durstewitz_2016_b200.scaled import multicolumn_synapses_device, tile_synapses_device
@@ -116,6 +182,16 @@ def make_engine(cls, net, args, seed, host=False, **kw):
         kw = dict(kw, plan=args.plan, instance_size=net["n_per_column"] if (args.instances or args.workload == "column") else 0)
     e = cls(n, args.dt, method=args.method, accum=args.accum, seed=seed, **kw)
     load_codes_network(e, net["NeuPar"], net["V0"], net["STypPar"], net["SynPar"], net["source_arr"], net["target_arr"], net["I_DC"])
+    if "distinct_cols" in net:
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import distinct_synapses_device
+        dev = "cuda:%d" % kw.get("device", 0)
+        if kw.get("n_ranks", 1) > 1:                          # every neuron with a synapse somewhere in the ring
+            e.set_has_outgoing(np.ones(kw["n_global"], dtype=np.uint8))
+        syn = distinct_synapses_device(net["distinct_cols"], net["first_column"], net["columns_total"], dev,
+                                       inter_column=args.workload == "multicolumn", seed=1)
+        net["nsyn"] = int(syn[0].numel())
+        e.set_synapses_dev(*syn, syn_id_base=kw.get("rank", 0) * (1 << 31))
+        return e
     if "col" in net:
         from rescience_hass_hertag_durstewitz_2016_b200.scaled import tile_synapses_device
         col = net["col"]
@@ -211,7 +287,8 @@ class CpuSample:
         if args.workload != "column":
             a2.columns = min(args.columns or 1000, CPU_SAMPLE_COLUMNS)
         self.args = a2
-        net = build_workload(a2, 0, 1, device_synapses=args.workload != "column")
+        net = build_workload(a2, 0, 1, device_synapses=args.workload != "column",
+                             prebuilt=prebuild_columns(a2, 0, 1, ncol=a2.columns) if args.workload != "column" else None)
         t0 = time.perf_counter()
         self.e = make_engine(OracleEngine, net, a2, seed=1, record_spikes=False, host=True)
         self.n = net["NeuPar"].shape[1]
@@ -275,8 +352,24 @@ def brian2_probe():
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    net = build_workload(args, 0, 1 if args.workload == "column" else world, device_synapses=True)   # config only
-    net["nsyn"] = int(net["nsyn"] * (1.0766 if args.workload == "multicolumn" else 1.0))              # + inter-column synapses (measured ratio)
+    w = 1 if args.workload == "column" else world
+    if distinct_draws(args):
+        # the whole workload's columns are built here too (and left in the column cache for the GPU arm): the synapse count of the
+        # config is the real one; the timed sample below is a ring of the first CPU_SAMPLE_COLUMNS of them
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import inter_column_count
+        pre = prebuild_columns(args, 0, 1)
+        net = build_workload(args, 0, 1, device_synapses=True, prebuilt=pre)
+        net["total_synapses"] = net["nsyn"] + (inter_column_count(net["groups"], net["columns_total"]) if args.workload == "multicolumn" else 0)
+        net["total_neurons"] = net["NeuPar"].shape[1]
+        net["NeuPar"] = net["NeuPar"][:, :net["NeuPar"].shape[1] // w]                  # per rank, as the GPU arm sees it (the l2 note)
+        for k in [c for c in _DRAWS if c >= CPU_SAMPLE_COLUMNS]:
+            del _DRAWS[k]
+        net.pop("distinct_cols")
+        net["distinct_cols"] = True
+        pre = None
+    else:
+        net = build_workload(args, 0, w, device_synapses=True)   # config only
+        net["nsyn"] = int(net["nsyn"] * (1.0766 if args.workload == "multicolumn" else 1.0))              # + inter-column synapses (measured ratio)
     cs, probes = best_cpu_sample(args)
     # one bench step = one bounded sample; K steps + W warm-ups must end within a few minutes
     budget = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
@@ -300,11 +393,13 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(args, net, world):
     n = net["NeuPar"].shape[1]
-    name = {"columns": "%d-column PFC network (%s tiled, block-diagonal)" % (net["columns_total"], net["template"]),
-            "multicolumn": "ring of %d PFC columns (%s tiled) with inter-column synapses drawn by the reference's rules" % (net["columns_total"], net["template"]),
+    how = "%s" if "distinct_cols" in net else "%s tiled"
+    name = {"columns": ("%d-column PFC network (" + how + ", block-diagonal)") % (net["columns_total"], net["template"]),
+            "multicolumn": ("ring of %d PFC columns (" + how + ") with inter-column synapses drawn by the reference's rules") % (net["columns_total"], net["template"]),
             "column": "one PFC column (%s)" % net["template"]}[args.workload]
     return dict(workload=name,
-                neurons=n * (world if args.workload != "column" else 1), synapses=net["nsyn"] * (world if args.workload != "column" else 1),
+                neurons=net.get("total_neurons", n * (world if args.workload != "column" else 1)),
+                synapses=net.get("total_synapses", net["nsyn"] * (world if args.workload != "column" else 1)),
                 method=args.method, dt_ms=args.dt, time_steps_per_step=args.window, accumulate=args.accum,
                 monitors="spikes + summed I_tot (LFP) every time step", background="250/200 pA constant current",
                 l2="state+parameters %.0f MB per GPU vs 126 MB L2" % (n * BYTES_PER_NEURON_UPDATE / 1e6),
@@ -364,6 +459,50 @@ def column_leg(args, method, device, cpu=True):
     return out
 
 
+def config3_leg(args, device, n_instances=256, dt=0.01, duration_ms=4000.0, method="rk4"):
+    """BASELINE config 3 as stated: 256 independent instances of the 1003-neuron column in ONE engine on one GPU, dt = 0.01 ms,
+    4000 ms (codes/Main_poisson.py:29-30), even instances with the Poisson protocol (100 sources x 30 Hz x 100 ms, 2 nS, pCon 0.1
+    onto PC_L23 at 1000 ms and PC_L5 at 2500 ms, :145-150), odd ones with the regular protocol (250 / 500 spikes in 5 ms, 0.1 nS,
+    codes/Main_regular.py:165-172); each instance draws its own stimulus with its own numpy seed and has its own synapse indices
+    (release failures).  Timed: the whole 400 000-step run, device time, after building; replicas only — no exchange."""
+    import copy
+    from oracle_binding import golden_groups, load_golden
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import POISSON_STIMULI, REGULAR_STIMULI, attach_stimuli, draw_instance_stimuli
+    a2 = copy.copy(args)
+    a2.workload, a2.method, a2.plan, a2.columns, a2.instances, a2.dt = "columns", method, "auto", n_instances, True, dt
+    net = build_workload(a2, 0, 1, device_synapses=True)
+    n, n1 = net["NeuPar"].shape[1], net["n_per_column"]
+    g = load_golden("net_n1000_s0_full")
+    groups = [[list(map(int, s)) for s in grp] for grp in golden_groups(g)]
+    t0 = time.perf_counter()
+    stim = draw_instance_stimuli(groups, n_instances, n1, dt, poisson=POISSON_STIMULI, regular=REGULAR_STIMULI, seed=0)
+    eng = make_engine(Engine, net, a2, seed=1, device=device)
+    attach_stimuli(eng, stim)
+    setup_s = time.perf_counter() - t0
+    steps = int(round(duration_ms / dt))
+    c0 = eng.counters()
+    t0 = time.perf_counter()
+    eng.run(steps)
+    i, sp = eng.spikes()                                      # the 256 spike monitors, read back once at the end
+    wall = time.perf_counter() - t0
+    c1 = eng.counters()
+    eng.close()
+    dev_s = (c1["run_ms_device"] - c0["run_ms_device"]) * 1e-3
+    inst = np.asarray(i) // n1
+    t_ms = np.asarray(sp) * dt
+    in_stim = ((t_ms >= 1000) & (t_ms < 1100)) | ((t_ms >= 2500) & (t_ms < 2600))
+    return dict(workload="BASELINE config 3: %d independent instances of %s, dt %.2f ms, %.0f ms, Poisson (even) / regular (odd) stimuli at 1000 and 2500 ms"
+                         % (n_instances, net["template"], dt, duration_ms), method=method, neurons=n, synapses=int(net["nsyn"]), time_steps=steps,
+                external_sources=int(stim["n_sources"]), external_spikes=int(len(stim["spk_t"])), external_synapses=int(len(stim["syn_src"])),
+                us_per_time_step=dev_s / steps * 1e6, neuron_updates_per_s=n * steps / dev_s, syn_events_per_s=(c1["syn_events"] - c0["syn_events"]) / dev_s,
+                ext_events=int(c1["ext_events"] - c0["ext_events"]), realtime_factor_per_instance=duration_ms * 1e-3 / dev_s,
+                instance_seconds_per_wall_second=n_instances * duration_ms * 1e-3 / dev_s, mean_rate_hz=len(i) / n / (duration_ms * 1e-3),
+                rate_hz_inside_stimulus_windows=float(in_stim.sum()) / n / 0.2, rate_hz_outside=float((~in_stim).sum()) / n / (duration_ms * 1e-3 - 0.2),
+                spikes_per_instance_min_max=[int(np.bincount(inst, minlength=n_instances).min()), int(np.bincount(inst, minlength=n_instances).max())],
+                e2e_wall_s=wall, setup_s=setup_s)
+
+
 def numpy_oracle_us_per_step(net, a2, steps=300):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from numpy_oracle import NumpyOracle
@@ -418,18 +557,22 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    import torch
-    import torch.distributed as dist
-    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
     import __graft_entry__ as ge
     if rank == 0:
         ge.build()
+    prebuilt = None if args.config3_only else prebuild_columns(args, rank, world)
+    import torch
+    import torch.distributed as dist
+    from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     torch.cuda.set_device(local_rank)
 
-    net = build_workload(args, rank, world, device_synapses=True)
+    if args.config3_only:
+        print(json.dumps(config3_leg(args, local_rank)), flush=True)
+        return
+    net = build_workload(args, rank, world, device_synapses=True, prebuilt=prebuilt)
     n = net["NeuPar"].shape[1]
     t_setup = time.perf_counter()
     if world > 1:
@@ -501,16 +644,17 @@ def main():
     prof = eng.profile_kernels(min(S, 200))
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(c1["syn_events"] - c0["syn_events"]), float(c1["spikes"] - c0["spikes"]),
-                      float(c1["kernel_launches"] - c0["kernel_launches"]), float(n)], dtype=torch.float64, device="cuda")
+                      float(c1["kernel_launches"] - c0["kernel_launches"]), float(n), float(net["nsyn"])], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_ms = mx[0].item(), mx[1].item()
-        syn_ev, spikes, launches, n_total = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item()
+        syn_ev, spikes, launches, n_total, nsyn_total = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item(), sm[6].item()
     else:
-        dev_ms, e2e_ms, syn_ev, spikes, launches, n_total = [x.item() for x in t]
+        dev_ms, e2e_ms, syn_ev, spikes, launches, n_total, nsyn_total = [x.item() for x in t]
+    net["total_neurons"], net["total_synapses"] = int(n_total), int(nsyn_total)
     if rank != 0:
         return
     updates = n_total * S * args.steps
@@ -564,7 +708,7 @@ def main():
                                  note="(240 B x neurons + 96 B x synaptic events) per rank / time per time step"),
         e2e=dict(value=e2e_value, unit="neuron-updates/s", h2d_bytes_per_step=int(n * 8), d2h_bytes_per_step=int(d2h / args.steps),
                  ms_per_step=e2e_ms / args.steps),
-        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, wall_s_device_leg=wall_dev)
+        gpu_launches=int(launches), clocks=clocks, setup_s=setup_s, wall_s_device_leg=wall_dev, column_build=net.get("column_build"))
     eng.close()
     if world == 1 and not args.no_extras and args.workload != "column":
         # the rest of BASELINE.json's metric on the same box, same process: the reference's default integrator at 1M neurons, a
@@ -578,6 +722,8 @@ def main():
             leg["frac_of_hbm_roofline_whole_step"] = b / (leg["us_per_time_step"] * 1e-6) / 1e9 / peak
             leg["delivery_gbs_algorithmic"] = BYTES_PER_SYN_EVENT * leg["syn_events_per_time_step"] / (leg["us_per_launch"]["k_synapse"] * 1e-6) / 1e9
         extra["column_1k"] = {m: column_leg(args, m, local_rank, cpu=not args.no_cpu_baseline) for m in ("euler", "rk4")}
+        if not args.no_config3:
+            extra["config3_256_instances"] = config3_leg(args, local_rank)
         out.update(extra)
     if not args.no_cpu_baseline and world == 1:
         cs, probes = best_cpu_sample(args)

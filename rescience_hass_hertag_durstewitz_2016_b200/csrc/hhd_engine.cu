@@ -164,13 +164,16 @@ struct Params {
   int n_ranks, xchg_cap;
   int* xchg_send;              /* [1 + xchg_cap] */
   int* xchg_recv;              /* [n_ranks][1 + xchg_cap] */
-  /* peer-memory exchange (push_spikes / recv_spikes): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] ints followed by
-   * MAX_RANKS arrival flags, mapped into this process (CUDA IPC over NVLink); peer_buf[rank] is the own one; NULL = the
-   * NCCL all-gather is used instead */
+  /* peer-memory exchange (k_neuron / push_spikes / recv_spikes): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] 64-bit
+   * words, mapped into this process (CUDA IPC over NVLink).  Every word validates itself: (payload << 32) | tag, tag = step + 1 —
+   * word 0 of a rank's slot carries its spike count, words 1.. one neuron id each — so the sender needs no fence and no separate
+   * flag, and the receiver polls the word it is about to use (the "LL" idea of NCCL).  peer_buf[rank] is the own buffer; NULL =
+   * the NCCL all-gather is used instead */
   int rank;
-  int* peer_buf[MAX_RANKS];
+  unsigned long long* peer_buf[MAX_RANKS];
   unsigned int* xchg_dead;     /* set when a peer did not arrive within the time limit: later steps do not wait again */
-  unsigned long long* xchg_done;/* k + 1 once CTA 0 of k_synapse has appended every rank's spikes of step k */
+  unsigned long long* xchg_done;/* [0]: k + 1 once CTA 0 of k_synapse has appended the other ranks' spikes of step k; [2 + (k & 1)]: the ring
+                                 * head after k_neuron(k) appended this rank's own spikes (written by its last CTA, push_spikes) */
   /* cluster-resident plan: the network is n_inst independent instances of inst_size neurons, one thread-block cluster each */
   int inst_size, n_inst, res_cap, res_cluster;
   unsigned int* res_store;     /* [n_inst][2 + W + 2*res_cap] head, pad, end[W], neuron[cap], step[cap]: the instance's spike list between launches */
@@ -327,6 +330,7 @@ __device__ __forceinline__ void dbg_stamp(const Params& P, const long long k, co
 }
 
 __device__ __forceinline__ void push_spikes(const Params& P, const long long k);
+__device__ __forceinline__ void send_spike(const Params& P, const long long k, const int pos, const int id);
 
 /* What the appender of a spike (k_neuron on a single rank, recv_spikes / k_append after the exchange) records besides the
  * ring entry: the neuron's previous spike time for the STP update that follows (p0..p6 read it, possibly from many CTAs),
@@ -614,22 +618,24 @@ __device__ __forceinline__ void neuron_phase(const Params& P, const long long k,
     /* ---- warp-ballot spike compaction: one atomic per warp that has spikes ----------------------------------- */
     const unsigned bal = __ballot_sync(0xffffffffu, spiked);
     if (bal) {
-      if (P.n_ranks > 1) {          /* partitioned network: the step's local spikes go to the exchange's send list */
+      if (P.n_ranks > 1) {          /* partitioned network: the step's local spikes also go to the exchange's send list */
         int base = 0;
         if (lane == 0) base = atomicAdd(&P.xchg_send[0], __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (spiked) {
           const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          if (pos < P.xchg_cap) P.xchg_send[1 + pos] = P.off + i;
-          else atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
+          if (pos < P.xchg_cap) {
+            P.xchg_send[1 + pos] = P.off + i;                       /* the list the NCCL fallback gathers */
+            if (P.peer_buf[P.rank]) send_spike(P, k, pos, P.off + i);
+          } else atomicAdd(&P.counters[CNT_OVERFLOW], 1ull);
         }
-      } else {
+      }
+      {                             /* the ring entry and what note_spike records, from registers only */
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(P.head, (unsigned long long)__popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (spiked) {
           const unsigned pos = (unsigned)(base + __popc(bal & ((1u << lane) - 1u))) & P.cap_mask;
-          /* the ring entry and what note_spike records, from registers only */
           const int j = P.off + i;
           P.spk_neuron[pos] = j;
           P.spk_step[pos] = (int)k;
@@ -764,61 +770,74 @@ __device__ __forceinline__ void ext_events(const Params& P, const long long k, l
  * is exact; in fp64 accumulation the replacement is one rounded difference.
  * Also the SpikeGeneratorGroup events of the step (no delay).
  */
+/* one task: block `chunk` of `chunks` of the outgoing row of neuron j, which spiked in step k (whole CTA) */
 template <bool LONG>
-__device__ __forceinline__ void spike_new_phase(const Params& P, const long long k, const unsigned bid, const unsigned nblk) {
-  __shared__ int older_sh[17];
+__device__ __forceinline__ void spike_task(const Params& P, const long long k, const int j, const unsigned chunk, const unsigned chunks,
+                                           int* const older_sh, unsigned long long& pushed) {
   const double t = (double)k * P.dt_s;
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned long long lo_new = P.step_end[((int)k + P.W - 1) % P.W];
-  const unsigned long long hi = *P.head;
-  if (bid == 0 && threadIdx.x == 0) P.step_end[(int)k % P.W] = hi;
-  unsigned long long pushed = 0;
-  const unsigned chunks = (unsigned)P.stp_chunks;
-  const unsigned ntasks = (unsigned)(hi - lo_new) * chunks;
   const size_t slot_stride = (size_t)3 * (size_t)P.n_pad;
-  for (unsigned task = bid; task < ntasks; task += nblk) {
-    const unsigned chunk = task % chunks;
-    const int j = P.spk_neuron[(unsigned)(lo_new + task / chunks) & P.cap_mask];
-    const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
-    const double last = P.prev_spike[j];
-    if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
-    /* ages of the neuron's older spikes that can still have deliveries in flight (else -1): the same for every thread of the
-     * task, so they are worked out once per task into shared memory */
-    if (LONG) {
-      __syncthreads();                                         /* the previous task's readers are done */
-      if (threadIdx.x < 17) {
-        int a = -1;
-        if ((int)threadIdx.x < P.hist_depth) {
-          const int age = (int)(k - (long long)P.spk_hist[(size_t)j * P.hist_depth + threadIdx.x]);
-          if (age > 0 && age <= (int)P.row_maxd[j]) a = age;
-        }
-        older_sh[threadIdx.x] = a;
+  /* everything the task needs of neuron j is requested in one go (row bounds, previous spike time, spike history, longest
+   * delay): one global round trip instead of two before the synapse records can be requested */
+  const long long r0 = P.row_ptr[j], r1 = P.row_ptr[j + 1];
+  const double last = P.prev_spike[j];
+  int hist_k = 0, maxd = 0;
+  if (LONG && (int)threadIdx.x < P.hist_depth) {
+    hist_k = P.spk_hist[(size_t)j * P.hist_depth + threadIdx.x];
+    maxd = (int)P.row_maxd[j];
+  }
+  if (chunk == 0 && threadIdx.x == 0 && r1 > r0) atomicAdd(&P.counters[CNT_SYN_EVENTS], (unsigned long long)(r1 - r0));
+  /* ages of the neuron's older spikes that can still have deliveries in flight (else -1): the same for every thread of the
+   * task, so they are worked out once per task into shared memory */
+  if (LONG) {
+    __syncthreads();                                         /* the previous task's readers are done */
+    if (threadIdx.x < 17) {
+      int a = -1;
+      if ((int)threadIdx.x < P.hist_depth) {
+        const int age = (int)(k - (long long)hist_k);
+        if (age > 0 && age <= maxd) a = age;
       }
-      __syncthreads();
+      older_sh[threadIdx.x] = a;
     }
-    for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x) {
-      const SynHot sh = P.hot[r];
-      SynStp sy = P.stp[r];
-      const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t, last,
-                                        P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)k);
-      P.stp[r].u = sy.u;
-      P.stp[r].R = sy.R;
-      P.hot[r].amp = amp;
-      const int d = (int)sh.delay;
-      ++pushed;
-      if (amp != 0.0) add_increment(P, P.pend + (size_t)((k + d) % P.n_slots) * slot_stride, sh.chan, sh.tgt, amp);
-      if (LONG) {
-        for (int q = 0; q < P.hist_depth; ++q) {
-          const int a = older_sh[q];
-          if (a > 0 && a <= d)                     /* the older spike's delivery of this synapse is still to come: slot k - a + d */
-            add_correction(P, P.pend + (size_t)((k - a + d) % P.n_slots) * slot_stride, sh.chan, sh.tgt, amp, sh.amp);
-        }
+    __syncthreads();
+  }
+  for (long long r = r0 + (long long)chunk * blockDim.x + threadIdx.x; r < r1; r += (long long)chunks * blockDim.x) {
+    const SynHot sh = P.hot[r];
+    SynStp sy = P.stp[r];
+    const double amp = hhd_stp_update(sy.u, sy.R, sy.U, sy.tau_rec, sy.tau_fac, sy.gmax, P.cc.gsyn[sh.chan], sy.pfail, t, last,
+                                      P.seed, (unsigned long long)(P.syn_id_base + (long long)sy.orig), (unsigned long long)k);
+    P.stp[r].u = sy.u;
+    P.stp[r].R = sy.R;
+    P.hot[r].amp = amp;
+    const int d = (int)sh.delay;
+    ++pushed;
+    if (amp != 0.0) add_increment(P, P.pend + (size_t)((k + d) % P.n_slots) * slot_stride, sh.chan, sh.tgt, amp);
+    if (LONG) {
+      for (int q = 0; q < P.hist_depth; ++q) {
+        const int a = older_sh[q];
+        if (a > 0 && a <= d)                     /* the older spike's delivery of this synapse is still to come: slot k - a + d */
+          add_correction(P, P.pend + (size_t)((k - a + d) % P.n_slots) * slot_stride, sh.chan, sh.tgt, amp, sh.amp);
       }
     }
   }
+}
+
+__device__ __forceinline__ void count_pushed(const Params& P, unsigned long long pushed, const unsigned bid) {
   pushed = (unsigned long long)warp_sum((double)pushed);
-  if (lane == 0 && pushed) atomicAdd(&P.del_slots[(bid * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], pushed);
-  ext_events(P, k, pend_of_slot(P, k), bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
+  if ((threadIdx.x & 31) == 0 && pushed) atomicAdd(&P.del_slots[(bid * 4 + (threadIdx.x >> 5)) & (CNT_SLOTS - 1)], pushed);
+}
+
+/* the spikes at ring positions [lo_new, hi): stp_chunks tasks each, dealt out to the CTAs */
+template <bool LONG>
+__device__ __forceinline__ void spike_new_phase(const Params& P, const long long k, const unsigned long long lo_new, const unsigned long long hi,
+                                                const unsigned bid, const unsigned nblk, const bool with_ext) {
+  __shared__ int older_sh[17];
+  unsigned long long pushed = 0;
+  const unsigned chunks = (unsigned)P.stp_chunks;
+  const unsigned ntasks = (unsigned)(hi - lo_new) * chunks;
+  for (unsigned task = bid; task < ntasks; task += nblk)
+    spike_task<LONG>(P, k, P.spk_neuron[(unsigned)(lo_new + task / chunks) & P.cap_mask], task % chunks, chunks, older_sh, pushed);
+  count_pushed(P, pushed, bid);
+  if (with_ext) ext_events(P, k, pend_of_slot(P, k), bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
 }
 
 /* Deliveries that were pushed into the conductance buffer but whose slot lies beyond the last completed step `last` (one warp
@@ -857,94 +876,126 @@ __device__ __forceinline__ void ext_events(const Params& P, const long long k, l
 /* ================================================================================================================== *
  * Spike exchange of a partitioned network over peer memory (CUDA IPC over NVLink), split over the two launches of a step
  * so that it costs no launch of its own:
- *   push_spikes   the CTA of k_neuron that finishes LAST writes this rank's (count, ids...) list of step k into slot
- *                 [k & 1][rank] of EVERY rank's receive buffer — one warp per peer —, fences at system scope and raises
- *                 its flag (k + 1) on every rank;
- *   recv_spikes   CTA 0 of k_synapse waits until every rank's flag in its own buffer has reached k + 1, appends all lists
- *                 to the spike ring in rank order (note_spike for local and remote neurons) and releases the other CTAs
- *                 of the launch, which spin on a device flag meanwhile.
+ *   send_spike    a lane of k_neuron whose neuron spikes stores (id, step tag) as ONE 64-bit word into its position of this
+ *                 rank's list in EVERY peer's receive buffer — straight from the tile loop, no staging, no fence;
+ *   push_spikes   the CTA of k_neuron that finishes LAST stores (count, step tag) into word 0 of that list on every peer;
+ *   remote_spike_phase   every CTA of k_synapse first does its share of the LOCAL spikes' work (k_neuron put those into the
+ *                 ring itself), then reads the other ranks' count words (tag = this step) and takes remote spike q = its index,
+ *                 index + grid, ... whole: polls the id word (usually long there), files the spike in the ring behind the local
+ *                 ones, note_spike, the row's spike-time work.  No CTA waits for another CTA.
  * Two parities suffice: a rank can only write step k + 2 after it has consumed everybody's step k + 1, which a peer only
- * sends after it has consumed step k.  A peer that does not arrive within 20 s (it died) is reported through CNT_TIMEOUT
- * instead of hanging the device.  If the buffers cannot be mapped the engine falls back to ncclAllGather + k_append.
- * HHD_DEBUG_TIMES: %globaltimer stamps per step — 0 k_neuron's first CTA starts, 1 its last CTA is done, 2 push done,
- * 3 k_synapse's CTA 0 starts, 4 all flags seen, 5 append done, 6 CTA 0 of k_synapse done.
+ * sends after it has consumed step k; a stale word carries the tag of step k - 2 and never validates.  A peer that does not
+ * arrive within 20 s (it died) is reported through CNT_TIMEOUT instead of hanging the device.  If the buffers cannot be
+ * mapped the engine falls back to ncclAllGather + k_append.
+ * HHD_DEBUG_TIMES: %globaltimer stamps per step — 0 k_neuron's first CTA starts, 1 its last CTA is done, 2 counts sent,
+ * 3 k_synapse's CTA 0 starts, 4 its share of the local spikes done and all counts seen, 5 its share of the remote spikes done, 6 CTA 0 of k_synapse done (tools/step_stamps.py).
  * ================================================================================================================== */
-/* whole CTA (the last one of k_neuron to finish) */
+__device__ __forceinline__ void st_peer(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_peer(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+/* spin until the word carries this step's tag; false if the peer never delivers (20 s: it died) */
+__device__ __forceinline__ bool wait_peer_word(const Params& P, const unsigned long long* p, const unsigned tag, unsigned long long& v) {
+  v = ld_peer(p);
+  if ((unsigned)v == tag) return true;
+  if (*(volatile unsigned int*)P.xchg_dead) return false;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    v = ld_peer(p);
+    if ((unsigned)v == tag) return true;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull || *(volatile unsigned int*)P.xchg_dead) {
+      if (!atomicExch(P.xchg_dead, 1u)) atomicAdd(&P.counters[CNT_TIMEOUT], 1ull);
+      return false;
+    }
+  }
+}
+
+/* a spiking lane of k_neuron: its id straight into every peer's slot, position `pos` of this rank's list of step k */
+__device__ __forceinline__ void send_spike(const Params& P, const long long k, const int pos, const int id) {
+  const size_t slot = (size_t)1 + P.xchg_cap;
+  const unsigned long long w = ((unsigned long long)(unsigned)id << 32) | (unsigned long long)(unsigned)(k + 1);
+  for (int r = 0; r < P.n_ranks; ++r)
+    if (r != P.rank) st_peer(P.peer_buf[r] + ((size_t)(k & 1) * P.n_ranks + P.rank) * slot + 1 + pos, w);
+}
+
+/* whole CTA (the last one of k_neuron to finish): the ids are on their way already, what is left is the count */
 __device__ __forceinline__ void push_spikes(const Params& P, const long long k) {
   const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
-  const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
-  const int n_mine = min(__ldcg(P.xchg_send), P.xchg_cap);
-  const int lane = tid & 31, warp = tid >> 5, n_warps = (int)blockDim.x >> 5;
+  const size_t slot = (size_t)1 + P.xchg_cap;
   if (tid == 0) dbg_stamp(P, k, 1);
-  for (int r = warp; r < P.n_ranks; r += n_warps) {
-    int* dst = P.peer_buf[r] + ((size_t)par * P.n_ranks + me) * slot;
-    for (int q = lane; q < n_mine; q += 32) dst[1 + q] = __ldcg(P.xchg_send + 1 + q);
-    if (lane == 0) dst[0] = n_mine;
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) *(volatile int*)(P.peer_buf[r] + flags_off + me) = (int)(k + 1);
+  if (tid < P.n_ranks && tid != me) {
+    const int n_mine = min(__ldcg(P.xchg_send), P.xchg_cap);
+    st_peer(P.peer_buf[tid] + ((size_t)par * P.n_ranks + me) * slot, ((unsigned long long)(unsigned)n_mine << 32) | (unsigned long long)(unsigned)(k + 1));
   }
   __syncthreads();
   if (tid == 0) {
     P.xchg_send[0] = 0;
+    P.xchg_done[2 + par] = *P.head;          /* every CTA of this pass has appended (pass_done): the rank's own spikes end here */
     dbg_stamp(P, k, 2);
   }
 }
 
-/* CTA 0 of k_synapse */
-__device__ __forceinline__ void recv_spikes(const Params& P, const long long k) {
+/* The other ranks' spikes of step k (every CTA of k_synapse): CTA q mod nblk takes remote spike q WHOLE — it polls the id word,
+ * files the spike in the ring behind the local ones, does note_spike and then the spike-time work of the row, which holds local
+ * targets only and is short or empty.  No CTA waits for another one: every CTA reads the ranks' count words itself. */
+template <bool LONG>
+__device__ __forceinline__ void remote_spike_phase(const Params& P, const long long k, const unsigned long long hi_local, const unsigned bid,
+                                                   const unsigned nblk) {
+  __shared__ int older_sh[17];
+  __shared__ int count_sh[MAX_RANKS], base_sh[MAX_RANKS + 1], j_sh;
   const int par = (int)(k & 1), me = P.rank, tid = threadIdx.x;
-  const size_t slot = (size_t)1 + P.xchg_cap, flags_off = (size_t)2 * P.n_ranks * slot;
-  __shared__ unsigned long long base_sh[MAX_RANKS + 1];
-  if (tid == 0) dbg_stamp(P, k, 3);
+  const size_t slot = (size_t)1 + P.xchg_cap;
+  const unsigned tag = (unsigned)(k + 1);
+  const unsigned long long* recv = P.peer_buf[me] + (size_t)par * P.n_ranks * slot;
   if (tid < P.n_ranks) {
-    volatile int* mine = P.peer_buf[me] + flags_off + tid;
-    if (!*(volatile unsigned int*)P.xchg_dead) {
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (*mine < (int)(k + 1)) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) {
-          *P.xchg_dead = 1u;
-          atomicAdd(&P.counters[CNT_TIMEOUT], 1ull);
-          break;
-        }
-      }
-    }
-    __threadfence_system();
+    unsigned long long hdr = 0;
+    count_sh[tid] = (tid != me && wait_peer_word(P, recv + (size_t)tid * slot, tag, hdr)) ? min((int)(hdr >> 32), P.xchg_cap) : 0;
   }
   __syncthreads();
-  const int* recv = P.peer_buf[me] + (size_t)par * P.n_ranks * slot;
   if (tid == 0) {
-    dbg_stamp(P, k, 4);
-    unsigned long long b = *P.head;
-    for (int r = 0; r < P.n_ranks; ++r) {
-      base_sh[r] = b;
-      b += (unsigned long long)min(max(__ldcg(recv + (size_t)r * slot), 0), P.xchg_cap);
-    }
+    if (bid == 0) dbg_stamp(P, k, 4);
+    int b = 0;
+    for (int r = 0; r < P.n_ranks; ++r) { base_sh[r] = b; b += count_sh[r]; }
     base_sh[P.n_ranks] = b;
   }
   __syncthreads();
-  for (int r = 0; r < P.n_ranks; ++r) {
-    const int* src = recv + (size_t)r * slot;
-    const int n = (int)(base_sh[r + 1] - base_sh[r]);
-    for (int q = tid; q < n; q += blockDim.x) {
-      const unsigned pos = (unsigned)(base_sh[r] + q) & P.cap_mask;
-      const int j = __ldcg(src + 1 + q);             /* written by another GPU: not through this SM's L1 */
-      P.spk_neuron[pos] = j;
-      P.spk_step[pos] = (int)k;
-      note_spike(P, j, (int)k, (double)k * P.dt_s);
+  const int total = base_sh[P.n_ranks];
+  unsigned long long pushed = 0;
+  /* remote spike q goes to CTA nblk - 1 - q: the local spikes' tasks were dealt out from CTA 0 upwards, so with the usual
+   * handful of spikes per step the two kinds of work land on different CTAs and run side by side */
+  for (int q = (int)(nblk - 1u - bid); q < total; q += (int)nblk) {
+    if (tid == 0) {
+      int r = 0;
+      while (r + 1 < P.n_ranks && q >= base_sh[r + 1]) ++r;
+      unsigned long long w = 0;
+      int j = -1;
+      if (wait_peer_word(P, recv + (size_t)r * slot + 1 + (q - base_sh[r]), tag, w)) {
+        j = (int)(w >> 32);
+        const unsigned pos = (unsigned)(hi_local + (unsigned long long)q) & P.cap_mask;
+        P.spk_neuron[pos] = j;
+        P.spk_step[pos] = (int)k;
+        note_spike(P, j, (int)k, (double)k * P.dt_s);
+      }
+      j_sh = j;
     }
+    __syncthreads();
+    const int j = j_sh;
+    if (j >= 0) spike_task<LONG>(P, k, j, 0u, 1u, older_sh, pushed);
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid == 0) {
-    *P.head = base_sh[P.n_ranks];
-    __threadfence();
-    const unsigned long long v = (unsigned long long)(k + 1);
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.xchg_done), "l"(v) : "memory");
+  count_pushed(P, pushed, bid);
+  if (bid == 0 && tid == 0) {
+    const unsigned long long hi = hi_local + (unsigned long long)total;
+    *P.head = hi;
+    P.step_end[(int)k % P.W] = hi;
     dbg_stamp(P, k, 5);
   }
-  __syncthreads();
 }
 
 #ifndef HHD_SYNAPSE_MINBLOCKS
@@ -954,21 +1005,21 @@ template <bool LONG>
 __global__ void __launch_bounds__(STP_BLOCK, HHD_SYNAPSE_MINBLOCKS) k_synapse(const __grid_constant__ Params P, const int step_offset, const int stp_blocks) {
   pdl_wait();
   const long long k = *P.base_step + step_offset;
-  if (P.n_ranks > 1 && P.peer_buf[P.rank]) {
-    if (blockIdx.x == 0) {
-      recv_spikes(P, k);
-    } else {
-      if (threadIdx.x == 0) {
-        unsigned long long seen;
-        do {
-          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.xchg_done) : "memory");
-        } while (seen < (unsigned long long)(k + 1) && !*(volatile unsigned int*)P.xchg_dead);
-      }
-      __syncthreads();
-    }
-  }
   (void)stp_blocks;
-  spike_new_phase<LONG>(P, k, blockIdx.x, gridDim.x);
+  const unsigned long long lo = P.step_end[((int)k + P.W - 1) % P.W];
+  if (P.n_ranks > 1 && P.peer_buf[P.rank]) {
+    /* Partitioned network, exchange over peer memory.  k_neuron put this rank's own spikes into the ring already: every CTA
+     * does its share of their spike-time work first (by then the other ranks' words have usually landed), then its share of
+     * the remote spikes. */
+    const unsigned long long hi_local = __ldcg(P.xchg_done + 2 + (int)(k & 1));
+    if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P, k, 3);
+    spike_new_phase<LONG>(P, k, lo, hi_local, blockIdx.x, gridDim.x, true);
+    remote_spike_phase<LONG>(P, k, hi_local, blockIdx.x, gridDim.x);
+  } else {
+    const unsigned long long hi = *P.head;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.step_end[(int)k % P.W] = hi;
+    spike_new_phase<LONG>(P, k, lo, hi, blockIdx.x, gridDim.x, true);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P, k, 6);
   pdl_trigger();
 }
@@ -1246,8 +1297,8 @@ __global__ void __launch_bounds__(RES_BLOCK, 1) k_resident(const __grid_constant
   }
 }
 
-/* After the all-gather: append every rank's spikes of this step to the ring (same order on every rank) and clear the
- * send counter for the next step.  One CTA. */
+/* After the all-gather (NCCL fallback of the exchange): append the OTHER ranks' spikes of this step to the ring — k_neuron
+ * appended this rank's own — and clear the send counter for the next step.  One CTA. */
 __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P, const int step_offset) {
   const long long k = *P.base_step + step_offset;
   __shared__ unsigned long long base_sh[17];
@@ -1255,12 +1306,13 @@ __global__ void __launch_bounds__(256) k_append(const __grid_constant__ Params P
     unsigned long long b = *P.head;
     for (int r = 0; r < P.n_ranks; ++r) {
       base_sh[r] = b;
-      b += (unsigned long long)min(P.xchg_recv[(size_t)r * (1 + P.xchg_cap)], P.xchg_cap);
+      if (r != P.rank) b += (unsigned long long)min(P.xchg_recv[(size_t)r * (1 + P.xchg_cap)], P.xchg_cap);
     }
     base_sh[P.n_ranks] = b;
   }
   __syncthreads();
   for (int r = 0; r < P.n_ranks; ++r) {
+    if (r == P.rank) continue;
     const int* src = P.xchg_recv + (size_t)r * (1 + P.xchg_cap);
     const int n = min(src[0], P.xchg_cap);
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
@@ -2085,9 +2137,9 @@ static int setup_p2p(hhd_handle h) {
   const int R = P.n_ranks;
   h->p2p = false;
   if (!h->comm_ready || R > MAX_RANKS) return 0;
-  const size_t n_int = (size_t)2 * R * (1 + (size_t)P.xchg_cap) + MAX_RANKS;
-  int* buf = nullptr;
-  int rc = dev_alloc(h, &buf, n_int, true);
+  const size_t n_words = (size_t)2 * R * (1 + (size_t)P.xchg_cap);
+  unsigned long long* buf = nullptr;
+  int rc = dev_alloc(h, &buf, n_words, true);          /* zeroed: tag 0 is never a step's tag (step + 1 >= 1) */
   if (rc) return rc;
   int ok = getenv("HHD_NO_P2P") ? 0 : 1;
   cudaIpcMemHandle_t mine;
@@ -2112,7 +2164,7 @@ static int setup_p2p(hhd_handle h) {
     void* ptr = nullptr;
     if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
     h->peer_mapped[r] = ptr;
-    P.peer_buf[r] = (int*)ptr;
+    P.peer_buf[r] = (unsigned long long*)ptr;
   }
   CU(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, h->stream));
   if (ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream) != ncclSuccess) return fail(h, HHD_E_COMM, "all-reduce failed");
@@ -2180,7 +2232,7 @@ static int finalize_setup(hhd_handle h) {
     rc = dev_alloc(h, &P.xchg_send, (size_t)1 + P.xchg_cap, true);
     if (!rc) rc = dev_alloc(h, &P.xchg_recv, (size_t)P.n_ranks * (1 + P.xchg_cap), true);
     if (!rc) rc = dev_alloc(h, &P.xchg_dead, 1, true);
-    if (!rc) rc = dev_alloc(h, &P.xchg_done, 1, true);
+    if (!rc) rc = dev_alloc(h, &P.xchg_done, 4, true);     /* [0] flag, [2 + parity] ring head after the rank's own spikes */
     if (rc) return rc;
     P.rank = h->cfg.rank;
 #ifdef HHD_WITH_NCCL
@@ -2549,19 +2601,16 @@ extern "C" int hhd_run(hhd_handle h, int64_t n_steps) {
   CU(cudaEventRecord(h->ev1, h->stream));
   if (pending >= 0 && (rc = segment_collect(h, pending))) return rc;
   CU(cudaStreamSynchronize(h->stream));
-  if (h->P.dbg_times) {
-    std::vector<unsigned long long> tt((size_t)16 * 4096);
+  if (h->P.dbg_times) {          /* HHD_DEBUG_TIMES=path: the last 4096 steps' stamps of this rank -> path.rank<r> (tools/step_stamps.py) */
+    std::vector<unsigned long long> tt((size_t)8 * 4096);
     CU(cudaMemcpy(tt.data(), h->P.dbg_times, tt.size() * 8, cudaMemcpyDeviceToHost));
-    if (FILE* f = fopen(getenv("HHD_DEBUG_TIMES"), "w")) {
-      for (int half = 0; half < 2; ++half)
-        for (int b = 0; b < h->neuron_grid && b < 4096; ++b) {
-          const size_t o = ((size_t)half * 4096 + b) * 4;
-          fprintf(f, "%d %llu %llu %llu %llu\n", b, tt[o], tt[o + 1], tt[o + 2], tt[o + 3]);
-        }
-      fclose(f);
-    }
-    if (FILE* f = fopen((std::string(getenv("HHD_DEBUG_TIMES")) + ".passes").c_str(), "w")) {
-      for (int q = 0; q < 4096; ++q) fprintf(f, "%d %llu %llu\n", q, tt[8 * 4096 + 2 * q], tt[8 * 4096 + 2 * q + 1]);
+    const std::string path = std::string(getenv("HHD_DEBUG_TIMES")) + ".rank" + std::to_string(h->cfg.rank);
+    if (FILE* f = fopen(path.c_str(), "w")) {
+      for (int q = 0; q < 4096; ++q) {
+        fprintf(f, "%d", q);
+        for (int j = 0; j < 8; ++j) fprintf(f, " %llu", tt[(size_t)q * 8 + j]);
+        fprintf(f, "\n");
+      }
       fclose(f);
     }
   }

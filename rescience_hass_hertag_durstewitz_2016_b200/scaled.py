@@ -39,26 +39,44 @@ def shift_stimuli(stimuli_list, factor):
     return [[a, b, c, d, e, t0 * factor, t0 * factor + (t1 - t0), tg] for a, b, c, d, e, t0, t1, tg in stimuli_list]
 
 
-def draw_instance_stimuli(group_distr, n_instances, n_per_instance, dt, poisson=None, regular=None, seed=0):
-    """The external spike sources of BASELINE config 3 for `n_instances` independent copies of one column: instance q draws
-    with np.random.seed(seed + q) exactly as a separate run of codes/Main_poisson.py / Main_regular.py would (stimuli.draw_*).
-    Even instances get the Poisson protocol, odd ones the regular protocol when both are given.
-    -> stimulus dict for `attach_stimuli` (global source / target ids)."""
+def _one_instance_stimulus(job):
+    q, seed, use_poisson, protocol, group_distr, dt = job
     from . import stimuli as st
-    parts, n_src = [], 0
     state = np.random.get_state()
     try:
-        for q in range(int(n_instances)):
-            np.random.seed(int(seed) + q)
-            use_poisson = poisson is not None and (regular is None or q % 2 == 0)
-            s = st.draw_poisson_input(poisson, group_distr, dt) if use_poisson else st.draw_regular_input(regular, group_distr, dt)
-            st.check_one_spike_per_step(s["spk_src"], s["spk_t"], dt)
-            parts.append(dict(spk_src=s["spk_src"] + n_src, spk_t=s["spk_t"], syn_src=s["syn_src"] + n_src,
-                              syn_tgt=s["syn_tgt"] + q * n_per_instance, mask=st.channel_mask(s["syn_type"]), gmax=s["syn_gmax"],
-                              pfail=np.full(len(s["syn_src"]), s["pfail"])))
-            n_src += s["n_sources"]
+        np.random.seed(int(seed) + q)
+        s = st.draw_poisson_input(protocol, group_distr, dt) if use_poisson else st.draw_regular_input(protocol, group_distr, dt)
     finally:
         np.random.set_state(state)
+    st.check_one_spike_per_step(s["spk_src"], s["spk_t"], dt)
+    return s
+
+
+def draw_instance_stimuli(group_distr, n_instances, n_per_instance, dt, poisson=None, regular=None, seed=0, workers=None):
+    """The external spike sources of BASELINE config 3 for `n_instances` independent copies of one column: instance q draws
+    with np.random.seed(seed + q) exactly as a separate run of codes/Main_poisson.py / Main_regular.py would (stimuli.draw_*).
+    Even instances get the Poisson protocol, odd ones the regular protocol when both are given.  Instances are independent,
+    so they are drawn by a pool of worker processes (256 instances: 30 s of numpy shuffles on one core).
+    -> stimulus dict for `attach_stimuli` (global source / target ids)."""
+    from . import stimuli as st
+    jobs = []
+    for q in range(int(n_instances)):
+        use_poisson = poisson is not None and (regular is None or q % 2 == 0)
+        jobs.append((q, seed, use_poisson, poisson if use_poisson else regular, group_distr, dt))
+    import os
+    workers = min(len(jobs), workers or min(32, os.cpu_count() or 1))
+    if workers > 1 and len(jobs) >= 8:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            drawn = pool.map(_one_instance_stimulus, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+    else:
+        drawn = [_one_instance_stimulus(j) for j in jobs]
+    parts, n_src = [], 0
+    for q, s in enumerate(drawn):
+        parts.append(dict(spk_src=s["spk_src"] + n_src, spk_t=s["spk_t"], syn_src=s["syn_src"] + n_src,
+                          syn_tgt=s["syn_tgt"] + q * n_per_instance, mask=st.channel_mask(s["syn_type"]), gmax=s["syn_gmax"],
+                          pfail=np.full(len(s["syn_src"]), s["pfail"])))
+        n_src += s["n_sources"]
     stim = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
     stim["n_sources"] = n_src
     return stim
@@ -137,6 +155,25 @@ def inter_column_synapses_device(groups, n_per_column, n_columns, device, col_lo
     return tuple(torch.cat([p[q] for p in parts]).contiguous() for q in range(9))
 
 
+def inter_column_count(groups, n_columns):
+    """How many synapses inter_column_synapses_device draws for a whole ring of `n_columns` columns (counts are fixed by the
+    rules: round(pCon exp(-d/0.909) N_target N_source) pairs per target column, rule and offset, twice for AMPA + NMDA)."""
+    import contextlib
+    import io
+    from .codes.ParamSetup import ParamSetup
+    with contextlib.redirect_stdout(io.StringIO()):
+        ps = ParamSetup(1000, 1, ([1, 1, 1, 1], [1, 1, 1, 1], np.ones((10, 14))))
+    SynTypes, pCon, get_SynType = ps[8], ps[14], ps[27]
+    rules, coef, offsets = ps[31]
+    per_column = 0
+    for q, (ia, ja) in enumerate(rules):
+        for off in offsets[q]:
+            n = int(round(pCon[ia, ja] * float(np.exp(-abs(off) / coef[q][0])) * len(groups[ia]) * len(groups[ja]), 0))
+            if n and n_columns > abs(off):
+                per_column += n * len(get_SynType[int(SynTypes[ia, ja])])
+    return per_column * int(n_columns)
+
+
 def _inter_column_chunk(torch, ps, groups, n_per_column, n_columns, device, col_lo, col_hi, seed):
     SynTypes, Syngmax, Syndelay, STSP_prob, STSP_types, pCon, S_sig = ps[8], ps[9], ps[10], ps[12], ps[13], ps[14], ps[16]
     STSP_setup, get_SynType, get_STSP_prob, get_STSP_types = ps[26], ps[27], ps[28], ps[29]
@@ -198,6 +235,114 @@ def multicolumn_synapses_device(SynPar, source_arr, target_arr, groups, n_column
     col_hi = n_columns if col_hi is None else col_hi
     intra = tile_synapses_device(SynPar, source_arr, target_arr, col_hi - col_lo, n_per_column, device, id_offset=col_lo * n_per_column)
     inter = inter_column_synapses_device(groups, n_per_column, n_columns, device, col_lo, col_hi, seed)
+    if inter is None:
+        return intra
+    return tuple(torch.cat([a, b]).contiguous() for a, b in zip(intra, inter))
+
+
+# ---- many DISTINCT columns ---------------------------------------------------------------------------------
+# Column c of a scaled network = what the reference's NetworkSetup(N1, 1 stripe) draws after np.random.seed(column_seed(seed, c)):
+# its own membrane parameters, I_ref, re-typed interneurons, connectivity (common-neighbour rule for PC -> PC included) and
+# synaptic parameters — the bit-exact port of codes/NetworkSetup.py with the vectorised per-neuron path (codes/fast_neuron.py:
+# I_ref within 1e-4 pA of the reference's value, everything else bit-identical, tests/test_fast_neuron.py).  Columns are
+# independent draws, so they are built by a pool of worker processes and do not depend on how the network is partitioned; the
+# inter-column synapses come from inter_column_synapses_device (the cell groups that project across columns — PC_L23, PC_L5,
+# IN_CC_L5, IN_F_L5 — are not re-typed, so their template-local ids are the same in every column).
+def column_seed(seed, c):
+    return (int(seed) * 1000003 + int(c)) % (2 ** 32)
+
+
+def _build_column(job):
+    seed, c, n1, cache_dir = job
+    import contextlib
+    import io
+    import os
+    import warnings
+    path = os.path.join(cache_dir, "col_n%d_s%d_c%05d.npz" % (n1, seed, c)) if cache_dir else None
+    if path and os.path.exists(path):
+        try:
+            with np.load(path) as d:
+                return {k: d[k] for k in d.files}
+        except Exception:
+            pass
+    from .codes.NetworkSetup import sparse_network
+    state = np.random.get_state()
+    try:
+        np.random.seed(column_seed(seed, c))
+        with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            NeuPar, V0, _STyp, SynPar, (tgt, src), gd = sparse_network(n1, 1, ([1, 1, 1, 1], [1, 1, 1, 1], np.ones((10, 14))), True, fast=True)
+    finally:
+        np.random.set_state(state)
+    col = dict(NeuPar=NeuPar, V0=V0, src=np.asarray(src, dtype=np.int32), tgt=np.asarray(tgt, dtype=np.int32),
+               chan=(SynPar[0].astype(np.int64) - 1).astype(np.uint8), gmax=SynPar[4], U=SynPar[1], tau_rec=SynPar[2], tau_fac=SynPar[3],
+               pfail=SynPar[6], delay=SynPar[5],
+               group_sizes=np.asarray([len(gd[g][0]) for g in range(len(gd))], dtype=np.int32),
+               group_flat=np.asarray([x for g in range(len(gd)) for x in gd[g][0]], dtype=np.int32))
+    if path:
+        try:
+            os.makedirs(cache_dir, exist_ok=True)
+            tmp = path + ".%d.tmp.npz" % os.getpid()
+            np.savez(tmp, **col)
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return col
+
+
+def build_distinct_columns(n1, col_lo, col_hi, seed=0, workers=None, cache_dir=None):
+    """Columns [col_lo, col_hi) of the scaled network as host arrays (list of dicts, see _build_column).  Call BEFORE CUDA /
+    NCCL are initialised in this process: the pool forks.  A 1003-neuron column takes 1.5 s of one core."""
+    import os
+    jobs = [(seed, c, n1, cache_dir) for c in range(col_lo, col_hi)]
+    workers = min(len(jobs), workers or int(os.environ.get("HHD_SETUP_WORKERS", "0")) or (os.cpu_count() or 1))
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            return pool.map(_build_column, jobs, chunksize=1)
+    return [_build_column(j) for j in jobs]
+
+
+def distinct_columns_network(columns, i_exc=250.0, i_inh=200.0):
+    """Neuron-side arrays of a list of built columns: dict(NeuPar[12, N], V0[2, N], I_DC[N], n_per_column, groups) with the
+    background current of codes/Main.py:109-112 (PC groups 0 and 7: i_exc, interneurons: i_inh)."""
+    n1 = columns[0]["NeuPar"].shape[1]
+    idc = []
+    for col in columns:
+        sizes, flat = col["group_sizes"], col["group_flat"]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        cur = np.full(n1, i_inh)
+        for g in (0, 7):
+            cur[flat[offs[g]:offs[g + 1]]] = i_exc
+        idc.append(cur)
+    c0 = columns[0]
+    offs = np.concatenate([[0], np.cumsum(c0["group_sizes"])])
+    groups = [c0["group_flat"][offs[g]:offs[g + 1]].astype(np.int64) for g in range(len(c0["group_sizes"]))]
+    return dict(NeuPar=np.concatenate([c["NeuPar"] for c in columns], axis=1), V0=np.concatenate([c["V0"] for c in columns], axis=1),
+                I_DC=np.concatenate(idc), n_per_column=n1, groups=groups)
+
+
+def distinct_synapses_device(columns, col_lo, n_columns, device, inter_column=True, seed=0):
+    """The synapse arrays of the built columns [col_lo, col_lo + len(columns)) as torch tensors on `device` for
+    Engine.set_synapses_dev: every column's own intra-column synapses (global ids) + the drawn inter-column synapses of the ring."""
+    import torch
+    n1 = columns[0]["NeuPar"].shape[1]
+    keys = ("src", "tgt", "chan", "gmax", "U", "tau_rec", "tau_fac", "pfail", "delay")
+    parts = {k: [] for k in keys}
+    for q, col in enumerate(columns):
+        off = (col_lo + q) * n1
+        for k in keys:
+            t = torch.as_tensor(np.ascontiguousarray(col[k]), device=device)
+            if k in ("src", "tgt"):
+                t = (t + off).to(torch.int32)
+            parts[k].append(t)
+    intra = tuple(torch.cat(parts[k]).contiguous() for k in keys)
+    parts = None
+    if not inter_column:
+        return intra
+    offs = np.concatenate([[0], np.cumsum(columns[0]["group_sizes"])])
+    groups = [columns[0]["group_flat"][offs[g]:offs[g + 1]].astype(np.int64) for g in range(len(columns[0]["group_sizes"]))]
+    inter = inter_column_synapses_device(groups, n1, n_columns, device, col_lo, col_lo + len(columns), seed)
     if inter is None:
         return intra
     return tuple(torch.cat([a, b]).contiguous() for a, b in zip(intra, inter))

@@ -15,9 +15,9 @@ def _targets(targets, group_distr, inp_group, n_inp, tgt_all, src_all):
     for group, stripe, pcon in targets:
         target_group = np.asarray(group_distr[group][stripe]).astype(np.int64)
         n_target = int(round(pcon * len(target_group), 0))
-        order = list(range(len(target_group) * n_inp))
+        order = np.arange(len(target_group) * n_inp)      # the reference shuffles a list: same draws, same permutation
         np.random.shuffle(order)
-        pick = np.asarray(order[:n_target], dtype=np.int64)
+        pick = order[:n_target].astype(np.int64)
         tgt_all.extend(target_group[pick // n_inp])
         src_all.extend(inp_group[pick % n_inp])
 
