@@ -21,8 +21,11 @@ def _constants():
 
 
 def get_gmax(PSP, i, j):
-    """Peak conductance from PSP amplitude is already folded into the stored Syngmax table (codes/ParamSetup.py:604-612)."""
-    raise NotImplementedError("Syngmax is stored post-conversion in data/pfc_constants.npz")
+    """Peak conductance (nS) that gives a PSP of `PSP` mV on a cell of target group i from a source of group j: one factor per
+    target group for pyramidal sources (j = 0, 7) and one for interneuron sources (codes/ParamSetup.py:603-613).  The stored
+    Syngmax table already contains this conversion."""
+    c = _constants()
+    return PSP * float(c["gmax_per_psp_from_PC" if j in (0, 7) else "gmax_per_psp_from_IN"][i])
 
 
 def ParamSetup(N1, Nstripes, scales):

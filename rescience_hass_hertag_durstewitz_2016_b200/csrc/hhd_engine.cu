@@ -9,25 +9,26 @@
  *                 threshold + refractoriness, append spikes to the spike ring with one atomic per warp (ballot
  *                 compaction) and note what the synaptic kernel needs of a spike.  Replaces NeuronGroup's
  *                 stateupdater/thresholder/resetter + StateMonitor + SpikeMonitor (codes/CortexNetwork.py:304-311, 487, 510).
- *                 On a partitioned network its last CTA also pushes the step's spike list into every peer's memory.
- *   k_synapse     slot `synapses`, CTAs in two roles.  Spike-time half: pathways p0..p6 for the NEW spikes in 128-synapse
- *                 tasks — failure draw (Philox keyed by synapse and step), Tsodyks–Markram update of (u, R), the amplitude
- *                 the delayed pathways will add (codes/CortexNetwork.py:360-366), zero-delay deliveries; with delays
- *                 beyond the refractory period also the deliveries that are due from older spikes of the same neuron
- *                 (SURVEY F5).  Delivery half: one LANE per ACTIVE older spike — the row is sorted by delay and has
- *                 per-delay offsets, so the lane gets exactly the synapses whose delay equals the spike's age; the warp
- *                 walks its lanes' segments together and adds their CURRENT amplitudes to the targets' pending increments
- *                 (pathways p7a..p9b with `delay = dtax`, :367-372,463-468).  The spike history itself is the delay queue:
- *                 no per-event queue memory, bounded by one spike per neuron per refractory period, and values are read
- *                 at delivery time exactly as Brian's SpikeQueue does.  SpikeGeneratorGroup events (:570-622) as well.
- *                 On a partitioned network its CTA 0 first receives the peers' spike lists (recv_spikes).
+ *                 On a partitioned network every spiking lane also stores (id, step tag) as one self-validating 64-bit
+ *                 word into every peer's receive buffer, and the last CTA sends the count the same way (send_spike,
+ *                 push_spikes).
+ *   k_synapse     slot `synapses`.  Pathways p0..p6 for the spikes of THIS step in 128-synapse tasks — failure draw (Philox
+ *                 keyed by synapse and step), Tsodyks–Markram update of (u, R), the amplitude (codes/CortexNetwork.py:360-366)
+ *                 — and the delayed pathways p7a..p9b (:367-372, `delay = dtax` :463-468) as ONE atomic add of that amplitude
+ *                 into slot (k + delay) of a circular per-delay conductance buffer, which k_neuron(k + delay + 1) drains:
+ *                 no delivery pass, no per-event queue memory.  Brian reads the amplitude when the delayed pathway executes
+ *                 (SURVEY F5); that only differs if the neuron spikes again while an older spike is in flight (delays beyond
+ *                 the refractory period, template LONG), and then the new spike replaces the amplitude in every slot not yet
+ *                 consumed (add_correction).  SpikeGeneratorGroup events (:570-622) as well.  On a partitioned network every
+ *                 CTA then takes its share of the OTHER ranks' spikes whole (remote_spike_phase).
  * The other plan on the same arithmetic: k_resident (one thread-block cluster per small independent network, whole
  * segments in one launch).  Round 1's cooperative whole-run kernel and one-launch-per-step schedule were measured slower
  * (profiles/r1_notes.md) and are gone.
  *
- * Data layout in HBM: per block of 32 neurons 20 rows of 32 doubles (8 state + 12 parameters, 5120 B contiguous), blocked
- * pending increments and meta words, last_spike per global neuron (≈ 240 B read+written per neuron-update, the roofline
- * figure of SURVEY §8d); per synapse (CSR by presynaptic neuron, sorted by delay) a 16-byte record {target, delay,
+ * Data layout in HBM: per block of 32 neurons 17 rows of 32 doubles (8 state + the 9 parameters every step needs, 4352 B
+ * contiguous = one bulk copy; b, V_r and V_dep are only read by the neurons that spike / sit in their 5 ms window), the
+ * step's slot of the conductance buffer (3 words) and the meta word, last_spike per global neuron — 216 B moved per
+ * neuron-update against the 240 B roofline figure of SURVEY §8d; per synapse (CSR by presynaptic neuron, sorted by delay) a 16-byte record {target, delay,
  * channel, amplitude} and a 64-byte record {U, tau_rec, tau_fac, g_max, p_fail, u, R, original index}.
  */
 #include <cuda_runtime.h>

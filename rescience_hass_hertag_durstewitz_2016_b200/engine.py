@@ -100,6 +100,7 @@ class Engine:
         self.dt_ms = float(dt_ms)
         self.nsyn = 0
         self._monitors = {}
+        self._mon_active, self._mon_runs, self._spike_epoch = {}, {}, 0
         if self._fn("abi_version", C.c_int)() != ABI_VERSION:
             raise ImportError("libhhd ABI version mismatch")
         cfg = Config(
@@ -240,10 +241,20 @@ class Engine:
         self._check(self._fn("add_state_monitor")(self._h, C.c_int32(var_id), C.c_int64(n_idx), p, C.c_int32(red),
                                                    C.c_int64(capacity_steps), C.byref(mon)))
         self._monitors[mon.value] = (n_idx if red == 0 else 1)
+        self._mon_active[mon.value] = True
+        self._mon_runs[mon.value] = []
         return mon.value
 
     def set_monitor_active(self, mon_id, active):
         self._check(self._fn("set_monitor_active")(self._h, C.c_int32(mon_id), C.c_int32(1 if active else 0)))
+        self._mon_active[mon_id] = bool(active)
+        self._spike_epoch += mon_id == -1
+
+    def monitor_steps(self, mon_id):
+        """Time step of every sample the monitor holds: a monitor that was switched off and on again (the revision's
+        start/stop schedule, Brian's `monitor.active`) has gaps, so this is not first_step + arange(n)."""
+        runs = self._mon_runs.get(mon_id, [])
+        return np.concatenate([np.arange(a, a + n, dtype=np.int64) for a, n in runs]) if runs else np.zeros(0, dtype=np.int64)
 
     def set_spike_monitor_active(self, active):
         self.set_monitor_active(-1, active)
@@ -265,10 +276,22 @@ class Engine:
 
     def clear_monitor(self, mon_id):
         self._check(self._fn("clear_monitor")(self._h, C.c_int32(mon_id)))
+        if mon_id == -1:
+            self._spike_epoch += 1
+        else:
+            self._mon_runs[mon_id] = []
 
     # -- run and results -------------------------------------------------------------------------------------------
     def run(self, n_steps):
-        self._check(self._fn("run")(self._h, C.c_int64(int(n_steps))))
+        n_steps = int(n_steps)
+        k0 = self.current_step() if self._mon_runs else 0
+        self._check(self._fn("run")(self._h, C.c_int64(n_steps)))
+        for m, runs in self._mon_runs.items():               # which steps each active state monitor sampled
+            if self._mon_active.get(m) and n_steps > 0:
+                if runs and runs[-1][0] + runs[-1][1] == k0:
+                    runs[-1] = (runs[-1][0], runs[-1][1] + n_steps)
+                else:
+                    runs.append((k0, n_steps))
 
     def profile_kernels(self, n_steps):
         """Run n_steps with a CUDA event between kernels -> mean microseconds per launch: k_neuron, the exchange (only when

@@ -18,7 +18,7 @@ class SpikeMonitorView:
         self._cache_step = -1
 
     def _fetch(self):
-        step = self._e.current_step()
+        step = (self._e.current_step(), getattr(self._e, "_spike_epoch", 0))     # cleared or toggled monitors invalidate too
         if self._cache is None or self._cache_step != step:
             i, s = self._e.spikes()
             self._cache = (i.astype(np.int64) - self._off, s.astype(np.float64) * self._e.dt_ms * units.ms)
@@ -76,7 +76,10 @@ class StateMonitorView:
     @property
     def t(self):
         n, first = self._samples()
-        return (max(first, 0) + np.arange(n)) * self._e.dt_ms * units.ms
+        steps = self._e.monitor_steps(self._ids[self.variables[0]]) if hasattr(self._e, "monitor_steps") else np.zeros(0)
+        if len(steps) != n:                         # monitor capacity reached, or an engine that does not track runs
+            steps = max(first, 0) + np.arange(n)
+        return steps * self._e.dt_ms * units.ms
 
     t_ = t
 

@@ -96,3 +96,26 @@ def test_network_setup_draws_the_codes_network():
     assert np.array_equal(net.syn_pairs[0], g["target_arr"]) and np.array_equal(net.syn_pairs[1], g["source_arr"])
     assert np.array_equal(net.membr_params.values[1], g["NeuPar"][1])
     assert np.array_equal(net.refractory_current.values, g["NeuPar"][10])
+
+
+def test_monitor_times_follow_the_active_intervals_and_spike_cache_is_invalidated():
+    """A monitor switched off and on again has a gap in `.t` (advisor finding, round 1); clearing the spike monitor shows at once."""
+    from rescience_hass_hertag_durstewitz_2016_b200.monitors import SpikeMonitorView, StateMonitorView
+    from helpers import make_engine
+    g = load_golden("net_n200_s0")
+    e = make_engine("cpu", g, method="euler", seed=2)
+    sv = StateMonitorView(e, "V", [0, 5])
+    sm = SpikeMonitorView(e, 207)
+    e.run(40)
+    sv.set_active(False)
+    e.run(100)
+    sv.set_active(True)
+    e.run(20)
+    t = sv.t / units.ms
+    assert sv.V.shape == (2, 60) and len(t) == 60
+    assert np.allclose(t[:40], np.arange(40) * 0.05) and np.allclose(t[40:], (140 + np.arange(20)) * 0.05)
+    e.run(3000)
+    n = sm.num_spikes
+    assert n > 0
+    e.clear_monitor(-1)
+    assert sm.num_spikes == 0

@@ -83,3 +83,10 @@ def test_building_blocks():
     assert f_on > f_ss > 0                                        # adaptation lowers the steady-state rate
     out = ParamSetup(1000, 1, SCALES)
     assert int(out[0].sum()) == 1003 and out[14].shape == (14, 14)
+
+
+def test_get_gmax_conversion_factors():
+    """codes/ParamSetup.py:603-613: one PSP -> g_max factor per target group, pyramidal and interneuron sources apart."""
+    from rescience_hass_hertag_durstewitz_2016_b200.codes.ParamSetup import get_gmax
+    assert get_gmax(1.0, 0, 0) == 1.0569 and get_gmax(1.0, 0, 7) == 1.0569 and get_gmax(1.0, 0, 3) == 2.3859
+    assert get_gmax(0.5, 13, 0) == 0.5 * 0.6360 and get_gmax(2.0, 7, 12) == 2.0 * 3.5816

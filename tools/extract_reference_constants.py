@@ -40,6 +40,8 @@ data = dict(
     STSP_types_vals=np.asarray([list(get_STSP_types[k]) + [""] * (3 - len(get_STSP_types[k])) for k in sorted(get_STSP_types.keys())]),
     STypPar=np.asarray(STypPar), pConStripes=np.asarray(pConStripes), coefStripes=np.asarray(coefStripes),
     interStripes_flat=np.concatenate([np.asarray(x) for x in interStripes]), interStripes_len=np.asarray([len(x) for x in interStripes]),
+    # PSP amplitude -> peak conductance factors per target group (get_gmax, codes/ParamSetup.py:603-613), read off by calling it with PSP = 1
+    gmax_per_psp_from_PC=np.asarray([get_gmax(1.0, i, 0) for i in range(14)]), gmax_per_psp_from_IN=np.asarray([get_gmax(1.0, i, 1) for i in range(14)]),
 )
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rescience_hass_hertag_durstewitz_2016_b200", "data", "pfc_constants.npz")
 np.savez_compressed(path, **data)
