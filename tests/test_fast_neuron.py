@@ -41,7 +41,7 @@ def test_rates_latencies_and_adaptation_ratio_match_the_exact_path():
             assert np.abs(fast[ok] / ref[ok] - 1).max() < 1e-6
 
 
-@pytest.mark.parametrize("name,n1,stripes,seed", [("net_n200_s0", 200, 1, 0), ("net_n60x5_s1", 60, 5, 1)])
+@pytest.mark.parametrize("name,n1,stripes,seed", [("net_n200_s0", 200, 1, 0), ("net_n60x5_s1", 60, 5, 1), ("net_n40x7_s2", 40, 7, 2), ("net_n40x9_s3", 40, 9, 3)])
 def test_fast_builder_draws_the_references_network(name, n1, stripes, seed):
     """sparse_network(fast=True) = the reference's network — every membrane parameter, group membership after re-typing, every
     synapse and synaptic parameter bit-identical — except I_ref, which agrees to 1e-4 pA."""

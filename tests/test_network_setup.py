@@ -29,8 +29,10 @@ def build(n1, nstripes, seed, sparse=False, workers=4):
     return out, np.random.random()
 
 
-@pytest.mark.parametrize("name", ["net_n200_s0", "net_n60x5_s1"])
+@pytest.mark.parametrize("name", ["net_n200_s0", "net_n60x5_s1", "net_n40x7_s2", "net_n40x9_s3"])
 def test_bit_identical_to_the_reference(name):
+    """1, 5, 7 and 9 stripes: the stripe counts for which the reference's inter-stripe offsets (+-1, +-2, +-4 with wrap-around)
+    do not collide."""
     g = load_golden(name)
     (NeuPar, V0, STypPar, SynPar, SPMtx, group_distr), rng_after = build(int(g["n1"]), int(g["nstripes"]), int(g["seed"]))
     assert np.array_equal(NeuPar, g["NeuPar"])
