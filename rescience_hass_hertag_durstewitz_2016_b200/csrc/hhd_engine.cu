@@ -124,10 +124,8 @@ struct Params {
   const unsigned short* row_maxd; /* [NG] largest delay (steps) in the row */
   const unsigned int* row_bkt; /* [NG][DELAY_BUCKETS] offset inside the row of the first synapse with delay >= b*bkt_width */
   int bkt_width;
-  const unsigned short* row_doff; /* [NG][max_delay + 2] offset inside the row of the first synapse with delay >= d (one
-                                     lane per active spike reads exactly its due synapses); NULL = not built */
   unsigned long long* dbg_times;   /* HHD_DEBUG_TIMES: [4096 steps][8] %globaltimer stamps (dbg_stamp) */
-  int doff_stride, stp_chunks;     /* max_delay + 2; STP tasks per spike */
+  int stp_chunks;                  /* spike-time tasks per spike */
   long long syn_id_base;
   /* spike ring */
   int* spk_neuron;             /* global ids */
@@ -1774,21 +1772,6 @@ __global__ void k_mark_flags(int NG, int N, int off, const long long* row_ptr, c
   if (j >= off && j < off + N) meta[j - off] = (meta[j - off] & ~(FLAG_OUT | FLAG_ZERO)) | ((ho & 1) ? FLAG_OUT : 0) | ((ho & 2) ? FLAG_ZERO : 0);
 }
 
-/* row_doff[j][d] = offset inside row j of the first synapse whose delay is >= d, d = 0 .. max_delay + 1; also the longest row */
-__global__ void k_syn_doff(int NG, const long long* row_ptr, const SynHot* hot, int stride, unsigned short* row_doff, int* max_row) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= (long long)NG * stride) return;
-  const int j = (int)(q / stride), want = (int)(q % stride);
-  const long long r0 = row_ptr[j], r1 = row_ptr[j + 1];
-  long long lo = r0, hi = r1;
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if ((int)hot[mid].delay < want) lo = mid + 1; else hi = mid;
-  }
-  row_doff[q] = (unsigned short)min(lo - r0, 65535ll);
-  if (want == 0) atomicMax(max_row, (int)min(r1 - r0, (long long)INT_MAX));
-}
-
 static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, const int32_t* tgt, const uint8_t* chan,
                                const double* g_max, const double* U, const double* tau_rec, const double* tau_fac,
                                const double* p_fail, const double* delay_ms, int64_t syn_id_base) {
@@ -1853,33 +1836,10 @@ static int set_synapses_device(hhd_handle h, int64_t nsyn, const int32_t* src, c
     CU(cudaStreamSynchronize(h->stream));
     P.row_bkt = bkt;
   }
-  P.row_doff = nullptr;
   {
-    /* an STP task is one block of a spiking neuron's row: as many tasks per spike as 1.25 mean rows need.  Needed by
-     * the spike-time half of k_synapse whichever delivery index is built below. */
+    /* a spike-time task is one block of a spiking neuron's row: as many tasks per spike as 1.25 mean rows need */
     const double mean_row = (double)nsyn / std::max(1, h->NG);
     P.stp_chunks = std::max(1, (int)std::ceil(1.25 * mean_row / NEURON_BLOCK));
-  }
-  /* HHD_NO_DOFF=1 forces the 16-bucket fallback index (tests) */
-  if (!getenv("HHD_NO_DOFF") && (size_t)h->NG * (size_t)(maxd + 2) * 2 <= ((size_t)4 << 30)) {     /* per-delay offsets: lane-per-spike delivery */
-    unsigned short* doff = nullptr;
-    int* dmax_row = nullptr;
-    const int stride = maxd + 2;
-    rc = dev_alloc(h, &doff, (size_t)h->NG * stride, false);
-    if (!rc) rc = dev_alloc(h, &dmax_row, 1, true);
-    if (rc) return rc;
-    const long long nq = (long long)h->NG * stride;
-    k_syn_doff<<<(unsigned)((nq + T - 1) / T), T, 0, h->stream>>>(h->NG, P.row_ptr, P.hot, stride, doff, dmax_row);
-    int max_row = 0;
-    CU(cudaMemcpyAsync(&max_row, dmax_row, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    dev_free(h, dmax_row);
-    if (max_row < 65536) {
-      P.row_doff = doff;
-      P.doff_stride = stride;
-    } else {
-      dev_free(h, doff);
-    }
   }
   dev_free(h, keys); dev_free(h, keys2); dev_free(h, vals); dev_free(h, vals2); dev_free(h, derr); dev_free(h, dmaxd); dev_free(h, tmp);
   P.max_delay = maxd;
@@ -2275,11 +2235,6 @@ static int finalize_setup(hhd_handle h) {
     P.row_bkt = bkt;
     P.row_maxd = rmax;
     P.bkt_width = 1;
-    unsigned short* doff = nullptr;
-    rc = dev_alloc(h, &doff, (size_t)h->NG * 2, true);
-    if (rc) return rc;
-    P.row_doff = doff;
-    P.doff_stride = 2;
     P.stp_chunks = 1;
   }
   if (P.stp_chunks < 1) return fail(h, HHD_E_STATE, "internal: stp_chunks not set");
@@ -2296,7 +2251,7 @@ static int finalize_setup(hhd_handle h) {
       h->deliver_grid = std::max(1, cap - h->stp_grid);
     }
   }
-  h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : false;
+  h->pdl = getenv("HHD_PDL") ? atoi(getenv("HHD_PDL")) != 0 : true;     /* on: -1.6 % per step on 1 GPU, -3 % on 2 (profiles/r2_notes.md); HHD_PDL=0 turns it off */
   {
     const int inst = h->cfg.instance_size > 0 ? h->cfg.instance_size : h->N;
     const bool can = h->cfg.n_ranks == 1 && P.max_delay < P.refr_steps && inst <= RES_MAX_CLUSTER * RES_BLOCK && h->N % inst == 0 &&

@@ -222,13 +222,14 @@ def test_resident_plan_refuses_what_it_cannot_do():
 
 @pytest.mark.parametrize("golden,method", [("net_n200_s0", "rk4"), ("net_n60x5_s1", "rk2")])
 def test_bucket_index_fallback_bit_exact(golden, method, monkeypatch):
-    """The 16-bucket delay index (used when a row has >= 65536 synapses or the per-delay offsets would not fit) must run
-    pathways p0..p6 like the default index does (round-1 advisor finding: `stp_chunks` stayed 0 there and all recurrent
-    transmission was silently dead).  HHD_NO_DOFF=1 forces the fallback."""
+    """Round-1 advisor finding: `stp_chunks` (spike-time tasks per spike) was only set on one of two index-building paths and
+    stayed 0 on the other, so all recurrent transmission was silently dead there.  Since the per-delay conductance buffer there
+    is one path; it sets `stp_chunks` unconditionally and finalize_setup refuses to run with 0.  Kept as the regression test,
+    with programmatic dependent launch switched off (the default has it on)."""
     g = load_golden(golden)
-    monkeypatch.setenv("HHD_NO_DOFF", "1")
+    monkeypatch.setenv("HHD_PDL", "0")
     gpu = make_engine("gpu", g, plan="graph", method=method, accum="fixed", seed=11)
-    monkeypatch.delenv("HHD_NO_DOFF")
+    monkeypatch.delenv("HHD_PDL")
     cpu = make_engine("cpu", g, method=method, accum="fixed", seed=11)
     for e in (gpu, cpu):
         e.run(8000)
