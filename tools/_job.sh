@@ -1,7 +1,5 @@
-set -x
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py tests/test_gpu_analysis.py tests/test_fI_closed_form.py -m gpu -x -q ) > gpurun_out/r2g_gputests.log 2>&1
-tail -4 gpurun_out/r2g_gputests.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-( time timeout 600 python bench.py --no-config3 ) > gpurun_out/r2g_bench_default.json 2> gpurun_out/r2g_bench_default.err || tail -20 gpurun_out/r2g_bench_default.err
-python tools/benchline.py gpurun_out/r2g_bench_default.json
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533"
+HHD_DEBUG_TIMES=gpurun_out/stamps8p timeout 100 $T bench.py --gpus 8 --steps 3 --warmup 3 --window 1000 --no-cpu-baseline --no-extras --distinct 0 > gpurun_out/mg8p_ring.json 2> gpurun_out/mg8p.err || tail -5 gpurun_out/mg8p.err
+python tools/benchline.py gpurun_out/mg8p_ring.json
+python tools/step_stamps.py gpurun_out/stamps8p.rank0 gpurun_out/stamps8p.rank5
