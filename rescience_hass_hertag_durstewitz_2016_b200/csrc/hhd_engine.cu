@@ -163,7 +163,7 @@ struct Params {
   int n_ranks, xchg_cap;
   int* xchg_send;              /* [1 + xchg_cap] */
   int* xchg_recv;              /* [n_ranks][1 + xchg_cap] */
-  /* peer-memory exchange (k_neuron / push_spikes / recv_spikes): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] 64-bit
+  /* peer-memory exchange (send_spike / push_spikes / remote_spike_phase): every rank's receive buffer [2 parities][n_ranks][1 + xchg_cap] 64-bit
    * words, mapped into this process (CUDA IPC over NVLink).  Every word validates itself: (payload << 32) | tag, tag = step + 1 —
    * word 0 of a rank's slot carries its spike count, words 1.. one neuron id each — so the sender needs no fence and no separate
    * flag, and the receiver polls the word it is about to use (the "LL" idea of NCCL).  peer_buf[rank] is the own buffer; NULL =
@@ -331,7 +331,7 @@ __device__ __forceinline__ void dbg_stamp(const Params& P, const long long k, co
 __device__ __forceinline__ void push_spikes(const Params& P, const long long k);
 __device__ __forceinline__ void send_spike(const Params& P, const long long k, const int pos, const int id);
 
-/* What the appender of a spike (k_neuron on a single rank, recv_spikes / k_append after the exchange) records besides the
+/* What the appender of a spike (k_neuron for the rank's own neurons, remote_spike_phase / k_append for the other ranks') records besides the
  * ring entry: the neuron's previous spike time for the STP update that follows (p0..p6 read it, possibly from many CTAs),
  * the new one (p5: last_spike_pre = t, only neurons with outgoing synapses have that pathway), the step of its latest
  * spike, and — when delays can outlast the refractory period — its spike history.  Returns the has_out flags.
@@ -1402,7 +1402,7 @@ struct hhd_engine {
   hhd_counters cnt;
   int stp_grid = 0, deliver_grid = 0, sm_count = 0, neuron_grid = 0;
   bool mon_variant = false;         /* some state monitor is active: the k_neuron variant that samples them is launched */
-  bool p2p = false;                 /* spike exchange over mapped peer memory (k_exchange) instead of NCCL */
+  bool p2p = false;                 /* spike exchange over mapped peer memory (send_spike / remote_spike_phase) instead of NCCL */
   void* peer_mapped[MAX_RANKS] = {};/* cudaIpcOpenMemHandle results, closed in hhd_destroy */
 #ifdef HHD_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -2134,7 +2134,7 @@ static int setup_p2p(hhd_handle h) {
   CU(cudaStreamSynchronize(h->stream));
   dev_free(h, d_mine); dev_free(h, d_all); dev_free(h, d_ok);
   h->p2p = all_ok != 0;
-  if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] rank %d: spike exchange over %s\n", P.rank, h->p2p ? "peer memory (push_spikes / recv_spikes)" : "NCCL all-gather");
+  if (getenv("HHD_VERBOSE")) fprintf(stderr, "[hhd] rank %d: spike exchange over %s\n", P.rank, h->p2p ? "peer memory (send_spike / remote_spike_phase)" : "NCCL all-gather");
   if (!h->p2p) {
     for (int r = 0; r < R; ++r) {
       if (h->peer_mapped[r]) { cudaIpcCloseMemHandle(h->peer_mapped[r]); h->peer_mapped[r] = nullptr; }
@@ -2355,7 +2355,7 @@ static void launch_synapse(hhd_handle h, int offset) {
 }
 
 /* One time step: k_neuron, k_synapse.  On a partitioned network the step's spike indices travel every rank to every rank
- * in between — inside those two launches over peer memory (push_spikes / recv_spikes), or as ncclAllGather + k_append when
+ * in between — inside those two launches over peer memory (send_spike / remote_spike_phase), or as ncclAllGather + k_append when
  * the peers' buffers could not be mapped. */
 static void launch_step(hhd_handle h, int offset) {
   launch_neuron<true>(h, offset);
