@@ -98,7 +98,8 @@ def prebuild_columns(args, rank, world, ncol=None):
     per_rank = ncol // world
     need = sorted({p % D for p in range(rank * per_rank, (rank + 1) * per_rank)})
     t0 = time.perf_counter()
-    workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import usable_cpus
+    workers = max(1, usable_cpus() // max(1, world))
     runs, start = [], 0                                        # contiguous runs of draw indices -> one pool call each
     while start < len(need):
         end = start
@@ -325,7 +326,8 @@ class CpuSample:
 
 def best_cpu_sample(args):
     """All host threads if they help, else one: the probe decides, and `cores` reports the count that was used."""
-    ncpu = os.cpu_count() or 1
+    from rescience_hass_hertag_durstewitz_2016_b200.scaled import usable_cpus
+    ncpu = usable_cpus()
     one = CpuSample(args, 1)
     if ncpu == 1 or args.workload == "column":
         return one, {"1": one.probe()}
@@ -385,7 +387,7 @@ def run_reference_arm(args, rank, world):
     info["thread_probe_s_per_time_step"] = probes
     info["brian2"] = brian2_probe()
     out = dict(metric="neuron_updates_per_s", value=v, unit="neuron-updates/s", n_gpus=args.gpus, steps=args.steps,
-               warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True, scaling="weak", vs_baseline=None,
+               warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True, scaling="strong", vs_baseline=None,
                dtype="f64", data="synthetic", impl="reference", config=workload_config(args, net, world),
                cpu_baseline=info, e2e=dict(value=v, unit="neuron-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out), flush=True)

@@ -10,6 +10,15 @@ multi-column builder replaces it.
 import numpy as np
 
 
+def usable_cpus():
+    """Cores this process may run on (the affinity mask where the platform has one: a container often sees fewer than cpu_count)."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def tile_columns(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_columns, jitter_idc=0.0, seed=0):
     """-> dict(NeuPar, V0, SynPar, source_arr, target_arr, I_DC, n_per_column) for n_columns copies."""
     NeuPar = np.asarray(NeuPar, dtype=np.float64)
@@ -64,7 +73,7 @@ def draw_instance_stimuli(group_distr, n_instances, n_per_instance, dt, poisson=
         use_poisson = poisson is not None and (regular is None or q % 2 == 0)
         jobs.append((q, seed, use_poisson, poisson if use_poisson else regular, group_distr, dt))
     import os
-    workers = min(len(jobs), workers or min(32, os.cpu_count() or 1))
+    workers = min(len(jobs), workers or min(32, usable_cpus()))
     if workers > 1 and len(jobs) >= 8:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(workers) as pool:
@@ -295,7 +304,7 @@ def build_distinct_columns(n1, col_lo, col_hi, seed=0, workers=None, cache_dir=N
     NCCL are initialised in this process: the pool forks.  A 1003-neuron column takes 1.5 s of one core."""
     import os
     jobs = [(seed, c, n1, cache_dir) for c in range(col_lo, col_hi)]
-    workers = min(len(jobs), workers or int(os.environ.get("HHD_SETUP_WORKERS", "0")) or (os.cpu_count() or 1))
+    workers = min(len(jobs), workers or int(os.environ.get("HHD_SETUP_WORKERS", "0")) or usable_cpus())
     if workers > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(workers) as pool:
