@@ -248,7 +248,10 @@ def p_calc_recur(X, N_neigh, pCon, pSelfCon, slope):
 
 
 def _pairset(mask):
-    return set(map(tuple, zip(*np.where(mask))))
+    """Set of (target, source) tuples of the mask's True entries, inserted in row-major order.  Tuples of Python ints hash and
+    compare like the tuples of numpy integers the reference builds, so the set iterates in the same order — at a fifth of the cost."""
+    rows, cols = np.where(mask)
+    return set(zip(rows.tolist(), cols.tolist()))
 
 
 def SetCon_CommonNeighbour_Recur(Nsyn, Npop, pCon, pSelfCon):
