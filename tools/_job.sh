@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533"
-HHD_DEBUG_TIMES=gpurun_out/stamps8p timeout 100 $T bench.py --gpus 8 --steps 3 --warmup 3 --window 1000 --no-cpu-baseline --no-extras --distinct 0 > gpurun_out/mg8p_ring.json 2> gpurun_out/mg8p.err || tail -5 gpurun_out/mg8p.err
-python tools/benchline.py gpurun_out/mg8p_ring.json
-python tools/step_stamps.py gpurun_out/stamps8p.rank0 gpurun_out/stamps8p.rank5
+( time timeout 150 python -m pytest tests/test_gpu_revision.py tests/test_gpu_scaled.py -m gpu -x -q ) > gpurun_out/r2h_newtests.log 2>&1
+tail -15 gpurun_out/r2h_newtests.log
+timeout 120 python bench.py --steps 3 --warmup 3 --window 1000 --no-cpu-baseline --no-extras --distinct 200 > gpurun_out/r2h_bench.json 2> gpurun_out/r2h.err || tail -5 gpurun_out/r2h.err
+python tools/benchline.py gpurun_out/r2h_bench.json
