@@ -77,14 +77,21 @@ def one_column(template):
 
 
 _DRAWS = {}
+_DISTINCT_OK = [True]         # cleared when the column build fails: every leg then uses the tiled template
 DEFAULT_DISTINCT = 1000      # column c of the scaled network is draw (c mod DISTINCT): with 1000 every column of the default workload is its own draw
 
 
 def distinct_draws(args):
-    if args.workload == "column" or args.instances or args.template != "n1000":
+    if args.workload == "column" or args.instances or args.template != "n1000" or not _DISTINCT_OK[0]:
         return 0
     d = DEFAULT_DISTINCT if args.distinct < 0 else args.distinct
-    return min(d, args.columns or 1000)
+    d = min(d, args.columns or 1000)
+    if args.distinct < 0:
+        # a column takes 1.6 s of one core: keep the default build under ~150 s on hosts with few cores (16 cores build all 1000);
+        # the limit depends on the host only, so both arms and every rank count the same
+        from rescience_hass_hertag_durstewitz_2016_b200.scaled import usable_cpus
+        d = min(d, max(25, int(150 * usable_cpus() / 1.6) // 25 * 25))
+    return d
 
 
 def prebuild_columns(args, rank, world, ncol=None):
@@ -355,11 +362,17 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     w = 1 if args.workload == "column" else world
+    pre = None
     if distinct_draws(args):
+        try:
+            pre = prebuild_columns(args, 0, 1)
+        except Exception as exc:
+            _DISTINCT_OK[0] = False
+            print("bench.py: building distinct columns failed (%s: %s); falling back to the tiled template column" % (type(exc).__name__, exc), file=sys.stderr)
+    if pre is not None:
         # the whole workload's columns are built here too (and left in the column cache for the GPU arm): the synapse count of the
         # config is the real one; the timed sample below is a ring of the first CPU_SAMPLE_COLUMNS of them
         from rescience_hass_hertag_durstewitz_2016_b200.scaled import inter_column_count
-        pre = prebuild_columns(args, 0, 1)
         net = build_workload(args, 0, 1, device_synapses=True, prebuilt=pre)
         net["total_synapses"] = net["nsyn"] + (inter_column_count(net["groups"], net["columns_total"]) if args.workload == "multicolumn" else 0)
         net["total_neurons"] = net["NeuPar"].shape[1]
@@ -562,7 +575,14 @@ def main():
     import __graft_entry__ as ge
     if rank == 0:
         ge.build()
-    prebuilt = None if args.config3_only else prebuild_columns(args, rank, world)
+    prebuilt, build_error = None, None
+    if not args.config3_only:
+        try:
+            prebuilt = prebuild_columns(args, rank, world)
+        except Exception as exc:                               # no bench line is worse than a bench line on the tiled template
+            build_error = "%s: %s" % (type(exc).__name__, exc)
+            _DISTINCT_OK[0] = False
+            print("bench.py: building distinct columns failed (%s); falling back to the tiled template column" % build_error, file=sys.stderr)
     import torch
     import torch.distributed as dist
     from rescience_hass_hertag_durstewitz_2016_b200.engine import Engine
@@ -570,6 +590,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     torch.cuda.set_device(local_rank)
+    if world > 1 and distinct_draws(args):                    # every rank or none
+        ok = torch.tensor([0 if build_error else 1], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            prebuilt = None
+            _DISTINCT_OK[0] = False
 
     if args.config3_only:
         print(json.dumps(config3_leg(args, local_rank)), flush=True)
