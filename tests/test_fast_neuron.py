@@ -90,3 +90,27 @@ def test_inter_column_count_is_what_the_generator_draws():
     n1 = g["NeuPar"].shape[1]
     syn = scaled.inter_column_synapses_device(groups, n1, 40, "cpu", 0, 40, seed=1)
     assert syn[0].numel() == scaled.inter_column_count(groups, 40)
+
+
+def test_partitioned_build_is_the_same_network(tmp_path):
+    """Every rank builds only the columns it owns (and the inter-column synapses that target them); the union over the ranks is the
+    network a single rank builds — the column seeds and the chunked random stream of the inter-column draws do not depend on the
+    partition."""
+    import torch
+    ncol = 10
+    full_cols = scaled.build_distinct_columns(200, 0, ncol, seed=2, workers=2, cache_dir=str(tmp_path))
+    full = scaled.distinct_synapses_device(full_cols, 0, ncol, "cpu", inter_column=True, seed=1)
+    parts = []
+    for rank in range(2):
+        lo, hi = rank * 5, rank * 5 + 5
+        cols = scaled.build_distinct_columns(200, lo, hi, seed=2, workers=1, cache_dir=None)      # rebuilt, not read from the cache
+        assert all(np.array_equal(a["NeuPar"], b["NeuPar"]) and np.array_equal(a["gmax"], b["gmax"]) for a, b in zip(cols, full_cols[lo:hi]))
+        parts.append(scaled.distinct_synapses_device(cols, lo, ncol, "cpu", inter_column=True, seed=1))
+        n1 = cols[0]["NeuPar"].shape[1]
+        assert int(parts[-1][1].min()) >= lo * n1 and int(parts[-1][1].max()) < hi * n1               # a rank holds the synapses onto ITS neurons
+    union = [torch.cat([p[q] for p in parts]) for q in range(9)]
+    assert union[0].numel() == full[0].numel()
+    order = lambda t: np.lexsort(tuple(x.numpy() for x in (t[4], t[3], t[8], t[2], t[0], t[1])))      # by target, source, channel, delay, g_max, U
+    a, b = order(union), order(full)
+    for q in range(9):
+        assert np.array_equal(union[q].numpy()[a], full[q].numpy()[b]), q
