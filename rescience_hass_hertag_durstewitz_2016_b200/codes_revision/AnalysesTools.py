@@ -123,3 +123,66 @@ def get_LFP_SPD_from_Itotarray(Itotarray, fq, log=True, sigma=0):
     if sigma > 0:
         power = gf1d(power, sigma)
     return frequency, power
+
+
+# ---- membrane potential and LFP (host side: they work on recorded traces, not on spike lists) ----------------------------------
+def _without_spikes(Varr, V_T, spike_jump=1):
+    """A V trace with its spikes cut out (codes_revision/AnalysesTools.py:92-123): the trace is split where |V| jumps by at least
+    `spike_jump` mV from one sample to the next (the reset); every piece but the last ends at its last sample below V_T, i.e. loses
+    the upswing into the spike — or vanishes if it never is below V_T."""
+    after = np.where(np.diff(np.abs(Varr)) >= spike_jump)[0] + 1
+    pieces, start = [], 0
+    for stop in after:
+        piece = Varr[start:stop]
+        below = np.where(piece < V_T)[0]
+        pieces.append(piece[:below[-1] + 1] if len(below) else piece[:0])
+        start = stop
+    pieces.append(Varr[start:])
+    return np.concatenate(pieces)
+
+
+def get_V_stats(cortex, neuron_idcs=None, tlim=None, file=None):
+    """-> Vmean, Vstd, mean(V - V_T), and the same three with the spikes cut out, one entry per neuron (mV); `file`: the reference's
+    text report (codes_revision/AnalysesTools.py:88-172).  Needs a 'V' monitor (`set_neuron_monitors('V', 'V', ...)`)."""
+    V = np.asarray(cortex.recorded.V.V) / units.mV
+    if neuron_idcs is not None:
+        V = V[neuron_idcs]
+    else:
+        neuron_idcs = np.arange(cortex.neurons.N)
+    if tlim is not None:
+        t = np.asarray(cortex.recorded.V.t) / units.ms
+        V = V[:, (t >= tlim[0]) & (t < tlim[1])]
+    rows = [[] for _ in range(6)]
+    for i in range(V.shape[0]):
+        V_T = cortex.network.membr_params.loc[dict(param="V_T", cell_index=neuron_idcs[i])].values
+        cut = _without_spikes(V[i], V_T)
+        for row, val in zip(rows, (np.mean(V[i]), np.std(V[i]), np.mean(V[i] - V_T), np.mean(cut), np.std(cut), np.mean(cut - V_T))):
+            row.append(val)
+    if file is not None:
+        names = ("Vmean", "Vstd", "V minus V_T mean")
+        with open(file, "w") as f:
+            print("V correlations", file=f)
+            print("{} cells".format(len(neuron_idcs)), end="\n\n", file=f)
+            for title, block, suffix in (("Full V arrays", rows[:3], ""), ("V arrays after spike extraction", rows[3:], "_extracted")):
+                print(title, file=f)
+                for name, row in zip(names, block):
+                    print("{}{} --> mean: {:.2f} mV, std: {:.2f} mV".format(name, suffix, np.mean(row), np.std(row)), file=f)
+                print(file=f)
+    return tuple(rows)
+
+
+def get_LFP(cortex, invert_Itot=True, population_agroupate=None):
+    """The recorded summed current as the LFP proxy (codes_revision/AnalysesTools.py:343-356): -> t (ms), LFP (pA)."""
+    LFP = np.asarray(cortex.recorded.var("I_tot")) / units.pA
+    t_LFP = np.asarray(cortex.recorded.t("I_tot")) / units.ms
+    if population_agroupate == "mean":
+        LFP = np.mean(LFP, axis=0)
+    elif population_agroupate == "sum":
+        LFP = np.sum(LFP, axis=0)
+    return t_LFP, (-LFP if invert_Itot else LFP)
+
+
+def get_LFP_SPD(cortex, log=True, sigma=0):
+    """Periodogram of the LFP proxy, sampling rate from the monitor's time axis (:358-373)."""
+    t, LFP = get_LFP(cortex, invert_Itot=False)
+    return get_LFP_SPD_from_Itotarray(LFP, 1000 / (t[1] - t[0]), log, sigma)

@@ -87,6 +87,50 @@ def main():
     out["orig_isi_cv"] = np.asarray([np.std(np.diff(tr)) / np.mean(np.diff(tr)) for tr in stset])
     lag, corr = AE.Pearson_correlation_group(stset, 1000, 61000, 2, -30, 30)
     out["orig_corr_lags"], out["orig_corr"] = lag, corr
+    # ---- membrane-potential statistics with spike excision and the LFP spectrum (codes_revision/AnalysesTools.py:88-172, 343-373) on a
+    # stand-in `cortex` that exposes what those functions touch (recorded.V.V / .t, recorded.var / .t, neurons.N, network.membr_params)
+    class _Loc:
+        def __init__(self, vt):
+            self.vt = vt
+
+        def __getitem__(self, sel):
+            return types.SimpleNamespace(values=self.vt[sel["cell_index"]])
+
+    rngv = np.random.default_rng(77)
+    nV, nT = 6, 4000
+    V_T = np.array([-50.0, -48.0, -52.0, -45.0, -55.0, -50.0])
+    Vtr = np.zeros((nV, nT))
+    for i in range(nV):
+        v, trace = -70.0, []
+        for k in range(nT):
+            v += rngv.normal(0.02 * (i + 1), 0.4) + (0.25 * (v - V_T[i]) if v > V_T[i] else 0.0)
+            if v > -20.0:
+                trace.append(-20.0 + rngv.random())
+                v = -75.0 - 5 * rngv.random()                      # reset: |V| jumps by far more than 1 mV
+            else:
+                trace.append(v)
+        Vtr[i] = trace
+    Vtr[4] = -80.0 + 0.01 * rngv.normal(size=nT)                   # one cell that never spikes
+    tV = np.arange(nT) * 0.05
+    Itot = np.cumsum(rngv.normal(size=(3, nT)), axis=1) + 200.0
+    fake = types.SimpleNamespace(
+        recorded=types.SimpleNamespace(V=types.SimpleNamespace(V=Vtr * 1e-3, t=tV * 1e-3),
+                                       var=lambda name: Itot * 1e-12, t=lambda name: tV * 1e-3),
+        neurons=types.SimpleNamespace(N=nV),
+        network=types.SimpleNamespace(membr_params=types.SimpleNamespace(loc=_Loc(V_T))))
+    import brian2 as _b
+    _b.mV = 1e-3
+    AT.br2.mV, AT.br2.ms, AT.br2.pA = 1e-3, 1e-3, 1e-12
+    out["vstats_V"], out["vstats_t"], out["vstats_VT"], out["lfp_Itot"] = Vtr, tV, V_T, Itot
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["vstats_all"] = np.asarray(AT.get_V_stats(fake))
+        out["vstats_sel"] = np.asarray(AT.get_V_stats(fake, neuron_idcs=[1, 3, 4], tlim=(20.0, 150.0)))
+    t_lfp, lfp = AT.get_LFP(fake, invert_Itot=True, population_agroupate="sum")
+    out["lfp_t"], out["lfp_sum_inverted"] = t_lfp, lfp
+    fake1 = types.SimpleNamespace(recorded=types.SimpleNamespace(var=lambda name: Itot[0] * 1e-12, t=lambda name: tV * 1e-3))
+    fq, pw = AT.get_LFP_SPD(fake1, log=True, sigma=2)
+    out["lfp_spd_f"], out["lfp_spd_p"] = fq, pw
     np.savez_compressed(os.path.join(HERE, "analysis_golden.npz"), **out)
     print("wrote analysis_golden.npz:", sorted(out))
 

@@ -91,3 +91,26 @@ def test_analyses_have_no_cpu_fallback():
         an.lagged_counts(an.pack_bits(np.eye(3, 70, dtype=int)), 70, [0, 1])
     with pytest.raises(HhdError):
         AE.Zero_lag_Pearson_correlation_group([np.array([1.0, 5.0]), np.array([2.0])], 0.0, 10.0, 1.0)
+
+
+def test_V_stats_and_LFP_match_the_reference():
+    """codes_revision/AnalysesTools.py:88-172 (membrane-potential statistics with the spikes cut out) and :343-373 (LFP proxy and its
+    periodogram), against values the reference's own functions returned for the same traces (make_golden_analysis.py)."""
+    import types
+    from rescience_hass_hertag_durstewitz_2016_b200 import units
+    from rescience_hass_hertag_durstewitz_2016_b200.codes_revision import AnalysesTools as AT
+    from rescience_hass_hertag_durstewitz_2016_b200.codes_revision.BasicsSetup import Table
+    g = G
+    V, t, V_T, Itot = g["vstats_V"], g["vstats_t"], g["vstats_VT"], g["lfp_Itot"]
+    membr = Table(V_T[None, :], ["param", "cell_index"], [["V_T"], np.arange(len(V_T))])
+    cortex = types.SimpleNamespace(
+        recorded=types.SimpleNamespace(V=types.SimpleNamespace(V=V * units.mV, t=t * units.ms), var=lambda name: Itot * units.pA,
+                                       t=lambda name: t * units.ms),
+        neurons=types.SimpleNamespace(N=V.shape[0]), network=types.SimpleNamespace(membr_params=membr))
+    assert np.allclose(np.asarray(AT.get_V_stats(cortex)), g["vstats_all"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.asarray(AT.get_V_stats(cortex, neuron_idcs=[1, 3, 4], tlim=(20.0, 150.0))), g["vstats_sel"], rtol=1e-12, atol=1e-12)
+    tl, lfp = AT.get_LFP(cortex, invert_Itot=True, population_agroupate="sum")
+    assert np.allclose(tl, g["lfp_t"]) and np.allclose(lfp, g["lfp_sum_inverted"], rtol=1e-12)
+    one = types.SimpleNamespace(recorded=types.SimpleNamespace(var=lambda name: Itot[0] * units.pA, t=lambda name: t * units.ms))
+    f, p = AT.get_LFP_SPD(one, log=True, sigma=2)
+    assert np.allclose(f, g["lfp_spd_f"], rtol=1e-9) and np.allclose(p, g["lfp_spd_p"], rtol=1e-9, atol=1e-9)
