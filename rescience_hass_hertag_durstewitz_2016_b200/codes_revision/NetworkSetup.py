@@ -125,7 +125,7 @@ class Network(BaseClass):
                             syn_pairs=self.syn_pairs, STypPar=np.zeros(0) if self.STypPar is None else self.STypPar,
                             group_flat=np.asarray(flat), group_offs=offs, nstripes=len(self.group_distr),
                             seed=-1 if self.seed is None else self.seed, Ncells_prompt=b.struct.Ncells_prompt,
-                            scales=np.frombuffer(__import__("pickle").dumps(b.scales), dtype=np.uint8))
+                            scales=np.asarray(__import__("json").dumps(b.scales)))
 
     @classmethod
     def load(cls, path):
@@ -136,7 +136,9 @@ class Network(BaseClass):
         gd = [[list(map(int, flat[offs[s * ng + g]:offs[s * ng + g + 1]])) for g in range(ng)] for s in range(ns)]
         syn = {k: Labelled(d[f], SYN_FIELDS[k], "syn_index") for k, f in (("channel", "channel"), ("spiking", "spiking"), ("STSP_params", "stsp"), ("delay", "delay"))}
         seed = int(d["seed"])
-        scales = __import__("pickle").loads(d["scales"].tobytes()) if "scales" in d.files else None
+        scales = __import__("json").loads(str(d["scales"])) if "scales" in d.files else None
+        if scales:
+            scales = {k: [(sel, fac) for sel, fac in v] for k, v in scales.items()}
         basics = basics_setup(int(d["Ncells_prompt"]), ns, scales, disp=False) if "Ncells_prompt" in d.files else None
         iref = Table(d["iref"], "cell_index", [np.arange(len(d["iref"]))])
         return cls(Labelled(d["membr"], MEMB_PARAM_NAMES), iref, syn, d["syn_pairs"], gd, None if seed < 0 else seed, basics,

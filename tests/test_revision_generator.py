@@ -52,6 +52,15 @@ def test_what_the_revision_generator_does_differently_from_codes():
     assert gi["PC_L5"] == 7 and net.channel_constants()["mg_fac"] == 1.0
 
 
+def test_save_and_load_keep_the_scaled_tables(tmp_path):
+    net = network_setup(150, 1, scales_case(), 3)
+    net.save(str(tmp_path / "scaled"))
+    back = Network.load(str(tmp_path / "scaled"))
+    assert np.array_equal(back.basics.struct.conn.pCon.values, net.basics.struct.conn.pCon.values)
+    assert np.array_equal(back.basics.syn.spiking.params.gmax["mean"].values, net.basics.syn.spiking.params.gmax["mean"].values)
+    assert back.basics.scales == scales_case() and np.array_equal(back.syn_params["spiking"].values, net.syn_params["spiking"].values)
+
+
 def test_more_than_one_stripe_is_refused_like_the_reference_fails():
     with pytest.raises(NotImplementedError):
         network_setup(100, 3, None, 0)
