@@ -110,3 +110,33 @@ def test_depolarisation_block_window_is_evaluated_in_seconds():
     ni, ns = n.spikes()
     assert len(ci) > 600 and first_divergence(ci, cs, ni, ns) == len(ci) == len(ni)
     assert np.max(np.abs(c.read_state("V") - n.read_state("V"))) <= 1e-9
+
+
+def test_oracles_agree_on_the_revisions_model_variant():
+    """A network drawn by the revision's own generator (codes_revision/NetworkSetup.py port, bit-identical to the reference's)
+    with the revision's constants — NMDA Mg factor 1, last_spike = -1000 ms, intra-stripe delays 1 ms longer — on both oracles."""
+    from rescience_hass_hertag_durstewitz_2016_b200.codes_revision.NetworkSetup import network_setup
+    net = network_setup(150, 1, None, 3)
+    P = net.membr_params.values
+    n = P.shape[1]
+    NeuPar = np.zeros((12, n))
+    NeuPar[[0, 1, 2, 3, 4, 5, 7, 8, 9]] = P
+    NeuPar[10], NeuPar[11] = net.refractory_current.values, P[7]
+    sp = net.syn_params
+    SynPar = np.stack([sp["channel"].values[0] + 1, sp["STSP_params"].values[0], sp["STSP_params"].values[1], sp["STSP_params"].values[2],
+                       sp["spiking"].values[0], sp["delay"].values[0], sp["spiking"].values[1]])
+    STyp = load_golden("net_n200_s0")["STypPar"].copy()
+    assert net.channel_constants()["mg_fac"] == 1.0
+    STyp[5, 2] = 1.0
+    idc = np.full(n, 200.0)
+    idc[net.neuron_idcs(("PC", 0))] = 250.0
+    g = dict(NeuPar=NeuPar, V0=np.stack([P[2], np.zeros(n)]), STypPar=STyp, SynPar=SynPar, source_arr=net.syn_pairs[1], target_arr=net.syn_pairs[0])
+    c, m = both(g, "rk4", idc=idc, last_spike0_ms=-1000.0)
+    for e in (c, m):
+        e.run(6000)
+    ci, cs = c.spikes()
+    ni, ns = m.spikes()
+    assert len(ci) > 200 and first_divergence(ci, cs, ni, ns) == len(ci) == len(ni)
+    for v in STATE:
+        assert np.max(np.abs(c.read_state(v) - m.read_state(v))) <= 1e-9, v
+    assert c.counters()["syn_events"] == m.counters()["syn_events"] > 5000
