@@ -202,8 +202,8 @@ def find_neigh_recur(X):
     n = X.shape[0]
     Xl = X.copy()
     Xl[np.arange(n), np.arange(n)] = 0
-    S = ((Xl + Xl.T) > 0).astype(np.int64)
-    neigh = (S @ S).astype(np.float64)             # pairs (a, b) sharing a neighbour i, counted over i
+    S = ((Xl + Xl.T) > 0).astype(np.float64)
+    neigh = S @ S                                  # pairs (a, b) sharing a neighbour i, counted over i (small integers: exact in fp64, and BLAS)
     neigh[np.arange(n), np.arange(n)] = -1
     return neigh
 
