@@ -18,11 +18,13 @@
  * PARITY STATUS: step-level parity with Brian 2 is UNPINNED — the reference ships no golden trajectories and Brian 2
  * cannot run in this environment.  What pins this oracle: (i) analytic known answers (closed-form simpAdEx f-I curve
  * of codes/NetworkSetup.py:444-553, hand-computed STP sequences, delay bookkeeping) in tests/test_oracle_*.py,
- * (ii) the reference's statistical targets (content.tex:239,318; codes/Original_spiketime.txt) in the long-run tests,
+ * (ii) the reference's statistical targets (content.tex:239,318,334-335,344; codes/Original_spiketime.txt) over 7 network
+ * realisations in the long-run tests, and a second, independent restatement (oracle/numpy_oracle.py, tests/test_numpy_oracle.py),
  * (iii) the network inputs themselves, which are bit-exact outputs of the reference's own NetworkSetup (tests/golden).
  *
  * Deliberately written the way Brian works (per-synapse event queue, values read at delivery time, one pass per
- * schedule slot) and NOT the way the CUDA engine works (delay-sorted CSR rows scanned per active spike), so that
+ * schedule slot) and NOT the way the CUDA engine works (amplitudes added to a circular per-delay conductance buffer at spike
+ * time, corrected when a neuron spikes again while an older spike is in flight), so that
  * agreement between the two is evidence.  Exports the ABI of include/hhd.h under the prefix `hhdo_`.
  */
 #include <math.h>

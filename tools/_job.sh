@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 100 python bench.py --steps 2 --warmup 3 --window 500 --no-cpu-baseline --no-extras --distinct 50 > gpurun_out/r2j_bench.json 2> gpurun_out/r2j.err || tail -5 gpurun_out/r2j.err
-python tools/benchline.py gpurun_out/r2j_bench.json
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 60 python bench.py --steps 1 --warmup 3 --window 300 --no-cpu-baseline --no-extras --distinct 25 > gpurun_out/r2k_bench.json 2> gpurun_out/r2k.err || tail -5 gpurun_out/r2k.err
+python tools/benchline.py gpurun_out/r2k_bench.json
